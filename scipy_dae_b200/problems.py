@@ -1,0 +1,224 @@
+"""Problem zoo: host-side (NumPy) statements of the residuals F(t, y, y', p) = 0
+that are compiled into the CUDA library as device functors.
+
+Every entry here has a twin with the same name and the same arithmetic in
+``scipy_dae_b200/csrc/problems.cuh`` (device functor) and in ``oracle/problems.c``
+(CPU oracle).  The NumPy versions are used
+
+* by ``oracle/gen_golden.py`` to drive the *unmodified* reference ``solve_dae``
+  (they are plain ``fun(t, y, yp, *params)`` callables, the reference's residual
+  convention, base.py:44-45 / dae.py:365-383),
+* by host-side consistency checks (``F(t0, y0, yp0) == 0``) and tests.
+
+They are never on the product hot path: the hot path evaluates the device functor.
+
+Problem definitions follow SURVEY.md App. D:
+  robertson  : README.md:37-47, tests/test_integration_robertson.py:73-87 (parameterised k1,k2,k3)
+  akzo_nobel : examples/daes/akzo_nobel.py:18-50 (parameterised rate constants)
+  transamp   : two-transistor amplifier, IVP test set "transamp" (n=8), SURVEY.md App. D.5
+  andrews    : examples/daes/andrews.py:20-225 (n=26 stabilised index-1 form)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Sequence
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class Problem:
+    """A residual known to the CUDA library under ``name``.
+
+    ``residual(t, y, yp, *params)`` is the NumPy twin of the device functor.
+    ``initial(params)`` returns consistent ``(y0, yp0)`` for one parameter vector.
+    """
+    name: str
+    n: int
+    n_params: int
+    residual: Callable
+    default_params: tuple
+    initial: Callable
+    t_span: tuple
+    doc: str = ""
+    param_names: tuple = field(default_factory=tuple)
+
+    def __call__(self, t, y, yp, *params):
+        if not params:
+            params = self.default_params
+        return self.residual(t, y, yp, *params)
+
+
+# --------------------------------------------------------------------------- #
+# Robertson (n = 3, index 1)
+# --------------------------------------------------------------------------- #
+def robertson_residual(t, y, yp, k1, k2, k3):
+    y1, y2, y3 = y
+    y1p, y2p, y3p = yp
+    return np.array([
+        y1p - (-k1 * y1 + k2 * y2 * y3),
+        y2p - (k1 * y1 - k2 * y2 * y3 - k3 * y2 * y2),
+        y1 + y2 + y3 - 1,
+    ])
+
+
+def robertson_initial(params):
+    k1 = params[0]
+    return np.array([1.0, 0.0, 0.0]), np.array([-k1, k1, 0.0])
+
+
+# --------------------------------------------------------------------------- #
+# Akzo Nobel chemical reaction (n = 6, index 1)
+# --------------------------------------------------------------------------- #
+AKZO_PO2 = 0.9
+AKZO_HEN = 737.0
+
+
+def akzo_rhs(y, k1, k2, k3, k4, kbig, kla, ks):
+    sq = np.sqrt(y[1])
+    r1 = k1 * (y[0] ** 4) * sq
+    r2 = k2 * y[2] * y[3]
+    r3 = k2 / kbig * y[0] * y[4]
+    r4 = k3 * y[0] * (y[3] ** 2)
+    r5 = k4 * (y[5] ** 2) * sq
+    fin = kla * (AKZO_PO2 / AKZO_HEN - y[1])
+    return np.array([
+        -2.0 * r1 + r2 - r3 - r4,
+        -0.5 * r1 - r4 - 0.5 * r5 + fin,
+        r1 - r2 + r3,
+        -r2 + r3 - 2.0 * r4,
+        r2 - r3 + r5,
+        ks * y[0] * y[3] - y[5],
+    ])
+
+
+def akzo_residual(t, y, yp, k1, k2, k3, k4, kbig, kla, ks):
+    with np.errstate(invalid="ignore"):
+        r = akzo_rhs(y, k1, k2, k3, k4, kbig, kla, ks)
+    out = np.empty(6)
+    out[:5] = yp[:5] - r[:5]
+    out[5] = -r[5]
+    return out
+
+
+def akzo_initial(params):
+    ks = params[6]
+    y0 = np.array([0.444, 0.00123, 0.0, 0.007, 0.0, ks * 0.444 * 0.007])
+    yp0 = akzo_rhs(y0, *params)
+    yp0[5] = 0.0 * yp0[5]  # algebraic row: F does not depend on yp[5]
+    return y0, yp0
+
+
+# --------------------------------------------------------------------------- #
+# Two-transistor amplifier "transamp" (n = 8, index 1)
+# --------------------------------------------------------------------------- #
+TA_UF = 0.026
+TA_ALPHA = 0.99
+TA_R = 9000.0
+
+
+def transamp_residual(t, y, yp, Ub, R0, beta):
+    C1, C2, C3, C4, C5 = 1e-6, 2e-6, 3e-6, 4e-6, 5e-6
+    R = TA_R
+    Ue = 0.1 * np.sin(200.0 * np.pi * t)
+    g23 = beta * (np.exp((y[1] - y[2]) / TA_UF) - 1.0)
+    g56 = beta * (np.exp((y[4] - y[5]) / TA_UF) - 1.0)
+    f = np.array([
+        -Ue / R0 + y[0] / R0,
+        -Ub / R + y[1] * (2.0 / R) - (TA_ALPHA - 1.0) * g23,
+        -g23 + y[2] / R,
+        -Ub / R + y[3] / R + TA_ALPHA * g23,
+        -Ub / R + y[4] * (2.0 / R) - (TA_ALPHA - 1.0) * g56,
+        -g56 + y[5] / R,
+        -Ub / R + y[6] / R + TA_ALPHA * g56,
+        y[7] / R,
+    ])
+    My = np.array([
+        -C1 * yp[0] + C1 * yp[1],
+        C1 * yp[0] - C1 * yp[1],
+        -C2 * yp[2],
+        -C3 * yp[3] + C3 * yp[4],
+        C3 * yp[3] - C3 * yp[4],
+        -C4 * yp[5],
+        -C5 * yp[6] + C5 * yp[7],
+        C5 * yp[6] - C5 * yp[7],
+    ])
+    return My - f
+
+
+def transamp_initial(params):
+    Ub = params[0]
+    R = TA_R
+    C2, C4 = 2e-6, 4e-6
+    y0 = np.array([0.0, Ub / 2.0, Ub / 2.0, Ub, Ub / 2.0, Ub / 2.0, Ub, 0.0])
+    yp0 = np.array([
+        51.338775, 51.338775, -Ub / (2.0 * C2 * R),
+        -24.9757667, -24.9757667, -Ub / (2.0 * C4 * R),
+        -10.00564453, -10.00564453,
+    ])
+    return y0, yp0
+
+
+# --------------------------------------------------------------------------- #
+# registry
+# --------------------------------------------------------------------------- #
+PROBLEMS: dict[str, Problem] = {}
+
+
+def _register(p: Problem):
+    PROBLEMS[p.name] = p
+    return p
+
+
+ROBERTSON = _register(Problem(
+    name="robertson", n=3, n_params=3, residual=robertson_residual,
+    default_params=(0.04, 1e4, 3e7), initial=robertson_initial, t_span=(0.0, 1e7),
+    param_names=("k1", "k2", "k3"),
+    doc="Robertson chemical kinetics as an index-1 DAE"))
+
+AKZO_NOBEL = _register(Problem(
+    name="akzo_nobel", n=6, n_params=7, residual=akzo_residual,
+    default_params=(18.7, 0.58, 0.09, 0.42, 34.4, 3.3, 115.83),
+    initial=akzo_initial, t_span=(0.0, 180.0),
+    param_names=("k1", "k2", "k3", "k4", "kbig", "kla", "ks"),
+    doc="Akzo Nobel chemical reaction, index 1"))
+
+TRANSAMP = _register(Problem(
+    name="transamp", n=8, n_params=3, residual=transamp_residual,
+    default_params=(6.0, 1000.0, 1e-6), initial=transamp_initial, t_span=(0.0, 0.2),
+    param_names=("Ub", "R0", "beta"),
+    doc="Two-transistor amplifier (IVP test set 'transamp'), index 1"))
+
+
+def get_problem(name_or_problem) -> Problem:
+    if isinstance(name_or_problem, Problem):
+        return name_or_problem
+    try:
+        return PROBLEMS[name_or_problem]
+    except KeyError:
+        raise ValueError(
+            f"unknown problem {name_or_problem!r}; registered: {sorted(PROBLEMS)}") from None
+
+
+def perturbed_params(problem, N: int, sigma: float, seed: int = 0) -> np.ndarray:
+    """Ensemble parameters ``p_i = p_nominal * exp(sigma * u_i)``, ``u ~ U(-1, 1)``.
+
+    Returns an ``(N, n_params)`` array (AoS on the host; the library wants SoA
+    ``[n_params][N]`` and the batched entry point transposes).  SURVEY.md §8(d) C2:
+    ``numpy.random.default_rng(seed)``, sigma = 0.1 headline, 0.5 divergence stress.
+    """
+    problem = get_problem(problem)
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-1.0, 1.0, size=(N, problem.n_params))
+    return np.asarray(problem.default_params)[None, :] * np.exp(sigma * u)
+
+
+def initial_conditions(problem, params: np.ndarray):
+    """Consistent ``(y0[N,n], yp0[N,n])`` for an ``(N, n_params)`` parameter array."""
+    problem = get_problem(problem)
+    params = np.atleast_2d(params)
+    y0 = np.empty((params.shape[0], problem.n))
+    yp0 = np.empty_like(y0)
+    for i, p in enumerate(params):
+        y0[i], yp0[i] = problem.initial(p)
+    return y0, yp0
