@@ -1,0 +1,167 @@
+"""ctypes binding of the CPU oracle (oracle/libdae_oracle.so) — TEST INFRASTRUCTURE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package
+``scipy_dae_b200`` never does.
+
+``solve_ensemble`` integrates N independent instances with the plain-C restatement of the
+reference's RadauDAE / BDFDAE step loops (dae_oracle.c) and returns the same fields as the
+product's batched entry point, so the parity tests can compare them one to one.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from scipy_dae_b200.constants import CRadauTables, radau_tables_c, NDF_STRATEGIES  # noqa: E402
+
+LIB_PATH = os.path.join(HERE, "libdae_oracle.so")
+
+COUNTER_NAMES = ("nfev", "njev", "nlu", "nsolve", "n_accepted", "n_err_rejected",
+                 "n_newton_fail", "n_newton_iter")
+
+
+class RadauOpts(ctypes.Structure):
+    _fields_ = [("rtol", ctypes.c_double), ("max_step", ctypes.c_double),
+                ("first_step", ctypes.c_double), ("continuous_error_weight", ctypes.c_double),
+                ("jac_recompute_rate", ctypes.c_double),
+                ("deadband_lo", ctypes.c_double), ("deadband_hi", ctypes.c_double),
+                ("newton_max_iter", ctypes.c_int), ("newton_iter_embedded", ctypes.c_int),
+                ("max_steps", ctypes.c_int64)]
+
+
+class BdfOpts(ctypes.Structure):
+    _fields_ = [("rtol", ctypes.c_double), ("max_step", ctypes.c_double),
+                ("first_step", ctypes.c_double), ("max_order", ctypes.c_int),
+                ("ndf_strategy", ctypes.c_int), ("max_steps", ctypes.c_int64)]
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(HERE, f) for f in ("dae_oracle.c", "problems.c", "dae_oracle.h")]
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    subprocess.run(["make", "-C", HERE, "-B", "libdae_oracle.so"], check=True,
+                   stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(LIB_PATH)
+        L.orc_problem_lookup.restype = ctypes.c_int
+        L.orc_problem_lookup.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int),
+                                         ctypes.POINTER(ctypes.c_int)]
+        L.orc_solve_ensemble.restype = ctypes.c_int
+        L.orc_problem_eval.restype = ctypes.c_int
+        L.orc_select_initial_step.restype = ctypes.c_double
+        _lib = L
+    return _lib
+
+
+def _p(a, ctype=ctypes.c_double):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def problem_id(name: str):
+    n, npar = ctypes.c_int(), ctypes.c_int()
+    pid = lib().orc_problem_lookup(name.encode(), ctypes.byref(n), ctypes.byref(npar))
+    if pid < 0:
+        raise ValueError(f"oracle does not know problem {name!r}")
+    return pid, n.value, npar.value
+
+
+def residual(name, t, y, yp, params):
+    pid, n, _ = problem_id(name)
+    y = np.ascontiguousarray(y, dtype=float)
+    yp = np.ascontiguousarray(yp, dtype=float)
+    p = np.ascontiguousarray(params, dtype=float)
+    out = np.empty(n)
+    lib().orc_problem_eval(ctypes.c_int(pid), ctypes.c_double(t), _p(y), _p(yp), _p(p), _p(out))
+    return out
+
+
+def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, atol=1e-6,
+                   t_eval=None, nthreads=1, max_steps=0, **options):
+    """N instances through the C oracle.  Arrays are AoS on the host: params[N,p], y0[N,n]."""
+    pid, n, npar = problem_id(problem)
+    params = np.ascontiguousarray(np.atleast_2d(params), dtype=float)
+    y0 = np.ascontiguousarray(np.atleast_2d(y0), dtype=float)
+    yp0 = np.ascontiguousarray(np.atleast_2d(yp0), dtype=float)
+    N = params.shape[0]
+    assert params.shape == (N, npar) and y0.shape == (N, n) and yp0.shape == (N, n)
+    atol_v = np.ascontiguousarray(np.broadcast_to(np.asarray(atol, dtype=float), (n,)))
+    t0, t_bound = map(float, t_span)
+
+    ropts = bopts = tb = None
+    if method == "Radau":
+        s = int(options.pop("stages", 3))
+        tb = radau_tables_c(s)
+        db = options.pop("controller_deadband", (1.0, 1.2))
+        nmi = options.pop("newton_max_iter", None)
+        ropts = RadauOpts(rtol=rtol, max_step=float(options.pop("max_step", np.inf)),
+                          first_step=float(options.pop("first_step", None) or 0.0),
+                          continuous_error_weight=float(options.pop("continuous_error_weight", 0.0)),
+                          jac_recompute_rate=float(options.pop("jac_recompute_rate", 1e-3)),
+                          deadband_lo=db[0], deadband_hi=db[1],
+                          newton_max_iter=int(nmi or 0),
+                          newton_iter_embedded=int(options.pop("newton_iter_embedded", 1)),
+                          max_steps=max_steps)
+        mcode = 0
+    elif method == "BDF":
+        bopts = BdfOpts(rtol=rtol, max_step=float(options.pop("max_step", np.inf)),
+                        first_step=float(options.pop("first_step", None) or 0.0),
+                        max_order=int(options.pop("max_order", 5)),
+                        ndf_strategy=NDF_STRATEGIES[options.pop("NDF_strategy", "stability")],
+                        max_steps=max_steps)
+        mcode = 1
+    else:
+        raise ValueError(method)
+    if options:
+        raise TypeError(f"unknown options {sorted(options)}")
+
+    m = 0
+    te = ye = ype = None
+    if t_eval is not None:
+        te = np.ascontiguousarray(t_eval, dtype=float)
+        m = te.shape[0]
+        ye = np.full((N, m, n), np.nan)
+        ype = np.full((N, m, n), np.nan)
+    nev = np.zeros(N, dtype=np.int64)
+    y_final = np.empty((N, n)); yp_final = np.empty((N, n)); t_final = np.empty(N)
+    status = np.zeros(N, dtype=np.int32)
+    counters = np.zeros((N, 8), dtype=np.int64)
+
+    rc = lib().orc_solve_ensemble(
+        ctypes.c_int(pid), ctypes.c_int(mcode), ctypes.c_int64(N),
+        _p(params), _p(y0), _p(yp0), ctypes.c_double(t0), ctypes.c_double(t_bound), _p(atol_v),
+        ctypes.byref(ropts) if ropts is not None else None,
+        ctypes.byref(tb) if tb is not None else None,
+        ctypes.byref(bopts) if bopts is not None else None,
+        _p(te), ctypes.c_int64(m), _p(ye), _p(ype), _p(nev, ctypes.c_int64),
+        _p(y_final), _p(yp_final), _p(t_final), _p(status, ctypes.c_int32),
+        _p(counters, ctypes.c_int64), ctypes.c_int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"orc_solve_ensemble returned {rc}")
+    out = dict(status=status, t_final=t_final, y_final=y_final, yp_final=yp_final,
+               n_eval_valid=nev)
+    for i, name in enumerate(COUNTER_NAMES):
+        out[name] = counters[:, i].copy()
+    if t_eval is not None:
+        out["y_eval"] = ye      # [N, m, n]
+        out["yp_eval"] = ype
+    return out

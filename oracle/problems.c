@@ -1,0 +1,218 @@
+/*
+ * problems.c — residuals of the problem zoo for the CPU ORACLE (TEST INFRASTRUCTURE).
+ *
+ * Twins of scipy_dae_b200/problems.py (NumPy, drives the unmodified reference when the
+ * goldens are minted) and scipy_dae_b200/csrc/problems.cuh (device functors).  Problem
+ * definitions: SURVEY.md App. D (reference: README.md:37-47, examples/daes/akzo_nobel.py:18-50,
+ * examples/daes/andrews.py:20-225; "transamp" is the IVP-test-set two-transistor amplifier).
+ */
+#include "dae_oracle.h"
+
+#include <math.h>
+#include <string.h>
+
+/* Robertson, p = (k1, k2, k3) */
+static void robertson(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    (void)t;
+    double k1 = p[0], k2 = p[1], k3 = p[2];
+    out[0] = yp[0] - (-k1 * y[0] + k2 * y[1] * y[2]);
+    out[1] = yp[1] - (k1 * y[0] - k2 * y[1] * y[2] - k3 * y[1] * y[1]);
+    out[2] = y[0] + y[1] + y[2] - 1;
+}
+
+/* Akzo Nobel, p = (k1, k2, k3, k4, kbig, kla, ks) */
+static void akzo_nobel(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    (void)t;
+    const double po2 = 0.9, hen = 737.0;
+    double k1 = p[0], k2 = p[1], k3 = p[2], k4 = p[3], kbig = p[4], kla = p[5], ks = p[6];
+    double sq = sqrt(y[1]);
+    double y0sq = y[0] * y[0];
+    double r1 = k1 * (y0sq * y0sq) * sq;
+    double r2 = k2 * y[2] * y[3];
+    double r3 = k2 / kbig * y[0] * y[4];
+    double r4 = k3 * y[0] * (y[3] * y[3]);
+    double r5 = k4 * (y[5] * y[5]) * sq;
+    double fin = kla * (po2 / hen - y[1]);
+    out[0] = yp[0] - (-2.0 * r1 + r2 - r3 - r4);
+    out[1] = yp[1] - (-0.5 * r1 - r4 - 0.5 * r5 + fin);
+    out[2] = yp[2] - (r1 - r2 + r3);
+    out[3] = yp[3] - (-r2 + r3 - 2.0 * r4);
+    out[4] = yp[4] - (r2 - r3 + r5);
+    out[5] = -(ks * y[0] * y[3] - y[5]);
+}
+
+/* two-transistor amplifier, p = (Ub, R0, beta) */
+static void transamp(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    const double UF = 0.026, ALPHA = 0.99, R = 9000.0;
+    const double C1 = 1e-6, C2 = 2e-6, C3 = 3e-6, C4 = 4e-6, C5 = 5e-6;
+    double Ub = p[0], R0 = p[1], beta = p[2];
+    double Ue = 0.1 * sin(200.0 * M_PI * t);
+    double g23 = beta * (exp((y[1] - y[2]) / UF) - 1.0);
+    double g56 = beta * (exp((y[4] - y[5]) / UF) - 1.0);
+    double f0 = -Ue / R0 + y[0] / R0;
+    double f1 = -Ub / R + y[1] * (2.0 / R) - (ALPHA - 1.0) * g23;
+    double f2 = -g23 + y[2] / R;
+    double f3 = -Ub / R + y[3] / R + ALPHA * g23;
+    double f4 = -Ub / R + y[4] * (2.0 / R) - (ALPHA - 1.0) * g56;
+    double f5 = -g56 + y[5] / R;
+    double f6 = -Ub / R + y[6] / R + ALPHA * g56;
+    double f7 = y[7] / R;
+    out[0] = (-C1 * yp[0] + C1 * yp[1]) - f0;
+    out[1] = (C1 * yp[0] - C1 * yp[1]) - f1;
+    out[2] = (-C2 * yp[2]) - f2;
+    out[3] = (-C3 * yp[3] + C3 * yp[4]) - f3;
+    out[4] = (C3 * yp[3] - C3 * yp[4]) - f4;
+    out[5] = (-C4 * yp[5]) - f5;
+    out[6] = (-C5 * yp[6] + C5 * yp[7]) - f6;
+    out[7] = (C5 * yp[6] - C5 * yp[7]) - f7;
+}
+
+/* Andrews' squeezer, stabilised index-1 form n = 26 (examples/daes/andrews.py:79-225),
+ * p = (mom, c0): driving torque and spring constant. y = (q[7], u[7], la[6], mu[6]),
+ * yp = (q'[7], u'[7], lambda[6], mu_mult[6]). */
+static void andrews(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    (void)t;
+    const double m1 = 0.04325, m2 = 0.00365, m3 = 0.02373, m4 = 0.00706, m5 = 0.07050,
+                 m6 = 0.00706, m7 = 0.05498;
+    const double I1 = 2.194e-6, I2 = 4.410e-7, I3 = 5.255e-6, I4 = 5.667e-7, I5 = 1.169e-5,
+                 I6 = 5.667e-7, I7 = 1.912e-5;
+    const double xa = -0.06934, ya = -0.00227, xb = -0.03635, yb = 0.03273, xc = 0.014, yc = 0.072;
+    const double d = 0.028, da = 0.0115, e = 0.02, ea = 0.01421, zf = 0.02, fa = 0.01421;
+    const double rr = 0.007, ra = 0.00092, ss = 0.035, sa = 0.01874, sb = 0.01043, sc = 0.018;
+    const double sd = 0.02, zt = 0.04, ta = 0.02308, tb = 0.00916, u = 0.04, ua = 0.01228,
+                 ub = 0.00449, l0 = 0.07785;
+    double mom = p[0], c0 = p[1];
+    const double *q = y, *v = y + 7;
+    const double *qd = yp, *vd = yp + 7, *la = yp + 14, *mu = yp + 20;
+
+    double sin_be = sin(q[0]), cos_be = cos(q[0]);
+    double sin_Th = sin(q[1]), cos_Th = cos(q[1]);
+    double sin_ga = sin(q[2]), cos_ga = cos(q[2]);
+    double sin_Phi = sin(q[3]), cos_Phi = cos(q[3]);
+    double sin_de = sin(q[4]), cos_de = cos(q[4]);
+    double sin_Om = sin(q[5]), cos_Om = cos(q[5]);
+    double sin_ep = sin(q[6]), cos_ep = cos(q[6]);
+    double sin_be_Th = sin(q[0] + q[1]), cos_be_Th = cos(q[0] + q[1]);
+    double sin_Ph_de = sin(q[3] + q[4]), cos_Ph_de = cos(q[3] + q[4]);
+    double sin_Om_ep = sin(q[5] + q[6]), cos_Om_ep = cos(q[5] + q[6]);
+
+    /* mass matrix (symmetric, block tridiagonal) */
+    double M00 = m1 * ra * ra + m2 * (rr * rr - 2 * da * rr * cos_Th + da * da) + I1 + I2;
+    double M01 = m2 * (da * da - da * rr * cos_Th) + I2;
+    double M11 = m2 * da * da + I2;
+    double M22 = m3 * (sa * sa + sb * sb) + I3;
+    double M33 = m4 * (e - ea) * (e - ea) + I4;
+    double M34 = m4 * ((e - ea) * (e - ea) + zt * (e - ea) * sin_Phi) + I4;
+    double M44 = m4 * (zt * zt + 2 * zt * (e - ea) * sin_Phi + (e - ea) * (e - ea)) + m5 * (ta * ta + tb * tb) + I4 + I5;
+    double M55 = m6 * (zf - fa) * (zf - fa) + I6;
+    double M56 = m6 * ((zf - fa) * (zf - fa) - u * (zf - fa) * sin_Om) + I6;
+    double M66 = m6 * ((zf - fa) * (zf - fa) - 2 * u * (zf - fa) * sin_Om + u * u) + m7 * (ua * ua + ub * ub) + I6 + I7;
+
+    /* forces */
+    double xd = sd * cos_ga + sc * sin_ga + xb;
+    double yd = sd * sin_ga - sc * cos_ga + yb;
+    double L = sqrt((xd - xc) * (xd - xc) + (yd - yc) * (yd - yc));
+    double Fs = -c0 * (L - l0) / L;
+    double Fx = Fs * (xd - xc), Fy = Fs * (yd - yc);
+    double h[7];
+    h[0] = mom - m2 * da * rr * v[1] * (v[1] + 2 * v[0]) * sin_Th;
+    h[1] = m2 * da * rr * v[0] * v[0] * sin_Th;
+    h[2] = Fx * (sc * cos_ga - sd * sin_ga) + Fy * (sd * cos_ga + sc * sin_ga);
+    h[3] = m4 * zt * (e - ea) * v[4] * v[4] * cos_Phi;
+    h[4] = -m4 * zt * (e - ea) * v[3] * (v[3] + 2 * v[4]) * cos_Phi;
+    h[5] = -m6 * u * (zf - fa) * v[6] * v[6] * cos_Om;
+    h[6] = m6 * u * (zf - fa) * v[5] * (v[5] + 2 * v[6]) * cos_Om;
+
+    /* constraints and their Jacobian G[6][7] */
+    double g[6];
+    g[0] = rr * cos_be - d * cos_be_Th - ss * sin_ga - xb;
+    g[1] = rr * sin_be - d * sin_be_Th + ss * cos_ga - yb;
+    g[2] = rr * cos_be - d * cos_be_Th - e * sin_Ph_de - zt * cos_de - xa;
+    g[3] = rr * sin_be - d * sin_be_Th + e * cos_Ph_de - zt * sin_de - ya;
+    g[4] = rr * cos_be - d * cos_be_Th - zf * cos_Om_ep - u * sin_ep - xa;
+    g[5] = rr * sin_be - d * sin_be_Th - zf * sin_Om_ep + u * cos_ep - ya;
+
+    double G[6][7];
+    memset(G, 0, sizeof(G));
+    double a0 = -rr * sin_be + d * sin_be_Th, a1 = d * sin_be_Th;
+    double b0 = rr * cos_be - d * cos_be_Th, b1 = -d * cos_be_Th;
+    G[0][0] = a0; G[0][1] = a1; G[0][2] = -ss * cos_ga;
+    G[1][0] = b0; G[1][1] = b1; G[1][2] = -ss * sin_ga;
+    G[2][0] = a0; G[2][1] = a1; G[2][3] = -e * cos_Ph_de; G[2][4] = -e * cos_Ph_de + zt * sin_de;
+    G[3][0] = b0; G[3][1] = b1; G[3][3] = -e * sin_Ph_de; G[3][4] = -e * sin_Ph_de - zt * cos_de;
+    G[4][0] = a0; G[4][1] = a1; G[4][5] = zf * sin_Om_ep; G[4][6] = zf * sin_Om_ep - u * cos_ep;
+    G[5][0] = b0; G[5][1] = b1; G[5][5] = -zf * cos_Om_ep; G[5][6] = -zf * cos_Om_ep - u * sin_ep;
+
+    double Mvd[7];
+    Mvd[0] = M00 * vd[0] + M01 * vd[1];
+    Mvd[1] = M01 * vd[0] + M11 * vd[1];
+    Mvd[2] = M22 * vd[2];
+    Mvd[3] = M33 * vd[3] + M34 * vd[4];
+    Mvd[4] = M34 * vd[3] + M44 * vd[4];
+    Mvd[5] = M55 * vd[5] + M56 * vd[6];
+    Mvd[6] = M56 * vd[5] + M66 * vd[6];
+
+    for (int i = 0; i < 7; ++i) {
+        double gt_mu = 0.0, gt_la = 0.0;
+        for (int k = 0; k < 6; ++k) { gt_mu += G[k][i] * mu[k]; gt_la += G[k][i] * la[k]; }
+        out[i] = qd[i] - v[i] + gt_mu;
+        out[7 + i] = Mvd[i] - h[i] - gt_la;
+    }
+    for (int k = 0; k < 6; ++k) {
+        double gu = 0.0;
+        for (int i = 0; i < 7; ++i) gu += G[k][i] * v[i];
+        out[14 + k] = gu;
+        out[20 + k] = g[k];
+    }
+}
+
+static const struct {
+    const char *name;
+    int n, n_params;
+    orc_residual_fn fn;
+} REGISTRY[] = {
+    {"robertson", 3, 3, robertson},
+    {"akzo_nobel", 6, 7, akzo_nobel},
+    {"transamp", 8, 3, transamp},
+    {"andrews", 26, 2, andrews},
+};
+#define N_PROBLEMS ((int)(sizeof(REGISTRY) / sizeof(REGISTRY[0])))
+
+int orc_problem_lookup(const char *name, int *n, int *n_params)
+{
+    for (int i = 0; i < N_PROBLEMS; ++i)
+        if (strcmp(REGISTRY[i].name, name) == 0) {
+            if (n) *n = REGISTRY[i].n;
+            if (n_params) *n_params = REGISTRY[i].n_params;
+            return i;
+        }
+    return -1;
+}
+
+int orc_problem_dims(int problem_id, int *n, int *n_params)
+{
+    if (problem_id < 0 || problem_id >= N_PROBLEMS) return -1;
+    if (n) *n = REGISTRY[problem_id].n;
+    if (n_params) *n_params = REGISTRY[problem_id].n_params;
+    return 0;
+}
+
+orc_residual_fn orc_problem_residual(int problem_id)
+{
+    if (problem_id < 0 || problem_id >= N_PROBLEMS) return 0;
+    return REGISTRY[problem_id].fn;
+}
+
+/* residual evaluation exported for tests (checks the C twin against problems.py) */
+int orc_problem_eval(int problem_id, double t, const double *y, const double *yp,
+                     const double *p, double *out)
+{
+    orc_residual_fn fn = orc_problem_residual(problem_id);
+    if (!fn) return -1;
+    fn(t, y, yp, p, out);
+    return 0;
+}
