@@ -1,0 +1,187 @@
+/*
+ * b200dae.h — C-ABI of libb200dae.so, the B200 (sm_100a) ensemble DAE/IDE integrator.
+ *
+ * The reference (JonasBreuling/scipy_dae v0.1.0) is pure Python and has no FFI; its plug-in
+ * boundary for the hot path is the DaeSolver protocol consumed by solve_dae
+ * (scipy_dae/integrate/_dae/dae.py:359-361,405-408,446-518; base.py:50-416).  This header is
+ * what a binding of that path binds instead.  Each entry point names the reference interface
+ * it replaces.  INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Plain C types only.  All bulk arrays are DEVICE pointers owned by the caller (the Python
+ *     host side passes torch.Tensor.data_ptr()).  Small descriptors (options, tables, atol[n])
+ *     are HOST pointers, copied into the launch.  The library allocates nothing persistent.
+ *   - Layout is structure-of-arrays with the instance index innermost: component j of instance
+ *     i lives at  a[j * ld + i]  (ld >= N, the leading dimension in instances), so that the 32
+ *     lanes of a warp (32 neighbouring instances) load and store 256 contiguous bytes.
+ *   - Work is queued on `stream` (a cudaStream_t passed as void*, NULL = legacy default
+ *     stream); the call returns without synchronising.
+ *   - Return value: 0 on success, otherwise a negative B200DAE_E* code; the message is
+ *     available from b200dae_last_error().  Per-instance solver outcomes are NOT errors: they
+ *     are written to status[] (the reference likewise reports them as DaeResult.status,
+ *     dae.py:451-453, and not as exceptions).
+ */
+#ifndef B200DAE_H
+#define B200DAE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DAE_VERSION 100
+#define B200DAE_MAX_STAGES 7
+#define B200DAE_MAX_ORDER 6
+#define B200DAE_MAX_N 32
+
+/* library-level error codes (return values) */
+#define B200DAE_OK 0
+#define B200DAE_EINVAL (-1)      /* bad argument (message says which) */
+#define B200DAE_ENOPROBLEM (-2)  /* unknown problem id / (problem, stages) not compiled */
+#define B200DAE_ECUDA (-3)       /* CUDA runtime error at launch */
+
+/* per-instance status[] values */
+#define B200DAE_ST_FINISHED 0         /* reached t_bound           (solve_dae status 0)  */
+#define B200DAE_ST_TOO_SMALL_STEP (-1)/* DaeSolver.TOO_SMALL_STEP  (base.py:158; solve_dae status -1) */
+#define B200DAE_ST_NONFINITE (-2)     /* non-finite iteration matrix / rhs: the reference raises
+                                         ValueError from scipy lu_factor/lu_solve(check_finite=True),
+                                         base.py:234,238 */
+#define B200DAE_ST_MAX_STEPS (-3)     /* opts.max_steps accepted steps done, t_bound not reached
+                                         (resumable; no reference equivalent) */
+#define B200DAE_ST_RUNNING 1          /* only ever seen in a state block between resumed launches */
+
+/* rows of counters[8][ld] (int32).  nfev/njev/nlu are DaeSolver.nfev/njev/nlu (base.py:180-182),
+ * nsolve is DaeSolver._nlusove (base.py:183); the rest are derived in the reference by wrapping
+ * solve_collocation_system / solve_bdf_system. */
+enum {
+    B200DAE_CNT_NFEV = 0,
+    B200DAE_CNT_NJEV = 1,
+    B200DAE_CNT_NLU = 2,
+    B200DAE_CNT_NSOLVE = 3,
+    B200DAE_CNT_ACCEPTED = 4,
+    B200DAE_CNT_ERR_REJECTED = 5,
+    B200DAE_CNT_NEWTON_FAIL = 6,
+    B200DAE_CNT_NEWTON_ITER = 7,
+    B200DAE_NUM_COUNTERS = 8
+};
+
+/* Radau IIA method tables = the return value of radau_constants(s) (radau.py:51-134), computed
+ * on the host in float64 with the same NumPy/SciPy primitives (scipy_dae_b200/constants.py).
+ * Matrices are row-major with stride s. */
+typedef struct b200dae_radau_tables {
+    int32_t s;
+    int32_t order;
+    double A[B200DAE_MAX_STAGES * B200DAE_MAX_STAGES];
+    double C[B200DAE_MAX_STAGES];
+    double T[B200DAE_MAX_STAGES * B200DAE_MAX_STAGES];
+    double TI[B200DAE_MAX_STAGES * B200DAE_MAX_STAGES];
+    double P[B200DAE_MAX_STAGES * B200DAE_MAX_STAGES];
+    double P2row0[B200DAE_MAX_STAGES];
+    double v_implicit[B200DAE_MAX_STAGES];
+    double v_explicit[B200DAE_MAX_STAGES];
+    double b_hat_implicit[B200DAE_MAX_STAGES];
+    double mu_real;
+    double mu_re[B200DAE_MAX_STAGES / 2];
+    double mu_im[B200DAE_MAX_STAGES / 2];
+    double b_hat1_implicit;
+} b200dae_radau_tables;
+
+/* keyword arguments of RadauDAE.__init__ (radau.py:393-399) */
+typedef struct b200dae_radau_opts {
+    double rtol;
+    double max_step;                 /* +inf: unbounded */
+    double first_step;               /* <= 0: select_initial_step (common.py:129-183) */
+    double continuous_error_weight;  /* 0 */
+    double jac_recompute_rate;       /* 1e-3 */
+    double deadband_lo, deadband_hi; /* controller_deadband = (1.0, 1.2) */
+    int32_t newton_max_iter;         /* <= 0: 7 + int((s-3)*2.5) */
+    int32_t newton_iter_embedded;    /* 1 */
+    int64_t max_steps;               /* <= 0: no cap; otherwise stop after this many accepted steps */
+} b200dae_radau_opts;
+
+/* keyword arguments of BDFDAE.__init__ (bdf.py:224-227) */
+typedef struct b200dae_bdf_opts {
+    double rtol;
+    double max_step;
+    double first_step;
+    int32_t max_order;               /* 1..6, default 5 */
+    int32_t ndf_strategy;            /* 0 "stability", 1 "efficiency", 2 plain BDF (bdf.py:242-247) */
+    int64_t max_steps;
+} b200dae_bdf_opts;
+
+/* Output block shared by both integrators.  Any pointer may be NULL (that output is skipped),
+ * except y_final/t_final/status.
+ *   y_final, yp_final [n][ld]   state at t_final            (solver.y / solver.yp after the loop)
+ *   t_final           [ld]      solver.t
+ *   status            [ld]      B200DAE_ST_*
+ *   counters          [8][ld]   see enum above
+ *   t_eval            [m]       DEVICE, sorted in the direction of integration (dae.py:384-403)
+ *   y_eval, yp_eval   [m][n][ld] dense output at t_eval (dae.py:496-515; Radau: radau.py:681-699,
+ *                                BDF: bdf.py:525-548); rows >= n_eval_valid[i] are left untouched
+ *   n_eval_valid      [ld]      number of t_eval points produced (all m unless the instance failed:
+ *                               solve_dae breaks before recording a failed step, dae.py:451-453)
+ *   t_steps           [steps_cap][ld]     accepted step ends incl. t0 (what solve_dae returns as
+ *   y_steps, yp_steps [steps_cap][n][ld]   DaeResult.t/y/yp when t_eval is None, dae.py:492-495)
+ *   n_steps           [ld]      number of rows written to the step trace
+ */
+typedef struct b200dae_outputs {
+    double *y_final, *yp_final, *t_final;
+    int32_t *status;
+    int32_t *counters;
+    const double *t_eval;
+    int64_t m;
+    double *y_eval, *yp_eval;
+    int32_t *n_eval_valid;
+    int64_t steps_cap;
+    double *t_steps, *y_steps, *yp_steps;
+    int32_t *n_steps;
+} b200dae_outputs;
+
+int b200dae_version(void);
+const char *b200dae_last_error(void);
+
+/* Problem registry: residuals F(t, y, y'; p) compiled into the library as device functors
+ * (replaces the Python callable `fun(t, y, yp, *args)`, base.py:44-45, dae.py:365-383).
+ * Returns the problem id (>= 0) or B200DAE_ENOPROBLEM. */
+int b200dae_num_problems(void);
+int b200dae_problem_lookup(const char *name, int32_t *n, int32_t *n_params);
+const char *b200dae_problem_name(int problem_id);
+
+/* Evaluate the registered residual on the device for N instances (SoA, ld): out[n][ld].
+ * Lets the host side verify that a device functor matches its NumPy twin. */
+int b200dae_residual(int problem_id, int64_t N, int64_t ld, double t,
+                     const double *y, const double *yp, const double *params,
+                     double *out, void *stream);
+
+/* solve_dae(fun, (t0, t_bound), y0, yp0, method="Radau", rtol, atol, t_eval, **opts) for N
+ * instances at once: replaces RadauDAE.__init__ + the `while status is None: solver.step()` loop
+ * of solve_dae (dae.py:405-518) + RadauDAE._step_impl (radau.py:465-659) and everything below it
+ * (solve_collocation_system radau.py:137-195, num_jac, LU, predict_factor, dense output).
+ *   y0, yp0 [n][ld], params [n_params][ld] : DEVICE;  atol[n], opts, tb : HOST. */
+int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld,
+                        const double *y0, const double *yp0, const double *params,
+                        double t0, double t_bound, const double *atol,
+                        const b200dae_radau_opts *opts, const b200dae_radau_tables *tb,
+                        const b200dae_outputs *out, void *stream);
+
+/* Same for method="BDF": BDFDAE.__init__ (bdf.py:224-261), BDFDAE._step_impl (bdf.py:263-415),
+ * solve_bdf_system (bdf.py:32-64), change_D (bdf.py:14-29), BdfDenseOutput (bdf.py:422-548). */
+int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld,
+                      const double *y0, const double *yp0, const double *params,
+                      double t0, double t_bound, const double *atol,
+                      const b200dae_bdf_opts *opts,
+                      const b200dae_outputs *out, void *stream);
+
+/* Number of kernels launched by this library since load (bench.py's "gpu_launches" claim). */
+int64_t b200dae_launch_count(void);
+
+/* FP64 FMA-pipe peak microbenchmark used as the roofline denominator for the FP64 bound:
+ * every thread runs `iters` rounds of 8 independent dependent-chain DFMAs.  `sink` is a device
+ * buffer of at least `blocks*threads` doubles.  flops = blocks*threads*iters*8*2. */
+int b200dae_fp64_peak_kernel(int blocks, int threads, int64_t iters, double *sink, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DAE_H */

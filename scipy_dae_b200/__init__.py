@@ -1,0 +1,11 @@
+"""scipy_dae_b200 — B200-native ensemble DAE/IDE integrator (drop-in for scipy_dae's hot path).
+
+Importing the package does not need a GPU; calling a solver does, and fails loudly when
+libb200dae.so (the sm_100a CUDA library) is missing — there is no CPU fallback.
+"""
+from .batched import BatchedDaeResult, solve_dae_batched, device_residual
+from .problems import PROBLEMS, Problem, get_problem, perturbed_params, initial_conditions
+
+__all__ = ["solve_dae_batched", "BatchedDaeResult", "device_residual", "PROBLEMS", "Problem",
+           "get_problem", "perturbed_params", "initial_conditions"]
+__version__ = "0.1.0"

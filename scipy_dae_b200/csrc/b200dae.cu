@@ -1,0 +1,325 @@
+// b200dae.cu — C-ABI of libb200dae.so (include/b200dae.h): argument checking, launch
+// descriptors and the (problem, stages) -> kernel dispatch table.  No torch types, no allocation.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/b200dae.h"
+#include "bdf.cuh"
+#include "problems.cuh"
+#include "radau.cuh"
+
+namespace b200dae {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+// threads per block: register-regime kernels keep ~255 registers per thread live, so 128
+// threads x 2 blocks fill an SM's register file; the local-memory regime prefers fewer
+// threads per SM so that its per-thread arrays stay L1-resident.
+template <class P> struct BlockSize { static constexpr int value = Regime<P::N>::kReg ? 128 : 64; };
+
+typedef int (*radau_launcher)(const RadauLaunch&, cudaStream_t);
+typedef int (*bdf_launcher)(const BdfLaunch&, cudaStream_t);
+typedef int (*residual_launcher)(int64_t, int64_t, double, const double*, const double*,
+                                 const double*, double*, cudaStream_t);
+
+template <class P, int S>
+static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
+    constexpr int T = BlockSize<P>::value;
+    const int64_t blocks = (L.N + T - 1) / T;
+    radau_kernel<P, S, T><<<(unsigned)blocks, T, 0, st>>>(L);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <class P>
+static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
+    constexpr int T = BlockSize<P>::value;
+    const int64_t blocks = (L.N + T - 1) / T;
+    bdf_kernel<P, T><<<(unsigned)blocks, T, 0, st>>>(L);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <class P>
+__global__ void residual_kernel(int64_t N, int64_t ld, double t, const double* __restrict__ y,
+                                const double* __restrict__ yp, const double* __restrict__ params,
+                                double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double yy[P::N], yyp[P::N], pp[P::NP > 0 ? P::NP : 1], f[P::N];
+    for (int j = 0; j < P::N; ++j) { yy[j] = y[j * ld + i]; yyp[j] = yp[j * ld + i]; }
+    for (int j = 0; j < P::NP; ++j) pp[j] = params[j * ld + i];
+    P::eval(t, yy, yyp, pp, f);
+    for (int j = 0; j < P::N; ++j) out[j * ld + i] = f[j];
+}
+
+template <class P>
+static int launch_residual(int64_t N, int64_t ld, double t, const double* y, const double* yp,
+                           const double* params, double* out, cudaStream_t st) {
+    residual_kernel<P><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, ld, t, y, yp, params, out);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+struct ProblemEntry {
+    const char* name;
+    int n, n_params;
+    radau_launcher radau[B200DAE_MAX_STAGES + 1];   // indexed by the number of stages
+    bdf_launcher bdf;
+    residual_launcher residual;
+};
+
+template <class P>
+static ProblemEntry make_entry(bool s3, bool s5, bool s7) {
+    ProblemEntry e;
+    memset(&e, 0, sizeof(e));
+    e.name = P::name();
+    e.n = P::N;
+    e.n_params = P::NP;
+    e.radau[1] = launch_radau<P, 1>;
+    if (s3) e.radau[3] = launch_radau<P, 3>;
+    if (s5) e.radau[5] = launch_radau<P, 5>;
+    if (s7) e.radau[7] = launch_radau<P, 7>;
+    e.bdf = launch_bdf<P>;
+    e.residual = launch_residual<P>;
+    return e;
+}
+
+static const ProblemEntry* registry(int* count) {
+    static const ProblemEntry table[] = {
+        make_entry<Robertson>(true, true, true),
+        make_entry<AkzoNobel>(true, true, false),
+        make_entry<Transamp>(true, true, false),
+        make_entry<Andrews>(true, true, false),
+    };
+    *count = (int)(sizeof(table) / sizeof(table[0]));
+    return table;
+}
+
+static const ProblemEntry* find_problem(int id) {
+    int cnt;
+    const ProblemEntry* t = registry(&cnt);
+    return (id >= 0 && id < cnt) ? &t[id] : nullptr;
+}
+
+static int check_common(const ProblemEntry* e, int64_t N, int64_t ld, const double* y0,
+                        const double* yp0, const double* params, const double* atol,
+                        const b200dae_outputs* out) {
+    if (!e) return fail(B200DAE_ENOPROBLEM, "unknown problem id%s (%lld)", "", 0);
+    if (N < 0 || ld < N) return fail(B200DAE_EINVAL, "need 0 <= N <= ld%s (N=%lld)", "", (long long)N);
+    if (N > 0 && (!y0 || !yp0 || (e->n_params > 0 && !params)))
+        return fail(B200DAE_EINVAL, "y0 / yp0 / params must not be NULL%s", "");
+    if (!atol) return fail(B200DAE_EINVAL, "atol[n] must not be NULL%s", "");
+    for (int j = 0; j < e->n; ++j)
+        if (!(atol[j] >= 0.0)) return fail(B200DAE_EINVAL, "`atol` must be positive.%s", "");
+    if (!out || !out->y_final || !out->t_final || !out->status)
+        return fail(B200DAE_EINVAL, "out->y_final / t_final / status must not be NULL%s", "");
+    if (out->m < 0 || (out->m > 0 && (!out->t_eval || !out->y_eval)))
+        return fail(B200DAE_EINVAL, "m > 0 needs t_eval and y_eval%s", "");
+    if (out->steps_cap < 0 || (out->steps_cap > 0 && !out->t_steps))
+        return fail(B200DAE_EINVAL, "steps_cap > 0 needs t_steps%s", "");
+    return 0;
+}
+
+static b200dae_outputs normalise(const b200dae_outputs* out) {
+    b200dae_outputs o = *out;
+    if (o.m == 0) { o.t_eval = nullptr; o.y_eval = nullptr; o.yp_eval = nullptr; }
+    if (o.steps_cap == 0) { o.t_steps = nullptr; o.y_steps = nullptr; o.yp_steps = nullptr; }
+    return o;
+}
+
+// compute_R(order = 6, factor = 1) (bdf.py:14-21); leading blocks serve every lower order
+static void fill_U(double* Um) {
+    const int q = kBdfQ;
+    for (int j = 0; j < q; ++j) Um[j] = 1.0;
+    for (int i = 1; i < q; ++i)
+        for (int j = 0; j < q; ++j) {
+            const double mij = (j == 0) ? 0.0 : ((double)(i - 1) - 1.0 * j) / i;
+            Um[i * q + j] = Um[(i - 1) * q + j] * mij;
+        }
+}
+
+__global__ void fp64_peak_kernel(int64_t iters, double* __restrict__ sink) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double a0 = 1.0 + 1e-9 * threadIdx.x, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4,
+           a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
+    const double m = 0.9999999, c = 1e-7;
+    for (int64_t k = 0; k < iters; ++k) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    sink[i] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace b200dae
+
+using namespace b200dae;
+
+extern "C" {
+
+int b200dae_version(void) { return B200DAE_VERSION; }
+
+const char* b200dae_last_error(void) { return g_err; }
+
+int b200dae_num_problems(void) {
+    int cnt;
+    registry(&cnt);
+    return cnt;
+}
+
+int b200dae_problem_lookup(const char* name, int32_t* n, int32_t* n_params) {
+    int cnt;
+    const ProblemEntry* t = registry(&cnt);
+    if (name)
+        for (int i = 0; i < cnt; ++i)
+            if (strcmp(t[i].name, name) == 0) {
+                if (n) *n = t[i].n;
+                if (n_params) *n_params = t[i].n_params;
+                return i;
+            }
+    return fail(B200DAE_ENOPROBLEM, "unknown problem '%s'", name ? name : "(null)");
+}
+
+const char* b200dae_problem_name(int problem_id) {
+    const ProblemEntry* e = find_problem(problem_id);
+    return e ? e->name : nullptr;
+}
+
+int64_t b200dae_launch_count(void) { return g_launches.load(); }
+
+int b200dae_residual(int problem_id, int64_t N, int64_t ld, double t, const double* y,
+                     const double* yp, const double* params, double* out, void* stream) {
+    const ProblemEntry* e = find_problem(problem_id);
+    if (!e) return fail(B200DAE_ENOPROBLEM, "unknown problem id%s (%lld)", "", problem_id);
+    if (N < 0 || ld < N || !y || !yp || !out) return fail(B200DAE_EINVAL, "bad residual arguments%s", "");
+    if (N == 0) return 0;
+    const int rc = e->residual(N, ld, t, y, yp, params, out, (cudaStream_t)stream);
+    if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0, const double* yp0,
+                        const double* params, double t0, double t_bound, const double* atol,
+                        const b200dae_radau_opts* opts, const b200dae_radau_tables* tb,
+                        const b200dae_outputs* out, void* stream) {
+    const ProblemEntry* e = find_problem(problem_id);
+    int rc = check_common(e, N, ld, y0, yp0, params, atol, out);
+    if (rc) return rc;
+    if (!opts || !tb) return fail(B200DAE_EINVAL, "opts / tables must not be NULL%s", "");
+    const int s = tb->s;
+    if (s < 1 || s > B200DAE_MAX_STAGES || s % 2 != 1 || !e->radau[s])
+        return fail(B200DAE_ENOPROBLEM, "Radau stages not compiled for problem '%s' (stages=%lld)", e->name, s);
+    if (!(opts->max_step > 0)) return fail(B200DAE_EINVAL, "`max_step` must be positive.%s", "");
+    if (opts->first_step > fabs(t_bound - t0)) return fail(B200DAE_EINVAL, "`first_step` exceeds bounds.%s", "");
+    if (!(opts->continuous_error_weight >= 0 && opts->continuous_error_weight <= 1))
+        return fail(B200DAE_EINVAL, "need 0 <= continuous_error_weight <= 1%s", "");
+    if (!(opts->jac_recompute_rate > 0 && opts->jac_recompute_rate < 1))
+        return fail(B200DAE_EINVAL, "need 0 < jac_recompute_rate < 1%s", "");
+    if (!(opts->deadband_lo > 0 && opts->deadband_lo <= opts->deadband_hi))
+        return fail(B200DAE_EINVAL, "need 0 < controller_deadband[0] <= controller_deadband[1]%s", "");
+    if (opts->newton_iter_embedded < 0) return fail(B200DAE_EINVAL, "need newton_iter_embedded >= 0%s", "");
+    if (N == 0) return 0;
+
+    RadauLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.tb = *tb;
+    L.t0 = t0;
+    L.t_bound = t_bound;
+    L.dir = (t_bound != t0) ? ((t_bound > t0) ? 1.0 : -1.0) : 1.0;            // base.py:214
+    L.rtol = fmax(opts->rtol, 100 * kEps);                                     // validate_tol
+    L.max_step = opts->max_step;
+    L.first_step = opts->first_step;
+    L.cew = opts->continuous_error_weight;
+    L.jac_rate = opts->jac_recompute_rate;
+    L.db_lo = opts->deadband_lo;
+    L.db_hi = opts->deadband_hi;
+    {
+        const double expmns = (s + 1.0) / (2.0 * s);                           // radau.py:422-433
+        L.newton_tol = fmax(10 * kEps / L.rtol, fmin(0.03, pow(L.rtol, 1.0 / expmns - 1)));
+    }
+    for (int j = 0; j < e->n; ++j) { L.atol[j] = atol[j]; L.thr[j] = atol[j] / L.rtol; }
+    L.newton_max_iter = opts->newton_max_iter > 0 ? opts->newton_max_iter
+                                                  : 7 + (int)((s - 3) * 2.5);  // radau.py:440-441
+    L.newton_iter_embedded = opts->newton_iter_embedded;
+    L.max_steps = opts->max_steps;
+    L.N = N;
+    L.ld = ld;
+    L.y0 = y0;
+    L.yp0 = yp0;
+    L.params = params;
+    L.out = normalise(out);
+    rc = e->radau[s](L, (cudaStream_t)stream);
+    if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, const double* yp0,
+                      const double* params, double t0, double t_bound, const double* atol,
+                      const b200dae_bdf_opts* opts, const b200dae_outputs* out, void* stream) {
+    const ProblemEntry* e = find_problem(problem_id);
+    int rc = check_common(e, N, ld, y0, yp0, params, atol, out);
+    if (rc) return rc;
+    if (!opts) return fail(B200DAE_EINVAL, "opts must not be NULL%s", "");
+    if (opts->max_order < 1 || opts->max_order > B200DAE_MAX_ORDER)
+        return fail(B200DAE_EINVAL, "Ensure that 1 <= max_order <= 6.%s", "");
+    if (!(opts->max_step > 0)) return fail(B200DAE_EINVAL, "`max_step` must be positive.%s", "");
+    if (opts->first_step > fabs(t_bound - t0)) return fail(B200DAE_EINVAL, "`first_step` exceeds bounds.%s", "");
+    if (N == 0) return 0;
+
+    BdfLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.t0 = t0;
+    L.t_bound = t_bound;
+    L.dir = (t_bound != t0) ? ((t_bound > t0) ? 1.0 : -1.0) : 1.0;
+    L.rtol = fmax(opts->rtol, 100 * kEps);
+    L.max_step = opts->max_step;
+    L.first_step = opts->first_step;
+    L.newton_tol = fmax(10 * kEps / L.rtol, fmin(0.03, sqrt(L.rtol)));         // bdf.py:234
+    for (int j = 0; j < e->n; ++j) { L.atol[j] = atol[j]; L.thr[j] = atol[j] / L.rtol; }
+    {
+        static const double k_stab[7] = {0, -37.0 / 200, -1.0 / 9, 0.0834, 0.0665, 0.0551, 0.0464};
+        static const double k_eff[7] = {0, -37.0 / 200, -1.0 / 9, -0.0823, -0.0415, 0, 0};
+        static const double k_bdf[7] = {0, -37.0 / 200, -1.0 / 9, 0, 0, 0, 0};
+        const double* kappa = opts->ndf_strategy == 0 ? k_stab : (opts->ndf_strategy == 1 ? k_eff : k_bdf);
+        double g = 0.0;
+        for (int k = 1; k <= opts->max_order; ++k) { g += 1.0 / k; L.gamma[k] = g; }   // bdf.py:250-252
+        for (int k = 0; k <= opts->max_order; ++k) {
+            L.alpha[k] = (1 - kappa[k]) * L.gamma[k];
+            L.error_const[k] = kappa[k] * L.gamma[k] + 1.0 / (k + 1);
+        }
+    }
+    fill_U(L.U);
+    L.max_order = opts->max_order;
+    L.max_steps = opts->max_steps;
+    L.N = N;
+    L.ld = ld;
+    L.y0 = y0;
+    L.yp0 = yp0;
+    L.params = params;
+    L.out = normalise(out);
+    rc = e->bdf(L, (cudaStream_t)stream);
+    if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int b200dae_fp64_peak_kernel(int blocks, int threads, int64_t iters, double* sink, void* stream) {
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || !sink)
+        return fail(B200DAE_EINVAL, "bad fp64 peak arguments%s", "");
+    fp64_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+    g_launches.fetch_add(1);
+    const cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString(rc));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// bdf.cuh — the whole variable-order BDF/NDF integration of one system per thread.
+//
+// One launch replaces, for N independent instances, BDFDAE.__init__ (bdf.py:224-261), the
+// step loop + t_eval slicing of solve_dae (dae.py:446-518), BDFDAE._step_impl (bdf.py:263-415),
+// solve_bdf_system (bdf.py:32-64), change_D / compute_R (bdf.py:14-29) and BdfDenseOutput
+// (bdf.py:422-548).  Same flattened control flow as radau.cuh: one loop trip = one Newton solve,
+// each heavy phase at a single code site.
+//
+// The quasi-constant-step difference array D[(max_order+3)][n] is indexed by the run-time order,
+// so it lives in per-thread local memory (L1-resident: 9*n doubles per instance).
+#pragma once
+#include <stdint.h>
+#include "../../include/b200dae.h"
+#include "fd_jacobian.cuh"
+#include "radau.cuh"   // finite_d, powi
+
+namespace b200dae {
+
+constexpr int kBdfNewtonMaxIter = 4;     // bdf.py:9
+constexpr int kBdfRows = B200DAE_MAX_ORDER + 3;
+constexpr int kBdfQ = B200DAE_MAX_ORDER + 1;
+
+struct BdfLaunch {
+    double t0, t_bound, dir;
+    double rtol, max_step, first_step, newton_tol;
+    double atol[B200DAE_MAX_N];
+    double thr[B200DAE_MAX_N];
+    double gamma[kBdfQ], alpha[kBdfQ], error_const[kBdfQ + 1];
+    double U[kBdfQ * kBdfQ];   // compute_R(6, 1): its leading blocks are compute_R(order, 1)
+    int32_t max_order;
+    int64_t max_steps;
+    int64_t N, ld;
+    const double *y0, *yp0, *params;
+    b200dae_outputs out;
+};
+
+// change_D (bdf.py:24-29): D[:order+1] = (R @ U).T @ D[:order+1], evaluated as U.T @ (R.T @ D)
+// with R = cumprod_i (i - 1 - factor*j) / i generated column by column (bdf.py:14-21).
+template <int N>
+__device__ __noinline__ void change_D(double* __restrict__ D, int order, double factor,
+                                      const double* __restrict__ Umat) {
+    double E[kBdfQ * N];
+    const int q = order + 1;
+    for (int j = 0; j < q; ++j) {
+        double acc[N];
+        for (int c = 0; c < N; ++c) acc[c] = D[c];          // R[0][j] = 1
+        double r = 1.0;
+        for (int l = 1; l < q; ++l) {
+            r *= (j == 0) ? 0.0 : ((l - 1) - factor * j) / l;
+            for (int c = 0; c < N; ++c) acc[c] = fma(r, D[l * N + c], acc[c]);
+        }
+        for (int c = 0; c < N; ++c) E[j * N + c] = acc[c];
+    }
+    for (int i = 0; i < q; ++i)
+        for (int c = 0; c < N; ++c) {
+            double acc = 0.0;
+            for (int l = 0; l < q; ++l) acc = fma(Umat[l * kBdfQ + i], E[l * N + c], acc);
+            D[i * N + c] = acc;
+        }
+}
+
+template <class P, int kThreads>
+__global__ void __launch_bounds__(kThreads)
+bdf_kernel(const __grid_constant__ BdfLaunch L) {
+    constexpr int N = P::N, NP = P::NP;
+    constexpr int U = Regime<N>::kUnroll;
+    const int64_t inst = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (inst >= L.N) return;
+    const int64_t ld = L.ld;
+
+    double p[NP > 0 ? NP : 1], y[N], yp[N];
+#pragma unroll U
+    for (int j = 0; j < NP; ++j) p[j] = L.params[j * ld + inst];
+#pragma unroll U
+    for (int j = 0; j < N; ++j) { y[j] = L.y0[j * ld + inst]; yp[j] = L.yp0[j * ld + inst]; }
+
+    double Jy[N * N], Jyp[N * N], factor_y[N], factor_yp[N], LU[N * N];
+    int piv[N];
+    double D[kBdfRows * N];
+    double y_predict[N], psi[N], inv_scale[N], y_new[N], yp_new[N], d[N], f[N];
+#pragma unroll U
+    for (int j = 0; j < N; ++j) factor_y[j] = factor_yp[j] = kNjInitFactor;
+
+    const double dir = L.dir, rtol = L.rtol;
+    double t = L.t0;
+    double h_abs;
+    if (L.first_step > 0.0) {
+        h_abs = L.first_step;
+    } else {                                               // select_initial_step, common.py:129-183
+        double e = 0.0;
+#pragma unroll U
+        for (int j = 0; j < N; ++j) {
+            const double v = fabs(yp[j] / fmax(fabs(y[j]), L.thr[j]));
+            if (v > e || v != v) e = v;
+        }
+        const double rh = e / sqrt(rtol) / 0.8;
+        h_abs = fmin(L.max_step, fabs(L.t_bound - L.t0));
+        if (h_abs * rh > 1.0) h_abs = 1.0 / rh;
+        h_abs = fmax(h_abs, 16.0 * kEps * fabs(L.t0));
+    }
+    for (int k = 0; k < kBdfRows * N; ++k) D[k] = 0.0;     // bdf.py:254-257
+    for (int j = 0; j < N; ++j) { D[j] = y[j]; D[N + j] = yp[j] * h_abs * dir; }
+    int order = 1, n_equal_steps = 0;
+    const int max_order = L.max_order;
+
+    bool need_jac = true, lu_valid = false, step_begin = true, retry = false, current_jac = false;
+    int32_t nfev = 0, njev = 0, nlu = 0, nsolve = 0, nacc = 0, nrej = 0, nfail = 0, niter = 0;
+    int32_t status = B200DAE_ST_RUNNING;
+    int64_t ie = 0;
+    int32_t nst = 0;
+
+    if (L.out.t_steps != nullptr && L.out.steps_cap > 0) {
+        L.out.t_steps[inst] = t;
+        for (int j = 0; j < N; ++j) {
+            if (L.out.y_steps) L.out.y_steps[j * ld + inst] = y[j];
+            if (L.out.yp_steps) L.out.yp_steps[j * ld + inst] = yp[j];
+        }
+        nst = 1;
+    }
+    if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; njev = 1; }
+
+    double hl = 0.0, min_step = 0.0, h = 0.0, t_new = 0.0, c = 0.0;
+
+    while (status == B200DAE_ST_RUNNING) {
+        // ---- phase J: FD Jacobian at the committed (t, y, yp) (base.py:297, bdf.py:330) ------
+        if (need_jac) {
+            fd_jacobian<P>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
+            ++njev;
+            need_jac = false;
+        }
+        // ---- phase B: a new step begins (bdf.py:269-293) --------------------------------------
+        if (step_begin) {
+            min_step = 10.0 * fabs(nextafter(t, dir * INFINITY) - t);
+            if (h_abs > L.max_step) {
+                hl = L.max_step;
+                change_D<N>(D, order, L.max_step / h_abs, L.U);
+                n_equal_steps = 0;
+            } else if (h_abs < min_step) {
+                hl = min_step;
+                change_D<N>(D, order, min_step / h_abs, L.U);
+                n_equal_steps = 0;
+            } else {
+                hl = h_abs;
+            }
+            current_jac = false;      // `self.jac is None` is False for the FD wrapper, bdf.py:293
+            step_begin = false;
+        }
+        // ---- phase A: a new attempt (bdf.py:296-318) ---------------------------------------------
+        if (!retry) {
+            if (hl < min_step) { status = B200DAE_ST_TOO_SMALL_STEP; break; }
+            h = hl * dir;
+            t_new = t + h;
+            if (dir * (t_new - L.t_bound) > 0.0) {
+                t_new = L.t_bound;
+                change_D<N>(D, order, fabs(t_new - t) / hl, L.U);
+                n_equal_steps = 0;
+                lu_valid = false;
+            }
+            h = t_new - t;
+            hl = fabs(h);
+            const double rh = 1.0 / h;
+            for (int j = 0; j < N; ++j) {
+                double acc = 0.0, ps = 0.0;
+                for (int i = 0; i <= order; ++i) acc += D[i * N + j];
+                for (int i = 1; i <= order; ++i) ps = fma(D[i * N + j], L.gamma[i], ps);
+                y_predict[j] = acc;
+                inv_scale[j] = 1.0 / fma(rtol, fabs(acc), L.atol[j]);
+                psi[j] = ps * rh;
+            }
+            c = L.alpha[order] * rh;
+        }
+        retry = false;
+
+        // ---- phase F: LU of Jy + c*Jyp (bdf.py:320-321) -------------------------------------------
+        if (!lu_valid) {
+            bool fin = true;
+#pragma unroll U
+            for (int k = 0; k < N * N; ++k) {
+                const double v = fma(c, Jyp[k], Jy[k]);
+                fin = fin && finite_d(v);
+                LU[k] = v;
+            }
+            if (!fin) { status = B200DAE_ST_NONFINITE; break; }
+            lu_factor<N>(LU, piv);
+            ++nlu;
+            lu_valid = true;
+        }
+
+        // ---- phase N: simplified Newton (solve_bdf_system, bdf.py:32-64) ---------------------------
+        bool converged = false;
+        int n_iter;
+        {
+#pragma unroll U
+            for (int j = 0; j < N; ++j) { d[j] = 0.0; y_new[j] = y_predict[j]; }
+            double dy_norm_old = 0.0;
+            bool has_old = false;
+            int k = 0;
+            for (; k < kBdfNewtonMaxIter; ++k) {
+#pragma unroll U
+                for (int j = 0; j < N; ++j) yp_new[j] = fma(c, d[j], psi[j]);
+                P::eval(t_new, y_new, yp_new, p, f);
+                ++nfev;
+                bool fin = true;
+#pragma unroll U
+                for (int j = 0; j < N; ++j) { fin = fin && finite_d(f[j]); f[j] = -f[j]; }
+                if (!fin) break;
+                lu_solve<N>(LU, piv, f);                          // f <- dy
+                ++nsolve;
+                double ss = 0.0;
+#pragma unroll U
+                for (int j = 0; j < N; ++j) { const double q = f[j] * inv_scale[j]; ss = fma(q, q, ss); }
+                const double dy_norm = sqrt(ss * (1.0 / N));
+                double rate = 0.0;
+                if (has_old) rate = dy_norm / dy_norm_old;
+                if (has_old && (rate >= 1.0 ||
+                                powi(rate, kBdfNewtonMaxIter - k) / (1.0 - rate) * dy_norm > L.newton_tol))
+                    break;                                        // BEFORE the update (bdf.py:52-53)
+#pragma unroll U
+                for (int j = 0; j < N; ++j) { y_new[j] += f[j]; d[j] += f[j]; }
+                if (dy_norm == 0.0 || (has_old && rate / (1.0 - rate) * dy_norm < L.newton_tol)) {
+                    converged = true;
+                    break;
+                }
+                dy_norm_old = dy_norm;
+                has_old = true;
+            }
+            n_iter = (k == kBdfNewtonMaxIter) ? kBdfNewtonMaxIter : k + 1;
+            niter += n_iter;
+        }
+        if (!converged) {
+            ++nfail;
+            if (!current_jac) {                    // bdf.py:327-332: refresh J at the OLD point
+                need_jac = true;
+                current_jac = true;
+                lu_valid = false;
+                retry = true;
+                continue;
+            }
+            hl *= 0.5;                             // bdf.py:334-340
+            change_D<N>(D, order, 0.5, L.U);
+            n_equal_steps = 0;
+            lu_valid = false;
+            continue;
+        }
+
+        // ---- phase E: local error (bdf.py:342-355) -------------------------------------------------
+        const double safety = 0.9 * (2 * kBdfNewtonMaxIter + 1) / (double)(2 * kBdfNewtonMaxIter + n_iter);
+        double error_norm;
+        {
+            const double ec = L.error_const[order];
+            double ss = 0.0;
+#pragma unroll U
+            for (int j = 0; j < N; ++j) {
+                inv_scale[j] = 1.0 / fma(rtol, fabs(y_new[j]), L.atol[j]);
+                const double q = ec * d[j] * inv_scale[j];
+                ss = fma(q, q, ss);
+            }
+            error_norm = sqrt(ss * (1.0 / N));
+        }
+        if (error_norm > 1.0) {
+            const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (order + 1)));
+            hl *= factor;
+            change_D<N>(D, order, factor, L.U);
+            n_equal_steps = 0;                     // LU is kept (bdf.py:353-354)
+            ++nrej;
+            continue;
+        }
+
+        // ---- phase C: accepted (bdf.py:359-415) ----------------------------------------------------
+        ++n_equal_steps;
+        t = t_new;
+#pragma unroll U
+        for (int j = 0; j < N; ++j) { y[j] = y_new[j]; yp[j] = yp_new[j]; }
+        h_abs = hl;
+        ++nacc;
+        for (int j = 0; j < N; ++j) {              // bdf.py:374-377
+            D[(order + 2) * N + j] = d[j] - D[(order + 1) * N + j];
+            D[(order + 1) * N + j] = d[j];
+        }
+        for (int i = order; i >= 0; --i)
+            for (int j = 0; j < N; ++j) D[i * N + j] += D[(i + 1) * N + j];
+
+        if (n_equal_steps >= order + 1) {          // order / step selection, bdf.py:379-413
+            double norms[3];
+            norms[1] = error_norm;
+            if (order > 1) {
+                const double ec = L.error_const[order - 1];
+                double ss = 0.0;
+                for (int j = 0; j < N; ++j) { const double q = ec * D[order * N + j] * inv_scale[j]; ss = fma(q, q, ss); }
+                norms[0] = sqrt(ss * (1.0 / N));
+            } else {
+                norms[0] = INFINITY;
+            }
+            if (order < max_order) {
+                const double ec = L.error_const[order + 1];
+                double ss = 0.0;
+                for (int j = 0; j < N; ++j) { const double q = ec * D[(order + 2) * N + j] * inv_scale[j]; ss = fma(q, q, ss); }
+                norms[2] = sqrt(ss * (1.0 / N));
+            } else {
+                norms[2] = INFINITY;
+            }
+            double best = 0.0;
+            int arg = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double fc = pow(norms[i], -1.0 / (order + i));
+                if (i == 0 || (best == best && (fc > best || fc != fc))) { best = fc; arg = i; }
+            }
+            order += arg - 1;
+            const double factor = fmin(10.0, safety * best);
+            h_abs *= factor;
+            change_D<N>(D, order, factor, L.U);
+            n_equal_steps = 0;
+            lu_valid = false;
+        }
+
+        // t_eval points passed by this step; BdfDenseOutput is built AFTER the rescale with
+        // h = h_abs*direction (bdf.py:417-419, 525-548)
+        if (L.out.t_eval != nullptr) {
+            const double hh = h_abs * dir;
+            while (ie < L.out.m) {
+                const double te = __ldg(L.out.t_eval + ie);
+                if (!(dir > 0.0 ? te <= t : te >= t)) break;
+                double* ye = L.out.y_eval + ie * N * ld + inst;
+                double* ype = L.out.yp_eval ? L.out.yp_eval + ie * N * ld + inst : nullptr;
+                double ya[N], ypa[N];
+                for (int j = 0; j < N; ++j) { ya[j] = D[j]; ypa[j] = 0.0; }
+                double fact = 1.0, hj = 1.0;
+                for (int jj = 1; jj <= order; ++jj) {
+                    fact *= jj;
+                    hj *= hh;
+                    double fac = 1.0, dfac = 0.0;
+                    for (int mm = 0; mm < jj; ++mm) {
+                        fac *= te - (t - mm * hh);
+                        double dprod = 1.0;
+                        for (int i = 0; i < jj; ++i)
+                            if (i != mm) dprod *= te - (t - i * hh);
+                        dfac += dprod;
+                    }
+                    const double rden = 1.0 / (fact * hj);
+                    for (int j = 0; j < N; ++j) {
+                        ya[j] = fma(D[jj * N + j], fac * rden, ya[j]);
+                        ypa[j] = fma(D[jj * N + j], dfac * rden, ypa[j]);
+                    }
+                }
+                for (int j = 0; j < N; ++j) {
+                    ye[j * ld] = ya[j];
+                    if (ype) ype[j * ld] = ypa[j];
+                }
+                ++ie;
+            }
+        }
+        if (L.out.t_steps != nullptr && nst < L.out.steps_cap) {
+            L.out.t_steps[(int64_t)nst * ld + inst] = t;
+            for (int j = 0; j < N; ++j) {
+                if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + j) * ld + inst] = y[j];
+                if (L.out.yp_steps) L.out.yp_steps[((int64_t)nst * N + j) * ld + inst] = yp[j];
+            }
+            ++nst;
+        }
+        step_begin = true;
+        if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;
+        else if (L.max_steps > 0 && nacc >= L.max_steps) status = B200DAE_ST_MAX_STEPS;
+    }
+
+#pragma unroll U
+    for (int j = 0; j < N; ++j) {
+        L.out.y_final[j * ld + inst] = y[j];
+        if (L.out.yp_final) L.out.yp_final[j * ld + inst] = yp[j];
+    }
+    L.out.t_final[inst] = t;
+    L.out.status[inst] = status;
+    if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
+    if (L.out.n_steps) L.out.n_steps[inst] = nst;
+    if (L.out.counters) {
+        int32_t* cn = L.out.counters + inst;
+        cn[B200DAE_CNT_NFEV * ld] = nfev;
+        cn[B200DAE_CNT_NJEV * ld] = njev;
+        cn[B200DAE_CNT_NLU * ld] = nlu;
+        cn[B200DAE_CNT_NSOLVE * ld] = nsolve;
+        cn[B200DAE_CNT_ACCEPTED * ld] = nacc;
+        cn[B200DAE_CNT_ERR_REJECTED * ld] = nrej;
+        cn[B200DAE_CNT_NEWTON_FAIL * ld] = nfail;
+        cn[B200DAE_CNT_NEWTON_ITER * ld] = niter;
+    }
+}
+
+}  // namespace b200dae

@@ -1,0 +1,234 @@
+// dense_lu.cuh — per-instance dense LU with row partial pivoting and triangular solves, real and
+// complex, one system per thread.
+//
+// Replaces scipy.linalg.lu_factor / lu_solve as called by the reference (base.py:232-238), i.e.
+// LAPACK dgetrf/dgetrs for the real blocks and zgetrf/zgetrs for the complex Radau blocks:
+// first-maximal-element pivoting (idamax on |x|, izamax on |re|+|im|), rows swapped in full,
+// column scaled by the reciprocal of the pivot, a zero pivot is left in place (info > 0 in
+// LAPACK; the solve then produces inf/nan exactly like getrs).
+//
+// Two storage regimes, chosen at compile time:
+//   REG  (N <= 4): the matrix is a fully unrolled local array -> registers.  Row swaps and the
+//                  right-hand-side permutation are predicated selects, never dynamic indexing
+//                  (which would demote the arrays to local memory).
+//   !REG (N  > 4): the matrix lives in (L1-resident) local memory, loops are rolled, swaps index
+//                  dynamically.
+// The diagonal of U is stored as its reciprocal so the solves multiply instead of divide.
+#pragma once
+#include <math.h>
+
+namespace b200dae {
+
+template <int N>
+struct Regime {
+    static constexpr bool kReg = (N <= 4);
+    static constexpr int kUnroll = kReg ? 64 : 1;   // "#pragma unroll kUnroll": full vs none
+};
+
+// ---------------------------------------------------------------------------------------------
+// real
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void lu_factor(double* __restrict__ a, int* __restrict__ piv) {
+    constexpr bool REG = Regime<N>::kReg;
+    constexpr int U = Regime<N>::kUnroll;
+#pragma unroll U
+    for (int k = 0; k < N; ++k) {
+        int p = k;
+        double best = fabs(a[k * N + k]);
+#pragma unroll U
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(a[i * N + k]);
+            if (v > best) { best = v; p = i; }
+        }
+        piv[k] = p;
+        if (REG) {
+#pragma unroll U
+            for (int i = k + 1; i < N; ++i) {
+                const bool sw = (p == i);
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    const double x = a[k * N + j], z = a[i * N + j];
+                    a[k * N + j] = sw ? z : x;
+                    a[i * N + j] = sw ? x : z;
+                }
+            }
+        } else if (p != k) {
+            for (int j = 0; j < N; ++j) {
+                const double x = a[k * N + j];
+                a[k * N + j] = a[p * N + j];
+                a[p * N + j] = x;
+            }
+        }
+        const double pv = a[k * N + k];
+        const double r = 1.0 / pv;
+        a[k * N + k] = r;                              // reciprocal pivot
+        const double rs = (pv != 0.0) ? r : 1.0;       // LAPACK skips the scaling for a zero pivot
+#pragma unroll U
+        for (int i = k + 1; i < N; ++i) {
+            const double l = a[i * N + k] * rs;
+            a[i * N + k] = l;
+#pragma unroll U
+            for (int j = k + 1; j < N; ++j) a[i * N + j] = fma(-l, a[k * N + j], a[i * N + j]);
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const int* __restrict__ piv,
+                                         double* __restrict__ b) {
+    constexpr bool REG = Regime<N>::kReg;
+    constexpr int U = Regime<N>::kUnroll;
+#pragma unroll U
+    for (int k = 0; k < N; ++k) {
+        const int p = piv[k];
+        if (REG) {
+#pragma unroll U
+            for (int i = k + 1; i < N; ++i) {
+                const bool sw = (p == i);
+                const double x = b[k], z = b[i];
+                b[k] = sw ? z : x;
+                b[i] = sw ? x : z;
+            }
+        } else if (p != k) {
+            const double x = b[k]; b[k] = b[p]; b[p] = x;
+        }
+    }
+#pragma unroll U
+    for (int i = 1; i < N; ++i) {
+        double acc = b[i];
+#pragma unroll U
+        for (int j = 0; j < i; ++j) acc = fma(-lu[i * N + j], b[j], acc);
+        b[i] = acc;
+    }
+#pragma unroll U
+    for (int i = N - 1; i >= 0; --i) {
+        double acc = b[i];
+#pragma unroll U
+        for (int j = i + 1; j < N; ++j) acc = fma(-lu[i * N + j], b[j], acc);
+        b[i] = acc * lu[i * N + i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// complex, split re/im storage
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void crecip(double pr, double pi, double& rr, double& ri) {
+    // 1 / (pr + i pi), Smith's formula (robust against overflow of pr^2 + pi^2)
+    if (fabs(pr) >= fabs(pi)) {
+        const double q = pi / pr, d = 1.0 / fma(pi, q, pr);
+        rr = d; ri = -q * d;
+    } else {
+        const double q = pr / pi, d = 1.0 / fma(pr, q, pi);
+        rr = q * d; ri = -d;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void zlu_factor(double* __restrict__ ar, double* __restrict__ ai,
+                                           int* __restrict__ piv) {
+    constexpr bool REG = Regime<N>::kReg;
+    constexpr int U = Regime<N>::kUnroll;
+#pragma unroll U
+    for (int k = 0; k < N; ++k) {
+        int p = k;
+        double best = fabs(ar[k * N + k]) + fabs(ai[k * N + k]);
+#pragma unroll U
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(ar[i * N + k]) + fabs(ai[i * N + k]);
+            if (v > best) { best = v; p = i; }
+        }
+        piv[k] = p;
+        if (REG) {
+#pragma unroll U
+            for (int i = k + 1; i < N; ++i) {
+                const bool sw = (p == i);
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    double x = ar[k * N + j], z = ar[i * N + j];
+                    ar[k * N + j] = sw ? z : x;
+                    ar[i * N + j] = sw ? x : z;
+                    x = ai[k * N + j]; z = ai[i * N + j];
+                    ai[k * N + j] = sw ? z : x;
+                    ai[i * N + j] = sw ? x : z;
+                }
+            }
+        } else if (p != k) {
+            for (int j = 0; j < N; ++j) {
+                double x = ar[k * N + j]; ar[k * N + j] = ar[p * N + j]; ar[p * N + j] = x;
+                x = ai[k * N + j]; ai[k * N + j] = ai[p * N + j]; ai[p * N + j] = x;
+            }
+        }
+        const double pr = ar[k * N + k], pi = ai[k * N + k];
+        double rr, ri;
+        crecip(pr, pi, rr, ri);
+        ar[k * N + k] = rr;                            // reciprocal pivot
+        ai[k * N + k] = ri;
+        const bool nz = (pr != 0.0) || (pi != 0.0);
+        const double sr = nz ? rr : 1.0, si = nz ? ri : 0.0;
+#pragma unroll U
+        for (int i = k + 1; i < N; ++i) {
+            const double xr = ar[i * N + k], xi = ai[i * N + k];
+            const double lr = fma(xr, sr, -xi * si), li = fma(xr, si, xi * sr);
+            ar[i * N + k] = lr;
+            ai[i * N + k] = li;
+#pragma unroll U
+            for (int j = k + 1; j < N; ++j) {
+                const double ur = ar[k * N + j], ui = ai[k * N + j];
+                ar[i * N + j] = fma(li, ui, fma(-lr, ur, ar[i * N + j]));
+                ai[i * N + j] = fma(-li, ur, fma(-lr, ui, ai[i * N + j]));
+            }
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void zlu_solve(const double* __restrict__ ar, const double* __restrict__ ai,
+                                          const int* __restrict__ piv, double* __restrict__ br,
+                                          double* __restrict__ bi) {
+    constexpr bool REG = Regime<N>::kReg;
+    constexpr int U = Regime<N>::kUnroll;
+#pragma unroll U
+    for (int k = 0; k < N; ++k) {
+        const int p = piv[k];
+        if (REG) {
+#pragma unroll U
+            for (int i = k + 1; i < N; ++i) {
+                const bool sw = (p == i);
+                double x = br[k], z = br[i];
+                br[k] = sw ? z : x; br[i] = sw ? x : z;
+                x = bi[k]; z = bi[i];
+                bi[k] = sw ? z : x; bi[i] = sw ? x : z;
+            }
+        } else if (p != k) {
+            double x = br[k]; br[k] = br[p]; br[p] = x;
+            x = bi[k]; bi[k] = bi[p]; bi[p] = x;
+        }
+    }
+#pragma unroll U
+    for (int i = 1; i < N; ++i) {
+        double sr = br[i], si = bi[i];
+#pragma unroll U
+        for (int j = 0; j < i; ++j) {
+            const double lr = ar[i * N + j], li = ai[i * N + j];
+            sr = fma(li, bi[j], fma(-lr, br[j], sr));
+            si = fma(-li, br[j], fma(-lr, bi[j], si));
+        }
+        br[i] = sr; bi[i] = si;
+    }
+#pragma unroll U
+    for (int i = N - 1; i >= 0; --i) {
+        double sr = br[i], si = bi[i];
+#pragma unroll U
+        for (int j = i + 1; j < N; ++j) {
+            const double ur = ar[i * N + j], ui = ai[i * N + j];
+            sr = fma(ui, bi[j], fma(-ur, br[j], sr));
+            si = fma(-ui, br[j], fma(-ur, bi[j], si));
+        }
+        const double dr = ar[i * N + i], di = ai[i * N + i];   // reciprocal pivot
+        br[i] = fma(sr, dr, -si * di);
+        bi[i] = fma(sr, di, si * dr);
+    }
+}
+
+}  // namespace b200dae

@@ -1,0 +1,120 @@
+// fd_jacobian.cuh — forward-difference Jacobians Jy = dF/dy, Jyp = dF/dy' with per-column
+// adaptive step factors carried across the whole solve.
+//
+// Replaces jac_wrapped (base.py:264-295), which calls scipy's num_jac / _dense_num_jac twice
+// (scipy/integrate/_ivp/common.py:268-382) with threshold = atol / rtol (base.py:277):
+//   f_sign = +1 where f >= 0 else -1 (indexed like the perturbed variable);
+//   y_scale = f_sign * max(threshold, |x|);  h = (x + factor*y_scale) - x;  factor *= 10 while h == 0;
+//   column: diff = F(x + h e_i) - f;  max_ind = argmax|diff|;  scale = max(|f[max_ind]|, |f_new[max_ind]|);
+//   if max_diff < EPS^0.875 * scale: retry with 10*factor, keep it if max_diff*scale_new < max_diff_new*scale;
+//   J[:, i] = diff / h;  factor *= 10 if max_diff < EPS^0.75*scale;  factor *= 0.1 if max_diff > EPS^0.25*scale;
+//   factor = max(factor, 1e3*EPS).
+// The FD residual evaluations are not counted in nfev (base.py:83-87,267).
+#pragma once
+#include "dense_lu.cuh"
+
+namespace b200dae {
+
+constexpr double kEps = 2.220446049250313e-16;
+constexpr double kNjDiffReject = 2.0194839173657902e-14;   // EPS ** 0.875
+constexpr double kNjDiffSmall = 1.8189894035458565e-12;    // EPS ** 0.75
+constexpr double kNjDiffBig = 1.220703125e-04;             // EPS ** 0.25
+constexpr double kNjMinFactor = 1e3 * kEps;
+constexpr double kNjInitFactor = 1.4901161193847656e-08;   // EPS ** 0.5
+
+// One column of the difference quotient.  `x` is y or yp (the perturbed vector), `col` the
+// column, `xp` the perturbed entry.  Returns max_diff and scale (NaN-propagating like
+// np.argmax / np.maximum).
+template <class P>
+__device__ __forceinline__ void fd_column(double t, double* __restrict__ y, double* __restrict__ yp,
+                                          const double* __restrict__ p, const double* __restrict__ f,
+                                          bool wrt_yp, int col, double xp,
+                                          double* __restrict__ diff, double& max_diff, double& scale) {
+    constexpr int N = P::N;
+    constexpr int U = Regime<N>::kUnroll;
+    double fnew[N];
+    if constexpr (Regime<N>::kReg) {
+        double yy[N], yyp[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            yy[j] = (!wrt_yp && j == col) ? xp : y[j];
+            yyp[j] = (wrt_yp && j == col) ? xp : yp[j];
+        }
+        P::eval(t, yy, yyp, p, fnew);
+    } else {
+        double* x = wrt_yp ? yp : y;
+        const double saved = x[col];
+        x[col] = xp;
+        P::eval(t, y, yp, p, fnew);
+        x[col] = saved;
+    }
+    double best = -1.0, f_at = 0.0, fn_at = 0.0, d_at = 0.0;
+#pragma unroll U
+    for (int r = 0; r < N; ++r) {
+        const double dr = fnew[r] - f[r];
+        diff[r] = dr;
+        const double a = fabs(dr);
+        if (a > best || (a != a && best == best)) { best = a; f_at = f[r]; fn_at = fnew[r]; d_at = dr; }
+    }
+    max_diff = fabs(d_at);
+    scale = fmax(fabs(f_at), fabs(fn_at));
+    if (f_at != f_at || fn_at != fn_at) scale = nan("");
+}
+
+// Jy and Jyp (row-major N*N) at (t, y, yp).  thr[i] = atol[i] / rtol.
+template <class P>
+__device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, double* __restrict__ yp,
+                                            const double* __restrict__ p, const double* __restrict__ thr,
+                                            double* __restrict__ factor_y, double* __restrict__ factor_yp,
+                                            double* __restrict__ Jy, double* __restrict__ Jyp) {
+    constexpr int N = P::N;
+    constexpr int U = Regime<N>::kUnroll;
+    double f[N];
+    P::eval(t, y, yp, p, f);
+#pragma unroll U
+    for (int which = 0; which < 2; ++which) {
+        const bool wrt_yp = (which == 1);
+        const double* x = wrt_yp ? yp : y;
+        double* factor = wrt_yp ? factor_yp : factor_y;
+        double* J = wrt_yp ? Jyp : Jy;
+#pragma unroll U
+        for (int i = 0; i < N; ++i) {
+            const double xi = x[i];
+            const double f_sign = (f[i] >= 0.0) ? 1.0 : -1.0;
+            const double y_scale = f_sign * fmax(thr[i], fabs(xi));
+            double fac = factor[i];
+            double xp = fma(fac, y_scale, xi);
+            double h = xp - xi;
+            while (h == 0.0) {
+                fac *= 10.0;
+                xp = fma(fac, y_scale, xi);
+                h = xp - xi;
+            }
+            double diff[N], max_diff, scale;
+            fd_column<P>(t, y, yp, p, f, wrt_yp, i, xp, diff, max_diff, scale);
+            if (max_diff < kNjDiffReject * scale) {
+                const double new_fac = 10.0 * fac;
+                const double xp2 = fma(new_fac, y_scale, xi);
+                const double h_new = xp2 - xi;
+                double diff2[N], max_diff_new, scale_new;
+                fd_column<P>(t, y, yp, p, f, wrt_yp, i, xp2, diff2, max_diff_new, scale_new);
+                if (max_diff * scale_new < max_diff_new * scale) {
+                    fac = new_fac;
+                    h = h_new;
+#pragma unroll U
+                    for (int r = 0; r < N; ++r) diff[r] = diff2[r];
+                    scale = scale_new;
+                    max_diff = max_diff_new;
+                }
+            }
+            const double rh = 1.0 / h;
+#pragma unroll U
+            for (int r = 0; r < N; ++r) J[r * N + i] = diff[r] * rh;
+            if (max_diff < kNjDiffSmall * scale) fac *= 10.0;
+            if (max_diff > kNjDiffBig * scale) fac *= 0.1;
+            factor[i] = fmax(fac, kNjMinFactor);
+        }
+    }
+}
+
+}  // namespace b200dae

@@ -1,0 +1,206 @@
+// problems.cuh — residuals F(t, y, y'; p) = 0 as device functors.
+//
+// Replaces the Python callable `fun(t, y, yp, *args)` of the reference (base.py:44-45,
+// dae.py:365-383).  Twins: scipy_dae_b200/problems.py (NumPy, drives the unmodified reference
+// when goldens are minted) and oracle/problems.c (CPU oracle).  Definitions: SURVEY.md App. D
+// (reference README.md:37-47, examples/daes/akzo_nobel.py:18-50, examples/daes/andrews.py:20-225;
+// "transamp" is the IVP-test-set two-transistor amplifier).
+//
+// A functor provides  N (state size), NP (parameters per instance), name, and
+//   static __device__ void eval(double t, const double* y, const double* yp, const double* p, double* out)
+// All indexing is static so that, after inlining into a fully unrolled caller, every array
+// lives in registers.
+#pragma once
+#include <math.h>
+
+namespace b200dae {
+
+struct Robertson {
+    static constexpr int N = 3, NP = 3;
+    static constexpr const char* name() { return "robertson"; }
+    // flops of one residual as written (for the roofline model): 15
+    static constexpr int kFlops = 15;
+    __device__ __forceinline__ static void eval(double, const double* y, const double* yp,
+                                                const double* p, double* out) {
+        const double k1 = p[0], k2 = p[1], k3 = p[2];
+        const double r23 = k2 * y[1] * y[2];
+        out[0] = yp[0] - (-k1 * y[0] + r23);
+        out[1] = yp[1] - (k1 * y[0] - r23 - k3 * y[1] * y[1]);
+        out[2] = y[0] + y[1] + y[2] - 1.0;
+    }
+};
+
+struct AkzoNobel {
+    static constexpr int N = 6, NP = 7;
+    static constexpr const char* name() { return "akzo_nobel"; }
+    static constexpr int kFlops = 52;
+    __device__ __forceinline__ static void eval(double, const double* y, const double* yp,
+                                                const double* p, double* out) {
+        const double po2 = 0.9, hen = 737.0;
+        const double k1 = p[0], k2 = p[1], k3 = p[2], k4 = p[3], kbig = p[4], kla = p[5], ks = p[6];
+        const double sq = sqrt(y[1]);            // NaN for negative trial iterates: Newton treats it
+        const double y0sq = y[0] * y[0];         // as non-convergence (radau.py:157-158, bdf.py:41-42)
+        const double r1 = k1 * (y0sq * y0sq) * sq;
+        const double r2 = k2 * y[2] * y[3];
+        const double r3 = k2 / kbig * y[0] * y[4];
+        const double r4 = k3 * y[0] * (y[3] * y[3]);
+        const double r5 = k4 * (y[5] * y[5]) * sq;
+        const double fin = kla * (po2 / hen - y[1]);
+        out[0] = yp[0] - (-2.0 * r1 + r2 - r3 - r4);
+        out[1] = yp[1] - (-0.5 * r1 - r4 - 0.5 * r5 + fin);
+        out[2] = yp[2] - (r1 - r2 + r3);
+        out[3] = yp[3] - (-r2 + r3 - 2.0 * r4);
+        out[4] = yp[4] - (r2 - r3 + r5);
+        out[5] = -(ks * y[0] * y[3] - y[5]);
+    }
+};
+
+struct Transamp {
+    static constexpr int N = 8, NP = 3;
+    static constexpr const char* name() { return "transamp"; }
+    static constexpr int kFlops = 75;
+    __device__ __forceinline__ static void eval(double t, const double* y, const double* yp,
+                                                const double* p, double* out) {
+        const double UF = 0.026, ALPHA = 0.99, R = 9000.0;
+        const double C1 = 1e-6, C2 = 2e-6, C3 = 3e-6, C4 = 4e-6, C5 = 5e-6;
+        const double Ub = p[0], R0 = p[1], beta = p[2];
+        const double Ue = 0.1 * sin(200.0 * 3.14159265358979323846 * t);
+        const double g23 = beta * (exp((y[1] - y[2]) / UF) - 1.0);
+        const double g56 = beta * (exp((y[4] - y[5]) / UF) - 1.0);
+        const double f0 = -Ue / R0 + y[0] / R0;
+        const double f1 = -Ub / R + y[1] * (2.0 / R) - (ALPHA - 1.0) * g23;
+        const double f2 = -g23 + y[2] / R;
+        const double f3 = -Ub / R + y[3] / R + ALPHA * g23;
+        const double f4 = -Ub / R + y[4] * (2.0 / R) - (ALPHA - 1.0) * g56;
+        const double f5 = -g56 + y[5] / R;
+        const double f6 = -Ub / R + y[6] / R + ALPHA * g56;
+        const double f7 = y[7] / R;
+        out[0] = (-C1 * yp[0] + C1 * yp[1]) - f0;
+        out[1] = (C1 * yp[0] - C1 * yp[1]) - f1;
+        out[2] = (-C2 * yp[2]) - f2;
+        out[3] = (-C3 * yp[3] + C3 * yp[4]) - f3;
+        out[4] = (C3 * yp[3] - C3 * yp[4]) - f4;
+        out[5] = (-C4 * yp[5]) - f5;
+        out[6] = (-C5 * yp[6] + C5 * yp[7]) - f6;
+        out[7] = (C5 * yp[6] - C5 * yp[7]) - f7;
+    }
+};
+
+// Andrews' squeezer, stabilised index-1 form, n = 26: y = (q[7], u[7], la[6], mu[6]),
+// yp = (q'[7], u'[7], lambda[6], mu-multipliers[6]); p = (mom, c0).
+struct Andrews {
+    static constexpr int N = 26, NP = 2;
+    static constexpr const char* name() { return "andrews"; }
+    static constexpr int kFlops = 520;
+    __device__ __noinline__ static void eval(double, const double* y, const double* yp,
+                                             const double* p, double* out) {
+        const double m1 = 0.04325, m2 = 0.00365, m3 = 0.02373, m4 = 0.00706, m5 = 0.07050,
+                     m6 = 0.00706, m7 = 0.05498;
+        const double I1 = 2.194e-6, I2 = 4.410e-7, I3 = 5.255e-6, I4 = 5.667e-7, I5 = 1.169e-5,
+                     I6 = 5.667e-7, I7 = 1.912e-5;
+        const double xa = -0.06934, ya = -0.00227, xb = -0.03635, yb = 0.03273, xc = 0.014,
+                     yc = 0.072;
+        const double d = 0.028, da = 0.0115, e = 0.02, ea = 0.01421, zf = 0.02, fa = 0.01421;
+        const double rr = 0.007, ra = 0.00092, ss = 0.035, sa = 0.01874, sb = 0.01043, sc = 0.018;
+        const double sd = 0.02, zt = 0.04, ta = 0.02308, tb = 0.00916, u = 0.04, ua = 0.01228,
+                     ub = 0.00449, l0 = 0.07785;
+        const double mom = p[0], c0 = p[1];
+        const double* q = y;
+        const double* v = y + 7;
+        const double* qd = yp;
+        const double* vd = yp + 7;
+        const double* la = yp + 14;
+        const double* mu = yp + 20;
+
+        double sin_be, cos_be, sin_Th, cos_Th, sin_ga, cos_ga, sin_Phi, cos_Phi, sin_de, cos_de,
+            sin_Om, cos_Om, sin_ep, cos_ep, sin_be_Th, cos_be_Th, sin_Ph_de, cos_Ph_de, sin_Om_ep,
+            cos_Om_ep;
+        sincos(q[0], &sin_be, &cos_be);
+        sincos(q[1], &sin_Th, &cos_Th);
+        sincos(q[2], &sin_ga, &cos_ga);
+        sincos(q[3], &sin_Phi, &cos_Phi);
+        sincos(q[4], &sin_de, &cos_de);
+        sincos(q[5], &sin_Om, &cos_Om);
+        sincos(q[6], &sin_ep, &cos_ep);
+        sincos(q[0] + q[1], &sin_be_Th, &cos_be_Th);
+        sincos(q[3] + q[4], &sin_Ph_de, &cos_Ph_de);
+        sincos(q[5] + q[6], &sin_Om_ep, &cos_Om_ep);
+
+        const double M00 = m1 * ra * ra + m2 * (rr * rr - 2 * da * rr * cos_Th + da * da) + I1 + I2;
+        const double M01 = m2 * (da * da - da * rr * cos_Th) + I2;
+        const double M11 = m2 * da * da + I2;
+        const double M22 = m3 * (sa * sa + sb * sb) + I3;
+        const double M33 = m4 * (e - ea) * (e - ea) + I4;
+        const double M34 = m4 * ((e - ea) * (e - ea) + zt * (e - ea) * sin_Phi) + I4;
+        const double M44 = m4 * (zt * zt + 2 * zt * (e - ea) * sin_Phi + (e - ea) * (e - ea)) +
+                           m5 * (ta * ta + tb * tb) + I4 + I5;
+        const double M55 = m6 * (zf - fa) * (zf - fa) + I6;
+        const double M56 = m6 * ((zf - fa) * (zf - fa) - u * (zf - fa) * sin_Om) + I6;
+        const double M66 = m6 * ((zf - fa) * (zf - fa) - 2 * u * (zf - fa) * sin_Om + u * u) +
+                           m7 * (ua * ua + ub * ub) + I6 + I7;
+
+        const double xd = sd * cos_ga + sc * sin_ga + xb;
+        const double yd = sd * sin_ga - sc * cos_ga + yb;
+        const double L = sqrt((xd - xc) * (xd - xc) + (yd - yc) * (yd - yc));
+        const double Fs = -c0 * (L - l0) / L;
+        const double Fx = Fs * (xd - xc), Fy = Fs * (yd - yc);
+        const double h0 = mom - m2 * da * rr * v[1] * (v[1] + 2 * v[0]) * sin_Th;
+        const double h1 = m2 * da * rr * v[0] * v[0] * sin_Th;
+        const double h2 = Fx * (sc * cos_ga - sd * sin_ga) + Fy * (sd * cos_ga + sc * sin_ga);
+        const double h3 = m4 * zt * (e - ea) * v[4] * v[4] * cos_Phi;
+        const double h4 = -m4 * zt * (e - ea) * v[3] * (v[3] + 2 * v[4]) * cos_Phi;
+        const double h5 = -m6 * u * (zf - fa) * v[6] * v[6] * cos_Om;
+        const double h6 = m6 * u * (zf - fa) * v[5] * (v[5] + 2 * v[6]) * cos_Om;
+
+        // constraint Jacobian G = g_q (6 x 7), only its structural non-zeros
+        const double a0 = -rr * sin_be + d * sin_be_Th, a1 = d * sin_be_Th;
+        const double b0 = rr * cos_be - d * cos_be_Th, b1 = -d * cos_be_Th;
+        const double G02 = -ss * cos_ga, G12 = -ss * sin_ga;
+        const double G23 = -e * cos_Ph_de, G24 = -e * cos_Ph_de + zt * sin_de;
+        const double G33 = -e * sin_Ph_de, G34 = -e * sin_Ph_de - zt * cos_de;
+        const double G45 = zf * sin_Om_ep, G46 = zf * sin_Om_ep - u * cos_ep;
+        const double G55 = -zf * cos_Om_ep, G56 = -zf * cos_Om_ep - u * sin_ep;
+
+        // G^T w for w = mu and w = la
+        const double smu_a = mu[0] + mu[2] + mu[4], smu_b = mu[1] + mu[3] + mu[5];
+        const double sla_a = la[0] + la[2] + la[4], sla_b = la[1] + la[3] + la[5];
+        const double gtm0 = a0 * smu_a + b0 * smu_b, gtl0 = a0 * sla_a + b0 * sla_b;
+        const double gtm1 = a1 * smu_a + b1 * smu_b, gtl1 = a1 * sla_a + b1 * sla_b;
+        const double gtm2 = G02 * mu[0] + G12 * mu[1], gtl2 = G02 * la[0] + G12 * la[1];
+        const double gtm3 = G23 * mu[2] + G33 * mu[3], gtl3 = G23 * la[2] + G33 * la[3];
+        const double gtm4 = G24 * mu[2] + G34 * mu[3], gtl4 = G24 * la[2] + G34 * la[3];
+        const double gtm5 = G45 * mu[4] + G55 * mu[5], gtl5 = G45 * la[4] + G55 * la[5];
+        const double gtm6 = G46 * mu[4] + G56 * mu[5], gtl6 = G46 * la[4] + G56 * la[5];
+
+        out[0] = qd[0] - v[0] + gtm0;
+        out[1] = qd[1] - v[1] + gtm1;
+        out[2] = qd[2] - v[2] + gtm2;
+        out[3] = qd[3] - v[3] + gtm3;
+        out[4] = qd[4] - v[4] + gtm4;
+        out[5] = qd[5] - v[5] + gtm5;
+        out[6] = qd[6] - v[6] + gtm6;
+        out[7] = (M00 * vd[0] + M01 * vd[1]) - h0 - gtl0;
+        out[8] = (M01 * vd[0] + M11 * vd[1]) - h1 - gtl1;
+        out[9] = (M22 * vd[2]) - h2 - gtl2;
+        out[10] = (M33 * vd[3] + M34 * vd[4]) - h3 - gtl3;
+        out[11] = (M34 * vd[3] + M44 * vd[4]) - h4 - gtl4;
+        out[12] = (M55 * vd[5] + M56 * vd[6]) - h5 - gtl5;
+        out[13] = (M56 * vd[5] + M66 * vd[6]) - h6 - gtl6;
+        const double ab0 = a0 * v[0] + a1 * v[1], ab1 = b0 * v[0] + b1 * v[1];
+        out[14] = ab0 + G02 * v[2];
+        out[15] = ab1 + G12 * v[2];
+        out[16] = ab0 + G23 * v[3] + G24 * v[4];
+        out[17] = ab1 + G33 * v[3] + G34 * v[4];
+        out[18] = ab0 + G45 * v[5] + G46 * v[6];
+        out[19] = ab1 + G55 * v[5] + G56 * v[6];
+        const double gc = rr * cos_be - d * cos_be_Th, gs = rr * sin_be - d * sin_be_Th;
+        out[20] = gc - ss * sin_ga - xb;
+        out[21] = gs + ss * cos_ga - yb;
+        out[22] = gc - e * sin_Ph_de - zt * cos_de - xa;
+        out[23] = gs + e * cos_Ph_de - zt * sin_de - ya;
+        out[24] = gc - zf * cos_Om_ep - u * sin_ep - xa;
+        out[25] = gs - zf * sin_Om_ep + u * cos_ep - ya;
+    }
+};
+
+}  // namespace b200dae

@@ -1,0 +1,513 @@
+// radau.cuh — the whole adaptive Radau IIA integration of one system per thread.
+//
+// One launch replaces, for N independent instances, RadauDAE.__init__ (radau.py:393-463,
+// base.py:160-242), the `while status is None: solver.step()` loop of solve_dae with its t_eval
+// slicing (dae.py:446-518) and RadauDAE._step_impl (radau.py:465-659) with everything below it:
+// solve_collocation_system (radau.py:137-195), predict_factor (radau.py:198-240), the FD Jacobian
+// (fd_jacobian.cuh), the real + complex LUs (dense_lu.cuh), the embedded error estimate
+// (radau.py:568-594) and the collocation-polynomial dense output (radau.py:661-699).
+//
+// Control flow.  The reference nests four loops (steps > attempts > Jacobian refresh > Newton).
+// Here the three outer ones are flattened into ONE loop whose trip is "one simplified-Newton
+// solve", with the FD Jacobian, the LU factorisations, the error estimate and the accept phase
+// each appearing at exactly one code site, guarded by per-lane flags.  Lanes of a warp that are
+// at different points of their own step sequence (a halved step here, a Jacobian refresh there)
+// therefore still execute the same phase code together instead of serialising through
+// different call sites; only the trip counts differ.  Every quirk of the reference that moves
+// step sequences is kept and marked "quirk".
+#pragma once
+#include <stdint.h>
+#include "../../include/b200dae.h"
+#include "fd_jacobian.cuh"
+
+namespace b200dae {
+
+struct RadauLaunch {
+    b200dae_radau_tables tb;
+    double t0, t_bound, dir;
+    double rtol, max_step, first_step;
+    double cew;                 // continuous_error_weight
+    double jac_rate, db_lo, db_hi;
+    double newton_tol;
+    double atol[B200DAE_MAX_N];
+    double thr[B200DAE_MAX_N];  // atol / rtol (num_jac threshold, base.py:277)
+    int32_t newton_max_iter, newton_iter_embedded;
+    int64_t max_steps;
+    int64_t N, ld;
+    const double *y0, *yp0, *params;
+    b200dae_outputs out;
+};
+
+__device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
+
+__device__ __forceinline__ double powi(double x, int k) {   // x ** k for small k >= 0
+    double r = 1.0;
+    for (int i = 0; i < k; ++i) r *= x;
+    return r;
+}
+
+// predict_factor, radau.py:198-240 (KAPPA = 1).  inv_sp1 = 1 / (s + 1).
+template <int S>
+__device__ __forceinline__ double root_sp1(double x) {      // x ** (1 / (S + 1))
+    if constexpr (S == 3) return sqrt(sqrt(x));
+    else if constexpr (S == 7) return sqrt(sqrt(sqrt(x)));
+    else return pow(x, 1.0 / (S + 1));
+}
+
+template <int S>
+__device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old, double err,
+                                                 double err_old, bool have_old) {
+    double mult = 1.0;
+    if (have_old && err != 0.0) mult = h_abs / h_abs_old * root_sp1<S>(err_old / err);
+    const double factor = fmin(1.0, mult) / root_sp1<S>(err);   // err == 0 -> inf -> 1 + pi/2
+    return 1.0 + atan(factor - 1.0);
+}
+
+template <class P, int S, int kThreads>
+__global__ void __launch_bounds__(kThreads)
+radau_kernel(const __grid_constant__ RadauLaunch L) {
+    constexpr int N = P::N, NP = P::NP, NCS = S / 2;
+    constexpr int U = Regime<N>::kUnroll;
+    const int64_t inst = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (inst >= L.N) return;
+    const int64_t ld = L.ld;
+    const b200dae_radau_tables& tb = L.tb;
+
+    // ---- per-instance state -------------------------------------------------------------
+    double p[NP > 0 ? NP : 1], y[N], yp[N];
+#pragma unroll U
+    for (int j = 0; j < NP; ++j) p[j] = L.params[j * ld + inst];
+#pragma unroll U
+    for (int j = 0; j < N; ++j) { y[j] = L.y0[j * ld + inst]; yp[j] = L.yp0[j * ld + inst]; }
+
+    double Jy[N * N], Jyp[N * N], factor_y[N], factor_yp[N];
+    double LUr[N * N], LUcr[NCS > 0 ? NCS : 1][N * N], LUci[NCS > 0 ? NCS : 1][N * N];
+    int pivr[N], pivc[NCS > 0 ? NCS : 1][N];
+    double Y[S][N], Yp[S][N], W[S][N], G[S][N];
+    double ZP[N][S];                 // dense output of the last accepted step
+    double inv_scale[N];
+#pragma unroll U
+    for (int j = 0; j < N; ++j) factor_y[j] = factor_yp[j] = kNjInitFactor;
+
+    const double dir = L.dir, rtol = L.rtol;
+    double t = L.t0, t_old = L.t0, h_old = 1.0;
+    // select_initial_step, common.py:129-183 (or first_step, base.py:172-176)
+    double h_abs;
+    if (L.first_step > 0.0) {
+        h_abs = L.first_step;
+    } else {
+        double e = 0.0;
+#pragma unroll U
+        for (int j = 0; j < N; ++j) {
+            const double v = fabs(yp[j] / fmax(fabs(y[j]), L.thr[j]));
+            if (v > e || v != v) e = v;
+        }
+        const double rh = e / sqrt(rtol) / 0.8;
+        h_abs = fmin(L.max_step, fabs(L.t_bound - L.t0));
+        if (h_abs * rh > 1.0) h_abs = 1.0 / rh;
+        h_abs = fmax(h_abs, 16.0 * kEps * fabs(L.t0));
+    }
+    double h_abs_old = 0.0, err_old = 0.0;
+    bool have_old = false, have_sol = false;
+    bool need_jac = true;            // first Jacobian in the constructor, base.py:297
+    bool current_jac = true;         // radau.py:460 (quirk 7)
+    bool lu_valid = false, step_begin = true, retry = false;
+    int32_t nfev = 0, njev = 0, nlu = 0, nsolve = 0, nacc = 0, nrej = 0, nfail = 0, niter = 0;
+    int32_t status = B200DAE_ST_RUNNING;
+    int64_t ie = 0;                  // next t_eval index
+    int32_t nst = 0;                 // rows written to the step trace
+    const int newton_max_iter = L.newton_max_iter;
+
+    if (L.out.t_steps != nullptr && L.out.steps_cap > 0) {
+        L.out.t_steps[inst] = t;
+#pragma unroll U
+        for (int j = 0; j < N; ++j) {
+            if (L.out.y_steps) L.out.y_steps[j * ld + inst] = y[j];
+            if (L.out.yp_steps) L.out.yp_steps[j * ld + inst] = yp[j];
+        }
+        nst = 1;
+    }
+    if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; need_jac = false; njev = 1; }  // base.py:376-381
+
+    // per-step locals that survive across attempts of the same step
+    double hl = 0.0, hl_old = 0.0, errl_old = 0.0, min_step = 0.0, factor = 0.0;
+    double h = 0.0, t_new = 0.0;
+    bool havel_old = false, have_factor = false;
+
+    while (status == B200DAE_ST_RUNNING) {
+        // ---- phase J: finite-difference Jacobian at the current (t, y, yp) ----------------
+        if (need_jac) {
+            fd_jacobian<P>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
+            ++njev;
+            need_jac = false;
+        }
+        // ---- phase B: a new step begins (radau.py:489-512) --------------------------------
+        if (step_begin) {
+            min_step = 10.0 * fabs(nextafter(t, dir * INFINITY) - t);
+            if (h_abs > L.max_step) { hl = L.max_step; havel_old = false; }
+            else if (h_abs < min_step) { hl = min_step; havel_old = false; }
+            else { hl = h_abs; havel_old = have_old; }
+            hl_old = h_abs_old; errl_old = err_old;
+            have_factor = false;
+            step_begin = false;
+        }
+        // ---- phase A: a new attempt (radau.py:514-532); skipped on a Jacobian-refresh retry,
+        //      which restarts Newton from the FAILED iterate (quirk 1: Yp0 is aliased) ---------
+        if (!retry) {
+            if (hl < min_step) { status = B200DAE_ST_TOO_SMALL_STEP; break; }
+            h = hl * dir;
+            t_new = t + h;
+            if (dir * (t_new - L.t_bound) > 0.0) t_new = L.t_bound;
+            h = t_new - t;
+            hl = fabs(h);
+            if (!have_sol) {
+#pragma unroll U
+                for (int i = 0; i < S; ++i)
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) Yp[i][j] = yp[j];
+            } else {
+                // extrapolate the previous collocation polynomial's derivative (radau.py:531,693)
+                const double rho = 1.0 / h_old;
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const double x = (fma(h, tb.C[i], t) - t_old) * rho;
+                    double w[S];
+                    double xk = rho;
+#pragma unroll
+                    for (int k = 0; k < S; ++k) { w[k] = (k + 1) * xk; xk *= x; }
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < S; ++k) acc = fma(ZP[j][k], w[k], acc);
+                        Yp[i][j] = acc;
+                    }
+                }
+            }
+#pragma unroll U
+            for (int j = 0; j < N; ++j) inv_scale[j] = 1.0 / fma(fabs(y[j]), rtol, L.atol[j]);
+        }
+        retry = false;
+
+        // ---- phase F: iteration matrices and their LUs (radau.py:536-538) --------------------
+        if (!lu_valid) {
+            bool fin = true;
+            const double cr = h * tb.mu_real;
+#pragma unroll U
+            for (int k = 0; k < N * N; ++k) {
+                const double v = fma(cr, Jy[k], Jyp[k]);
+                fin = fin && finite_d(v);
+                LUr[k] = v;
+            }
+#pragma unroll
+            for (int c = 0; c < NCS; ++c) {
+                const double mr = h * tb.mu_re[c], mi = h * tb.mu_im[c];
+#pragma unroll U
+                for (int k = 0; k < N * N; ++k) {
+                    const double vr = fma(mr, Jy[k], Jyp[k]), vi = mi * Jy[k];
+                    fin = fin && finite_d(vr) && finite_d(vi);
+                    LUcr[c][k] = vr;
+                    LUci[c][k] = vi;
+                }
+            }
+            if (!fin) { status = B200DAE_ST_NONFINITE; break; }   // lu_factor(check_finite=True) raises
+            lu_factor<N>(LUr, pivr);
+#pragma unroll
+            for (int c = 0; c < NCS; ++c) zlu_factor<N>(LUcr[c], LUci[c], pivc[c]);
+            nlu += 1 + NCS;
+            lu_valid = true;
+        }
+
+        // ---- phase N: simplified Newton on the stage derivatives (radau.py:137-195) ----------
+        bool converged = false, have_rate = false;
+        double rate = 0.0;
+        int n_iter = 0;
+        {
+#pragma unroll
+            for (int i = 0; i < S; ++i)
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < S; ++l) acc = fma(tb.A[i * S + l], Yp[l][j], acc);
+                    Y[i][j] = fma(h, acc, y[j]);
+                }
+            double dY_norm_old = 0.0;
+            bool has_old = false;
+            int k = 0;
+            for (; k < newton_max_iter; ++k) {
+                bool fin = true;
+#pragma unroll U
+                for (int i = 0; i < S; ++i) {
+                    P::eval(fma(h, tb.C[i], t), Y[i], Yp[i], p, W[i]);
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) fin = fin && finite_d(W[i][j]);
+                }
+                nfev += S;
+                if (!fin) break;                                   // radau.py:157-158
+                // G = -(TI @ F); real block, then the complex blocks (radau.py:160-174)
+#pragma unroll
+                for (int i = 0; i < S; ++i)
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < S; ++l) acc = fma(tb.TI[i * S + l], W[l][j], acc);
+                        G[i][j] = -acc;
+                    }
+                lu_solve<N>(LUr, pivr, G[0]);
+#pragma unroll
+                for (int c = 0; c < NCS; ++c)
+                    zlu_solve<N>(LUcr[c], LUci[c], pivc[c], G[2 * c + 1], G[2 * c + 2]);
+                nsolve += 1 + NCS;
+                // dYp = T @ dW; Yp += dYp   (radau.py:176,179)
+#pragma unroll
+                for (int i = 0; i < S; ++i)
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < S; ++l) acc = fma(tb.T[i * S + l], G[l][j], acc);
+                        W[i][j] = acc;
+                        Yp[i][j] += acc;
+                    }
+                // dY = h * A @ dYp; Y += dY; ||dY / scale||_rms over all s*n entries (radau.py:177-182)
+                double ss = 0.0;
+#pragma unroll
+                for (int i = 0; i < S; ++i)
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int l = 0; l < S; ++l) acc = fma(tb.A[i * S + l], W[l][j], acc);
+                        const double dY = h * acc;
+                        Y[i][j] += dY;
+                        const double q = dY * inv_scale[j];
+                        ss = fma(q, q, ss);
+                    }
+                const double dY_norm = sqrt(ss * (1.0 / (S * N)));
+                if (has_old) { rate = dY_norm / dY_norm_old; have_rate = true; }
+                // quirk 2: the rate test breaks AFTER the update was applied
+                if (have_rate && (rate >= 1.0 ||
+                                  powi(rate, newton_max_iter - k) / (1.0 - rate) * dY_norm > L.newton_tol))
+                    break;
+                if (dY_norm == 0.0 || (have_rate && rate / (1.0 - rate) * dY_norm < L.newton_tol)) {
+                    converged = true;
+                    break;
+                }
+                dY_norm_old = dY_norm;
+                has_old = true;
+            }
+            n_iter = (k == newton_max_iter) ? newton_max_iter : k + 1;
+            niter += n_iter;
+        }
+        if (!converged) {
+            ++nfail;
+            if (!current_jac) {                    // radau.py:545-552: refresh J at the step START
+                need_jac = true;
+                current_jac = true;
+                lu_valid = false;
+                retry = true;
+                continue;
+            }
+            hl *= 0.5;                             // radau.py:554-558
+            lu_valid = false;
+            continue;
+        }
+
+        // ---- phase E: embedded error estimate (radau.py:560-596) ---------------------------
+        double err[N];
+        {
+            const int emb = L.newton_iter_embedded;
+            if (emb == 1) {
+                // implicit embedded method, one Newton iteration
+                double yph[N];
+                const double rmu = 1.0 / tb.mu_real;
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < S; ++l) acc = fma(tb.v_implicit[l], Yp[l][j], acc);
+                    yph[j] = (acc - tb.b_hat1_implicit * yp[j]) * rmu;
+                }
+                P::eval(t_new, Y[S - 1], yph, p, err);
+                ++nfev;
+                bool fin = true;
+#pragma unroll U
+                for (int j = 0; j < N; ++j) fin = fin && finite_d(err[j]);
+                if (!fin) { status = B200DAE_ST_NONFINITE; break; }   // lu_solve(check_finite) raises
+                lu_solve<N>(LUr, pivr, err);
+                ++nsolve;
+                const double sc = -h * tb.mu_real;
+#pragma unroll U
+                for (int j = 0; j < N; ++j) err[j] *= sc;
+            } else if (emb == 0) {
+                // explicit embedded method
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < S; ++l) acc = fma(tb.v_explicit[l], Yp[l][j], acc);
+                    err[j] = h * fma(tb.mu_real, yp[j], acc);
+                }
+            } else {
+                // implicit embedded method iterated `emb` times (radau.py:578-587)
+                double yh[N], yph0[N], yph[N];
+                const double rhm = 1.0 / (h * tb.mu_real);
+                bool fin = true;
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < S; ++l) acc = fma(tb.b_hat_implicit[l], Yp[l][j], acc);
+                    yph0[j] = -(y[j] / h + tb.b_hat1_implicit * yp[j] + acc) / tb.mu_real;
+                    yh[j] = Y[S - 1][j];
+                }
+                for (int it = 0; it < emb && fin; ++it) {
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) yph[j] = fma(yh[j], rhm, yph0[j]);
+                    P::eval(t_new, yh, yph, p, err);
+                    ++nfev;
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) fin = fin && finite_d(err[j]);
+                    if (!fin) break;
+                    lu_solve<N>(LUr, pivr, err);
+                    ++nsolve;
+#pragma unroll U
+                    for (int j = 0; j < N; ++j) yh[j] = fma(-h * tb.mu_real, err[j], yh[j]);
+                }
+                if (!fin) { status = B200DAE_ST_NONFINITE; break; }
+#pragma unroll U
+                for (int j = 0; j < N; ++j) err[j] = yh[j] - Y[S - 1][j];
+            }
+        }
+        double error_norm;
+        {
+            const double w = L.cew;
+            double ss = 0.0;
+#pragma unroll U
+            for (int j = 0; j < N; ++j) {
+                double e = (1.0 - w) * fabs(err[j]);
+                if (w != 0.0) {           // mix with the collocation error (radau.py:566,590-593)
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < S; ++l) acc = fma(tb.P2row0[l], Y[l][j], acc);
+                    e = fma(w, pow(fabs(y[j] - acc), (S + 1.0) / S), e);
+                }
+                const double sc = fma(fmax(fabs(y[j]), fabs(Y[S - 1][j])), rtol, L.atol[j]);
+                const double q = e / sc;
+                ss = fma(q, q, ss);
+            }
+            error_norm = sqrt(ss * (1.0 / N));
+        }
+        const double safety = 0.9 * (2 * newton_max_iter + 1) / (double)(2 * newton_max_iter + n_iter);
+
+        if (error_norm > 1.0) {                    // reject (radau.py:598-603); quirk 8: J is kept
+            factor = predict_factor<S>(hl, hl_old, error_norm, errl_old, havel_old);
+            have_factor = true;
+            hl *= safety * factor;
+            lu_valid = false;
+            ++nrej;
+            continue;
+        }
+
+        // ---- phase C: the step is accepted (radau.py:607-657) ---------------------------------
+        const bool recompute_jac = (n_iter > 2) && have_rate && (rate > L.jac_rate);   // quirk 6
+        // quirk 3: a factor left over from a rejected attempt is reused as is, without safety
+        if (!have_factor) factor = safety * predict_factor<S>(hl, hl_old, error_norm, errl_old, havel_old);
+        if (!recompute_jac && L.db_lo <= factor && factor <= L.db_hi) factor = 1.0;   // quirk 5: LUs kept
+        else lu_valid = false;
+        need_jac = recompute_jac;
+        current_jac = recompute_jac;
+        h_abs_old = h_abs;                         // quirk 4: the PRE-step proposal
+        err_old = error_norm;
+        have_old = true;
+        h_abs = hl * factor;
+
+        // dense output ZP = (Y - y_old).T @ P (radau.py:661-666)
+#pragma unroll U
+        for (int j = 0; j < N; ++j) {
+            double z[S];
+#pragma unroll
+            for (int l = 0; l < S; ++l) z[l] = Y[l][j] - y[j];
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < S; ++l) acc = fma(z[l], tb.P[l * S + k], acc);
+                ZP[j][k] = acc;
+            }
+        }
+        t_old = t;
+        h_old = h;
+        have_sol = true;
+
+        // t_eval points passed by this step (dae.py:496-515; RadauDenseOutput radau.py:681-699)
+        if (L.out.t_eval != nullptr) {
+            const double rho = 1.0 / h;
+            while (ie < L.out.m) {
+                const double te = __ldg(L.out.t_eval + ie);
+                if (!(dir > 0.0 ? te <= t_new : te >= t_new)) break;
+                const double x = (te - t) * rho;
+                double pw[S], dpw[S];
+                double xk = 1.0;
+#pragma unroll
+                for (int k = 0; k < S; ++k) { dpw[k] = (k + 1) * rho * xk; xk *= x; pw[k] = xk; }
+                double* ye = L.out.y_eval + ie * N * ld + inst;
+                double* ype = L.out.yp_eval ? L.out.yp_eval + ie * N * ld + inst : nullptr;
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    double a = 0.0, b = 0.0;
+#pragma unroll
+                    for (int k = 0; k < S; ++k) { a = fma(ZP[j][k], pw[k], a); b = fma(ZP[j][k], dpw[k], b); }
+                    ye[j * ld] = a + y[j];
+                    if (ype) ype[j * ld] = b;
+                }
+                ++ie;
+            }
+        }
+        // commit
+        t = t_new;
+#pragma unroll U
+        for (int j = 0; j < N; ++j) { y[j] = Y[S - 1][j]; yp[j] = Yp[S - 1][j]; }
+        ++nacc;
+        if (L.out.t_steps != nullptr && nst < L.out.steps_cap) {
+            L.out.t_steps[(int64_t)nst * ld + inst] = t;
+#pragma unroll U
+            for (int j = 0; j < N; ++j) {
+                if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + j) * ld + inst] = y[j];
+                if (L.out.yp_steps) L.out.yp_steps[((int64_t)nst * N + j) * ld + inst] = yp[j];
+            }
+            ++nst;
+        }
+        step_begin = true;
+        if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;            // base.py:389-390
+        else if (L.max_steps > 0 && nacc >= L.max_steps) status = B200DAE_ST_MAX_STEPS;
+        // the reference still evaluates the Jacobian after its last step (radau.py:628-630)
+        if (status != B200DAE_ST_RUNNING && need_jac) ++njev;
+    }
+
+    // ---- results ----------------------------------------------------------------------------
+#pragma unroll U
+    for (int j = 0; j < N; ++j) {
+        L.out.y_final[j * ld + inst] = y[j];
+        if (L.out.yp_final) L.out.yp_final[j * ld + inst] = yp[j];
+    }
+    L.out.t_final[inst] = t;
+    L.out.status[inst] = status;
+    if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
+    if (L.out.n_steps) L.out.n_steps[inst] = nst;
+    if (L.out.counters) {
+        int32_t* c = L.out.counters + inst;
+        c[B200DAE_CNT_NFEV * ld] = nfev;
+        c[B200DAE_CNT_NJEV * ld] = njev;
+        c[B200DAE_CNT_NLU * ld] = nlu;
+        c[B200DAE_CNT_NSOLVE * ld] = nsolve;
+        c[B200DAE_CNT_ACCEPTED * ld] = nacc;
+        c[B200DAE_CNT_ERR_REJECTED * ld] = nrej;
+        c[B200DAE_CNT_NEWTON_FAIL * ld] = nfail;
+        c[B200DAE_CNT_NEWTON_ITER * ld] = niter;
+    }
+}
+
+}  // namespace b200dae

@@ -160,6 +160,108 @@ def transamp_initial(params):
 
 
 # --------------------------------------------------------------------------- #
+# Andrews' squeezer, stabilised index-1 form (n = 26); p = (mom, c0)
+# --------------------------------------------------------------------------- #
+_AND = dict(
+    m1=0.04325, m2=0.00365, m3=0.02373, m4=0.00706, m5=0.07050, m6=0.00706, m7=0.05498,
+    I1=2.194e-6, I2=4.410e-7, I3=5.255e-6, I4=5.667e-7, I5=1.169e-5, I6=5.667e-7, I7=1.912e-5,
+    xa=-0.06934, ya=-0.00227, xb=-0.03635, yb=0.03273, xc=0.014, yc=0.072,
+    d=0.028, da=0.0115, e=0.02, ea=0.01421, zf=0.02, fa=0.01421,
+    rr=0.007, ra=0.00092, ss=0.035, sa=0.01874, sb=0.01043, sc=0.018,
+    sd=0.02, zt=0.04, ta=0.02308, tb=0.00916, u=0.04, ua=0.01228, ub=0.00449, l0=0.07785)
+
+ANDREWS_Q0 = np.array([
+    -0.0617138900142764496358948458001, 0.0, 0.455279819163070380255912382449,
+    0.222668390165885884674473185609, 0.487364979543842550225598953530,
+    -0.222668390165885884674473185609, 1.23054744454982119249735015568])
+
+
+def _andrews_terms(q, v, mom, c0):
+    """Mass matrix M(q), forces h(q, v), constraints g(q) and their Jacobian G(q) (6 x 7)."""
+    c = _AND
+    sin, cos = np.sin, np.cos
+    sbe, cbe = sin(q[0]), cos(q[0])
+    sth, cth = sin(q[1]), cos(q[1])
+    sga, cga = sin(q[2]), cos(q[2])
+    sph, cph = sin(q[3]), cos(q[3])
+    sde, cde = sin(q[4]), cos(q[4])
+    som, com = sin(q[5]), cos(q[5])
+    sep, cep = sin(q[6]), cos(q[6])
+    sbt, cbt = sin(q[0] + q[1]), cos(q[0] + q[1])
+    spd, cpd = sin(q[3] + q[4]), cos(q[3] + q[4])
+    soe, coe = sin(q[5] + q[6]), cos(q[5] + q[6])
+    eea, zfa = c["e"] - c["ea"], c["zf"] - c["fa"]
+
+    M = np.zeros((7, 7))
+    M[0, 0] = c["m1"] * c["ra"] ** 2 + c["m2"] * (c["rr"] ** 2 - 2 * c["da"] * c["rr"] * cth + c["da"] ** 2) + c["I1"] + c["I2"]
+    M[0, 1] = M[1, 0] = c["m2"] * (c["da"] ** 2 - c["da"] * c["rr"] * cth) + c["I2"]
+    M[1, 1] = c["m2"] * c["da"] ** 2 + c["I2"]
+    M[2, 2] = c["m3"] * (c["sa"] ** 2 + c["sb"] ** 2) + c["I3"]
+    M[3, 3] = c["m4"] * eea ** 2 + c["I4"]
+    M[3, 4] = M[4, 3] = c["m4"] * (eea ** 2 + c["zt"] * eea * sph) + c["I4"]
+    M[4, 4] = c["m4"] * (c["zt"] ** 2 + 2 * c["zt"] * eea * sph + eea ** 2) + c["m5"] * (c["ta"] ** 2 + c["tb"] ** 2) + c["I4"] + c["I5"]
+    M[5, 5] = c["m6"] * zfa ** 2 + c["I6"]
+    M[5, 6] = M[6, 5] = c["m6"] * (zfa ** 2 - c["u"] * zfa * som) + c["I6"]
+    M[6, 6] = c["m6"] * (zfa ** 2 - 2 * c["u"] * zfa * som + c["u"] ** 2) + c["m7"] * (c["ua"] ** 2 + c["ub"] ** 2) + c["I6"] + c["I7"]
+
+    xd = c["sd"] * cga + c["sc"] * sga + c["xb"]
+    yd = c["sd"] * sga - c["sc"] * cga + c["yb"]
+    L = np.sqrt((xd - c["xc"]) ** 2 + (yd - c["yc"]) ** 2)
+    Fs = -c0 * (L - c["l0"]) / L
+    Fx, Fy = Fs * (xd - c["xc"]), Fs * (yd - c["yc"])
+    h = np.array([
+        mom - c["m2"] * c["da"] * c["rr"] * v[1] * (v[1] + 2 * v[0]) * sth,
+        c["m2"] * c["da"] * c["rr"] * v[0] ** 2 * sth,
+        Fx * (c["sc"] * cga - c["sd"] * sga) + Fy * (c["sd"] * cga + c["sc"] * sga),
+        c["m4"] * c["zt"] * eea * v[4] ** 2 * cph,
+        -c["m4"] * c["zt"] * eea * v[3] * (v[3] + 2 * v[4]) * cph,
+        -c["m6"] * c["u"] * zfa * v[6] ** 2 * com,
+        c["m6"] * c["u"] * zfa * v[5] * (v[5] + 2 * v[6]) * com])
+
+    gc = c["rr"] * cbe - c["d"] * cbt
+    gs = c["rr"] * sbe - c["d"] * sbt
+    g = np.array([
+        gc - c["ss"] * sga - c["xb"],
+        gs + c["ss"] * cga - c["yb"],
+        gc - c["e"] * spd - c["zt"] * cde - c["xa"],
+        gs + c["e"] * cpd - c["zt"] * sde - c["ya"],
+        gc - c["zf"] * coe - c["u"] * sep - c["xa"],
+        gs - c["zf"] * soe + c["u"] * cep - c["ya"]])
+    a0, a1 = -c["rr"] * sbe + c["d"] * sbt, c["d"] * sbt
+    b0, b1 = c["rr"] * cbe - c["d"] * cbt, -c["d"] * cbt
+    G = np.zeros((6, 7))
+    G[0::2, 0], G[0::2, 1] = a0, a1
+    G[1::2, 0], G[1::2, 1] = b0, b1
+    G[0, 2], G[1, 2] = -c["ss"] * cga, -c["ss"] * sga
+    G[2, 3], G[2, 4] = -c["e"] * cpd, -c["e"] * cpd + c["zt"] * sde
+    G[3, 3], G[3, 4] = -c["e"] * spd, -c["e"] * spd - c["zt"] * cde
+    G[4, 5], G[4, 6] = c["zf"] * soe, c["zf"] * soe - c["u"] * cep
+    G[5, 5], G[5, 6] = -c["zf"] * coe, -c["zf"] * coe - c["u"] * sep
+    return M, h, g, G
+
+
+def andrews_residual(t, y, yp, mom, c0):
+    q, v = y[:7], y[7:14]
+    qd, vd, la, mu = yp[:7], yp[7:14], yp[14:20], yp[20:26]
+    M, h, g, G = _andrews_terms(q, v, mom, c0)
+    return np.concatenate([qd - v + G.T @ mu, M @ vd - h - G.T @ la, G @ v, g])
+
+
+def andrews_initial(params):
+    """q0 of the IVP test set at rest (u0 = 0); the accelerations and multipliers follow from
+    [[M, -G^T], [G, 0]] [u'; lambda] = [h; 0]  (g_qq(u, u) = 0 because u0 = 0), so they stay
+    consistent for every (mom, c0) draw."""
+    mom, c0 = params
+    q0 = ANDREWS_Q0
+    M, h, _, G = _andrews_terms(q0, np.zeros(7), mom, c0)
+    K = np.block([[M, -G.T], [G, np.zeros((6, 6))]])
+    sol = np.linalg.solve(K, np.concatenate([h, np.zeros(6)]))
+    y0 = np.concatenate([q0, np.zeros(7 + 6 + 6)])
+    yp0 = np.concatenate([np.zeros(7), sol[:7], sol[7:], np.zeros(6)])
+    return y0, yp0
+
+
+# --------------------------------------------------------------------------- #
 # registry
 # --------------------------------------------------------------------------- #
 PROBLEMS: dict[str, Problem] = {}
@@ -189,6 +291,11 @@ TRANSAMP = _register(Problem(
     param_names=("Ub", "R0", "beta"),
     doc="Two-transistor amplifier (IVP test set 'transamp'), index 1"))
 
+ANDREWS = _register(Problem(
+    name="andrews", n=26, n_params=2, residual=andrews_residual,
+    default_params=(0.033, 4530.0), initial=andrews_initial, t_span=(0.0, 0.03),
+    param_names=("mom", "c0"),
+    doc="Andrews' squeezer mechanism, stabilised index-1 formulation (n = 26)"))
 
 def get_problem(name_or_problem) -> Problem:
     if isinstance(name_or_problem, Problem):
