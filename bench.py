@@ -1,0 +1,417 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark: ensemble solves/sec (Robertson index-1 DAE, Radau IIA s=3,
+rtol=atol=1e-6, t in [0, 1e7], k_i = k * exp(0.1 u), u ~ U(-1,1)^3) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (rank 0 only)
+
+One "step" = one pass of the hot path over one batch: every rank integrates its own
+`--instances` (default 2^20) instances from t0 to t_bound in ONE kernel launch (weak scaling:
+per-GPU work is fixed, no collective on the data path).
+
+Timed regions
+  value : inputs already resident in HBM (SoA); CUDA events around each launch on the launching
+          stream; L2 flushed between timed iterations; max over ranks.
+  e2e   : the public API call a user makes (solve_dae_batched) with HOST (pinned) inputs, every
+          step including the host->device copies, the AoS->SoA relayout, the launch and the
+          device->host read-back of states, status and counters.
+  cpu_baseline : the CPU oracle (plain-C port of the reference's step loop, oracle/) over a
+          bounded sample of the same ensemble on the host cores of this box.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+WORKLOAD = dict(problem="robertson", method="Radau", stages=3, rtol=1e-6, atol=1e-6,
+                t_span=(0.0, 1e7), sigma=0.1)
+METRIC = "ensemble solves/sec (Robertson, Radau s=3)"
+UNIT = "solves/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--instances", type=int, default=1 << 20, help="instances per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(n_per_gpu, n_gpus):
+    return {"workload": f"robertson_dae_ensemble_N{n_per_gpu}_per_gpu", "problem": "robertson",
+            "method": "Radau IIA s=3, FD Jacobian", "rtol": 1e-6, "atol": 1e-6, "t_span": [0.0, 1e7],
+            "instances_per_gpu": n_per_gpu, "instances_total": n_per_gpu * n_gpus,
+            "param_perturbation": "k*exp(0.1*U(-1,1)), default_rng(seed=rank)",
+            "t_eval": None, "parallelism": f"instance-sharded x{n_gpus}, no collective",
+            "l2": "256 MiB buffer written between timed iterations (L2 flush)"}
+
+
+# --------------------------------------------------------------------------------------------
+# algorithmic flop model (DESIGN.md "Roofline"): counted from the per-instance
+# work counters the kernel returns, not from hardware
+# --------------------------------------------------------------------------------------------
+def algorithmic_flops(cnt: dict, n: int, s: int, c_f: int) -> float:
+    """cnt: dict of SUMS over instances of nfev, njev, nlu, nsolve, n_newton_iter, n_accepted."""
+    ncs = s // 2
+    n_lu_sets = cnt["nlu"] / (1 + ncs)
+    n_f = cnt["nfev"] + cnt["njev"] * (2 * n + 1)            # every residual evaluation incl. FD columns
+    it = cnt["n_newton_iter"]
+    solves_real = it + cnt["n_accepted"] + cnt.get("n_err_rejected", 0)   # + error-estimate solves
+    solves_cplx = it * ncs
+    fl = n_f * c_f
+    fl += n_lu_sets * ((2.0 / 3.0) * n ** 3 + ncs * (8.0 / 3.0) * n ** 3)  # real + complex LU
+    fl += n_lu_sets * (2 * n * n + ncs * 4 * n * n)                        # matrix assembly
+    fl += solves_real * 2 * n * n + solves_cplx * 8 * n * n                # triangular solves
+    fl += it * (3 * 2 * s * s * n + 8 * s * n)                             # TI/T/A transforms, updates, norm
+    fl += cnt["njev"] * 2 * n * 2 * n                                      # FD quotients
+    return float(fl)
+
+
+def compulsory_bytes(n: int, n_params: int) -> int:
+    """HBM bytes one instance must move without t_eval: params, y0, yp0 in; y, yp, t, status, 8 counters out."""
+    return 8 * (n_params + 2 * n) + 8 * (2 * n + 1) + 4 + 4 * 8
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "power_w_max": float(max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_port_run(params, y0, yp0, nthreads):
+    from oracle import oracle as O
+    t = time.perf_counter()
+    r = O.solve_ensemble(WORKLOAD["problem"], params, y0, yp0, WORKLOAD["t_span"], method="Radau",
+                         rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], nthreads=nthreads)
+    dt = time.perf_counter() - t
+    assert (r["status"] == 0).all()
+    return dt, r
+
+
+def cpu_baseline(sample: int, nthreads: int):
+    """Oracle port on the host cores over the first `sample` instances of rank 0's ensemble."""
+    from scipy_dae_b200 import perturbed_params, initial_conditions
+    if sample <= 0:
+        probe = 2048
+        p = perturbed_params("robertson", probe, WORKLOAD["sigma"], 0)
+        y0, yp0 = initial_conditions("robertson", p)
+        dt, _ = cpu_port_run(p, y0, yp0, nthreads)
+        sample = int(min(1 << 20, max(4096, 12.0 * probe / dt)))      # ~12 s of CPU work
+    p = perturbed_params("robertson", sample, WORKLOAD["sigma"], 0)
+    y0, yp0 = initial_conditions("robertson", p)
+    dt, _ = cpu_port_run(p, y0, yp0, nthreads)
+    return {"value": sample / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": f"first {sample} instances of the rank-0 ensemble, oracle/dae_oracle.c "
+                      f"(plain-C port of RadauDAE), {nthreads} POSIX threads, {dt:.2f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from scipy_dae_b200 import perturbed_params, initial_conditions
+    O.build()
+    nthreads = os.cpu_count() or 1
+    # bounded sample per step so that the whole run ends within a few minutes
+    probe = 2048
+    p = perturbed_params("robertson", probe, WORKLOAD["sigma"], 0)
+    y0, yp0 = initial_conditions("robertson", p)
+    dt, _ = cpu_port_run(p, y0, yp0, nthreads)
+    budget_s = 120.0 / max(1, args.steps + args.warmup)
+    sample = int(min(args.instances, max(4096, budget_s * probe / dt)))
+    p = perturbed_params("robertson", sample, WORKLOAD["sigma"], 0)
+    y0, yp0 = initial_conditions("robertson", p)
+    for _ in range(args.warmup):
+        cpu_port_run(p, y0, yp0, nthreads)
+    times = [cpu_port_run(p, y0, yp0, nthreads)[0] for _ in range(args.steps)]
+    total = float(sum(times))
+    value = sample * args.steps / total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "impl": "reference", "config": workload_config(args.instances, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
+                             "sample": f"{sample} instances per step (bounded sample of the "
+                                       f"{args.instances}-instance workload), oracle/dae_oracle.c, "
+                                       f"{nthreads} POSIX threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from scipy_dae_b200 import _lib, solve_dae_batched, perturbed_params, initial_conditions
+    from scipy_dae_b200.constants import radau_tables_c
+    from scipy_dae_b200.problems import get_problem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: scipy_dae_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = _lib.load()
+    prob = get_problem("robertson")
+    pid, n, npar = _lib.problem_lookup("robertson")
+    Nper = args.instances
+    s = WORKLOAD["stages"]
+
+    # ---- synthetic ensemble of this rank; rank 0 holds the config-2 ensemble (seed 0) ---------
+    params = perturbed_params("robertson", Nper, WORKLOAD["sigma"], seed=rank)
+    y0, yp0 = initial_conditions("robertson", params)
+    h_params = torch.from_numpy(params).pin_memory()
+    h_y0 = torch.from_numpy(y0).pin_memory()
+    h_yp0 = torch.from_numpy(yp0).pin_memory()
+
+    # ---- device-resident SoA inputs and outputs for the kernel-only measurement ---------------
+    d_p = h_params.to(dev).t().contiguous()
+    d_y0 = h_y0.to(dev).t().contiguous()
+    d_yp0 = h_yp0.to(dev).t().contiguous()
+    f64 = dict(dtype=torch.float64, device=dev)
+    y_final = torch.empty((n, Nper), **f64)
+    yp_final = torch.empty((n, Nper), **f64)
+    t_final = torch.empty((Nper,), **f64)
+    status = torch.empty((Nper,), dtype=torch.int32, device=dev)
+    counters = torch.empty((8, Nper), dtype=torch.int32, device=dev)
+    out = _lib.Outputs()
+    out.y_final, out.yp_final, out.t_final = y_final.data_ptr(), yp_final.data_ptr(), t_final.data_ptr()
+    out.status, out.counters = status.data_ptr(), counters.data_ptr()
+    ro = _lib.RadauOpts(rtol=WORKLOAD["rtol"], max_step=float("inf"), first_step=0.0,
+                        continuous_error_weight=0.0, jac_recompute_rate=1e-3, deadband_lo=1.0,
+                        deadband_hi=1.2, newton_max_iter=0, newton_iter_embedded=1, max_steps=0)
+    tb = radau_tables_c(s)
+    atol = (ctypes.c_double * n)(*([WORKLOAD["atol"]] * n))
+    stream = torch.cuda.current_stream(dev)
+
+    def launch():
+        rc = L.b200dae_solve_radau(pid, Nper, Nper, d_y0.data_ptr(), d_yp0.data_ptr(), d_p.data_ptr(),
+                                   WORKLOAD["t_span"][0], WORKLOAD["t_span"][1], atol,
+                                   ctypes.byref(ro), ctypes.byref(tb), ctypes.byref(out),
+                                   ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up ----------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        launch()
+    torch.cuda.synchronize(dev)
+    assert bool((status == 0).all()), "bench ensemble did not finish everywhere"
+
+    # ---- value: K launches, inputs resident, events per launch, L2 flushed in between ---------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record(stream)
+        launch()
+        b.record(stream)
+    barrier()
+    gpu_launches = _lib.launch_count() - launches0
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(kernel_ms))
+
+    # ---- e2e: public API, host (pinned) buffers, H2D + relayout + launch + D2H every step -----------
+    host_out = {k: None for k in ("y_final", "yp_final", "t_final", "status")}
+
+    def e2e_step():
+        r = solve_dae_batched("robertson", WORKLOAD["t_span"], h_y0, h_yp0, h_params, method="Radau",
+                              rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], device=dev)
+        host_out["y_final"] = r.y_final.cpu()
+        host_out["yp_final"] = r.yp_final.cpu()
+        host_out["t_final"] = r.t_final.cpu()
+        host_out["status"] = r.status.cpu()
+        host_out["counters"] = torch.stack([r.nfev, r.njev, r.nlu, r.n_accepted]).cpu()
+        return r
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e2e_step()
+        torch.cuda.synchronize(dev)
+        e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    barrier()
+    e2e_total_ms = float(sum(e2e_ms))
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = 8 * Nper * (npar + 2 * n)
+    d2h = 8 * Nper * (2 * n + 1) + 4 * Nper + 4 * 4 * Nper
+
+    # ---- work counters -> algorithmic flops / bytes of the dominant (only) kernel --------------------
+    csum = counters.to(torch.int64).sum(dim=1).cpu().numpy()
+    cnt = dict(nfev=csum[0], njev=csum[1], nlu=csum[2], nsolve=csum[3], n_accepted=csum[4],
+               n_err_rejected=csum[5], n_newton_fail=csum[6], n_newton_iter=csum[7])
+    flops_per_launch = algorithmic_flops(cnt, n, s, 15)
+    bytes_per_launch = compulsory_bytes(n, npar) * Nper
+
+    # ---- FP64 pipe peak of THIS device (MEASURED_PEAKS.json has no FP64 figure) ----------------------
+    sink = torch.empty(148 * 8 * 256, **f64)
+    iters = 1 << 16
+    for _ in range(2):
+        L.b200dae_fp64_peak_kernel(148 * 8, 256, iters, sink.data_ptr(), ctypes.c_void_p(stream.cuda_stream))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    L.b200dae_fp64_peak_kernel(148 * 8, 256, iters, sink.data_ptr(), ctypes.c_void_p(stream.cuda_stream))
+    b.record(stream)
+    torch.cuda.synchronize(dev)
+    fp64_peak_tflops = 148 * 8 * 256 * iters * 16 / (a.elapsed_time(b) * 1e-3) / 1e12
+
+    # ---- max over ranks ----------------------------------------------------------------------------------
+    t_all = torch.tensor([total_ms, e2e_total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    total_ms, e2e_total_ms = float(t_all[0]), float(t_all[1])
+
+    # one gather of the results (rank 0 receives every rank's final states), timed separately
+    gather_ms = None
+    if world > 1:
+        parts = [torch.empty_like(y_final) for _ in range(world)] if rank == 0 else None
+        barrier()
+        t0 = time.perf_counter()
+        dist.gather(y_final, parts, dst=0)
+        torch.cuda.synchronize(dev)
+        gather_ms = 1e3 * (time.perf_counter() - t0)
+
+    if rank == 0:
+        n_total = Nper * world
+        value = n_total * args.steps / (total_ms * 1e-3)
+        e2e_value = n_total * args.steps / (e2e_total_ms * 1e-3)
+        kernel_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach_tflops = flops_per_launch / kernel_s / 1e12
+        ach_gbs = bytes_per_launch / kernel_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(Nper, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
+                    "timer": "host perf_counter bracketed by cuda synchronize"},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp64",
+                "kernel": "radau_kernel<Robertson,3,128>",
+                "achieved": ach_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                "frac": ach_tflops / fp64_peak_tflops,
+                "peak_source": "DFMA-chain microbenchmark run in this process (b200dae_fp64_peak_kernel); "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "flops_per_launch": flops_per_launch, "flops_per_solve": flops_per_launch / Nper,
+                "kernel_ms": kernel_s * 1e3,
+                "traffic": None,
+                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                        "bytes_per_launch": bytes_per_launch,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            },
+            "work_per_solve": {k: float(v) / Nper for k, v in cnt.items()},
+            "gather_ms": gather_ms,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_sample, os.cpu_count() or 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -181,6 +181,11 @@ int64_t b200dae_launch_count(void);
  * buffer of at least `blocks*threads` doubles.  flops = blocks*threads*iters*8*2. */
 int b200dae_fp64_peak_kernel(int blocks, int threads, int64_t iters, double *sink, void *stream);
 
+/* Self-test hook: rcp_out[i] = 1/x[i], sqrt_out[i] = sqrt(x[i]) computed with the library's
+ * branch-free FP64 reciprocal / square root (csrc/fastmath.cuh), which stand in for the IEEE
+ * divisions and sqrt of the reference's NumPy arithmetic.  All pointers DEVICE. */
+int b200dae_selftest_fastmath(int64_t n, const double *x, double *rcp_out, double *sqrt_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,6 +202,13 @@ def cases():
     yield dict(name="transamp_radau3_loose", problem="transamp",
                params=perturbed_params("transamp", 4, 0.02, 1), method="Radau",
                rtol=1e-6, atol=1e-6)
+    # --- C4: Andrews' squeezer (n = 26, stabilised index-1 form), Radau s=5 and s=3
+    yield dict(name="andrews_radau5_ens", problem="andrews",
+               params=perturbed_params("andrews", 6, 0.05, 2), method="Radau",
+               rtol=1e-4, atol=1e-4, options=dict(stages=5), t_eval=np.linspace(0, 0.03, 7))
+    yield dict(name="andrews_radau3_ens", problem="andrews",
+               params=perturbed_params("andrews", 4, 0.05, 2), method="Radau",
+               rtol=1e-6, atol=1e-6, options=dict(stages=3))
     # backward integration (direction = -1) of a non-stiff stretch
     yield dict(name="robertson_radau3_backward", problem="robertson",
                params=rob_nom, method="Radau", rtol=1e-6, atol=1e-8, t_span=(1e-3, 0.0),

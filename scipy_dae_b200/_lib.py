@@ -20,7 +20,7 @@ ST_FINISHED, ST_TOO_SMALL_STEP, ST_NONFINITE, ST_MAX_STEPS, ST_RUNNING = 0, -1, 
 EXPORTS = ("b200dae_version", "b200dae_last_error", "b200dae_num_problems",
            "b200dae_problem_lookup", "b200dae_problem_name", "b200dae_residual",
            "b200dae_solve_radau", "b200dae_solve_bdf", "b200dae_launch_count",
-           "b200dae_fp64_peak_kernel")
+           "b200dae_fp64_peak_kernel", "b200dae_selftest_fastmath")
 
 
 class B200DaeLibraryError(ImportError):
@@ -96,6 +96,8 @@ def load():
                                     ctypes.POINTER(BdfOpts), ctypes.POINTER(Outputs), vp]
     L.b200dae_fp64_peak_kernel.restype = ctypes.c_int
     L.b200dae_fp64_peak_kernel.argtypes = [ctypes.c_int, ctypes.c_int, i64, vp, vp]
+    L.b200dae_selftest_fastmath.restype = ctypes.c_int
+    L.b200dae_selftest_fastmath.argtypes = [i64, vp, vp, vp, vp]
     if L.b200dae_version() != 100:
         raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 100")
     _lib = L

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200dae.so")
 SOURCES = ["b200dae.cu"]
-HEADERS = ["radau.cuh", "bdf.cuh", "fd_jacobian.cuh", "dense_lu.cuh", "problems.cuh",
+HEADERS = ["radau.cuh", "bdf.cuh", "fd_jacobian.cuh", "dense_lu.cuh", "fastmath.cuh", "problems.cuh",
            os.path.join("..", "..", "include", "b200dae.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

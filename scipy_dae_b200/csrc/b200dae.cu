@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -32,11 +33,25 @@ typedef int (*bdf_launcher)(const BdfLaunch&, cudaStream_t);
 typedef int (*residual_launcher)(int64_t, int64_t, double, const double*, const double*,
                                  const double*, double*, cudaStream_t);
 
+static int tune_minb() {   // experiment hook: B200DAE_TUNE_MINB=2|3|4 (register cap of the hot kernel)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B200DAE_TUNE_MINB"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 template <class P, int S>
 static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
     constexpr int T = BlockSize<P>::value;
     const int64_t blocks = (L.N + T - 1) / T;
-    radau_kernel<P, S, T><<<(unsigned)blocks, T, 0, st>>>(L);
+    if constexpr (P::N == 3 && S == 3) {
+        const int mb = tune_minb();
+        if (mb == 3) radau_kernel<P, S, T, 3><<<(unsigned)blocks, T, 0, st>>>(L);
+        else if (mb == 4) radau_kernel<P, S, T, 4><<<(unsigned)blocks, T, 0, st>>>(L);
+        else if (mb == 5) radau_kernel<P, S, 64, 6><<<(unsigned)((L.N + 63) / 64), 64, 0, st>>>(L);
+        else radau_kernel<P, S, T, 1><<<(unsigned)blocks, T, 0, st>>>(L);
+    } else {
+        radau_kernel<P, S, T, 1><<<(unsigned)blocks, T, 0, st>>>(L);
+    }
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
 }
@@ -159,6 +174,14 @@ __global__ void fp64_peak_kernel(int64_t iters, double* __restrict__ sink) {
         a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
     }
     sink[i] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void fastmath_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ rcp,
+                                double* __restrict__ sq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rcp[i] = fast_rcp(x[i]);
+    sq[i] = fast_sqrt(x[i]);
 }
 
 }  // namespace b200dae
@@ -309,6 +332,16 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
     L.out = normalise(out);
     rc = e->bdf(L, (cudaStream_t)stream);
     if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int b200dae_selftest_fastmath(int64_t n, const double* x, double* rcp_out, double* sqrt_out, void* stream) {
+    if (n < 0 || !x || !rcp_out || !sqrt_out) return fail(B200DAE_EINVAL, "bad selftest arguments%s", "");
+    if (n == 0) return 0;
+    fastmath_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, x, rcp_out, sqrt_out);
+    g_launches.fetch_add(1);
+    const cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString(rc));
     return 0;
 }
 

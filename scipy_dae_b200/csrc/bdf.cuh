@@ -158,13 +158,13 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             }
             h = t_new - t;
             hl = fabs(h);
-            const double rh = 1.0 / h;
+            const double rh = fast_rcp(h);
             for (int j = 0; j < N; ++j) {
                 double acc = 0.0, ps = 0.0;
                 for (int i = 0; i <= order; ++i) acc += D[i * N + j];
                 for (int i = 1; i <= order; ++i) ps = fma(D[i * N + j], L.gamma[i], ps);
                 y_predict[j] = acc;
-                inv_scale[j] = 1.0 / fma(rtol, fabs(acc), L.atol[j]);
+                inv_scale[j] = fast_rcp(fma(rtol, fabs(acc), L.atol[j]));
                 psi[j] = ps * rh;
             }
             c = L.alpha[order] * rh;
@@ -173,14 +173,14 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
 
         // ---- phase F: LU of Jy + c*Jyp (bdf.py:320-321) -------------------------------------------
         if (!lu_valid) {
-            bool fin = true;
+            FiniteAcc fin;
 #pragma unroll U
             for (int k = 0; k < N * N; ++k) {
                 const double v = fma(c, Jyp[k], Jy[k]);
-                fin = fin && finite_d(v);
+                fin.add(v);
                 LU[k] = v;
             }
-            if (!fin) { status = B200DAE_ST_NONFINITE; break; }
+            if (!fin.all_finite()) { status = B200DAE_ST_NONFINITE; break; }
             lu_factor<N>(LU, piv);
             ++nlu;
             lu_valid = true;
@@ -192,7 +192,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
         {
 #pragma unroll U
             for (int j = 0; j < N; ++j) { d[j] = 0.0; y_new[j] = y_predict[j]; }
-            double dy_norm_old = 0.0;
+            double inv_norm_old = 0.0;
             bool has_old = false;
             int k = 0;
             for (; k < kBdfNewtonMaxIter; ++k) {
@@ -200,28 +200,28 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
                 for (int j = 0; j < N; ++j) yp_new[j] = fma(c, d[j], psi[j]);
                 P::eval(t_new, y_new, yp_new, p, f);
                 ++nfev;
-                bool fin = true;
+                FiniteAcc fin;
 #pragma unroll U
-                for (int j = 0; j < N; ++j) { fin = fin && finite_d(f[j]); f[j] = -f[j]; }
-                if (!fin) break;
+                for (int j = 0; j < N; ++j) { fin.add(f[j]); f[j] = -f[j]; }
+                if (!fin.all_finite()) break;
                 lu_solve<N>(LU, piv, f);                          // f <- dy
                 ++nsolve;
                 double ss = 0.0;
 #pragma unroll U
                 for (int j = 0; j < N; ++j) { const double q = f[j] * inv_scale[j]; ss = fma(q, q, ss); }
-                const double dy_norm = sqrt(ss * (1.0 / N));
+                const double dy_norm = fast_sqrt(ss * (1.0 / N));
                 double rate = 0.0;
-                if (has_old) rate = dy_norm / dy_norm_old;
-                if (has_old && (rate >= 1.0 ||
-                                powi(rate, kBdfNewtonMaxIter - k) / (1.0 - rate) * dy_norm > L.newton_tol))
+                if (has_old) rate = dy_norm * inv_norm_old;
+                const double cc = dy_norm * fast_rcp(1.0 - rate);
+                if (has_old && (rate >= 1.0 || powi(rate, kBdfNewtonMaxIter - k) * cc > L.newton_tol))
                     break;                                        // BEFORE the update (bdf.py:52-53)
 #pragma unroll U
                 for (int j = 0; j < N; ++j) { y_new[j] += f[j]; d[j] += f[j]; }
-                if (dy_norm == 0.0 || (has_old && rate / (1.0 - rate) * dy_norm < L.newton_tol)) {
+                if (dy_norm == 0.0 || (has_old && rate * cc < L.newton_tol)) {
                     converged = true;
                     break;
                 }
-                dy_norm_old = dy_norm;
+                inv_norm_old = fast_rcp(dy_norm);
                 has_old = true;
             }
             n_iter = (k == kBdfNewtonMaxIter) ? kBdfNewtonMaxIter : k + 1;
@@ -244,18 +244,18 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
         }
 
         // ---- phase E: local error (bdf.py:342-355) -------------------------------------------------
-        const double safety = 0.9 * (2 * kBdfNewtonMaxIter + 1) / (double)(2 * kBdfNewtonMaxIter + n_iter);
+        const double safety = 0.9 * (2 * kBdfNewtonMaxIter + 1) * fast_rcp((double)(2 * kBdfNewtonMaxIter + n_iter));
         double error_norm;
         {
             const double ec = L.error_const[order];
             double ss = 0.0;
 #pragma unroll U
             for (int j = 0; j < N; ++j) {
-                inv_scale[j] = 1.0 / fma(rtol, fabs(y_new[j]), L.atol[j]);
+                inv_scale[j] = fast_rcp(fma(rtol, fabs(y_new[j]), L.atol[j]));
                 const double q = ec * d[j] * inv_scale[j];
                 ss = fma(q, q, ss);
             }
-            error_norm = sqrt(ss * (1.0 / N));
+            error_norm = fast_sqrt(ss * (1.0 / N));
         }
         if (error_norm > 1.0) {
             const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (order + 1)));

@@ -16,6 +16,7 @@
 // The diagonal of U is stored as its reciprocal so the solves multiply instead of divide.
 #pragma once
 #include <math.h>
+#include "fastmath.cuh"
 
 namespace b200dae {
 
@@ -61,7 +62,7 @@ __device__ __forceinline__ void lu_factor(double* __restrict__ a, int* __restric
             }
         }
         const double pv = a[k * N + k];
-        const double r = 1.0 / pv;
+        const double r = fast_rcp(pv);
         a[k * N + k] = r;                              // reciprocal pivot
         const double rs = (pv != 0.0) ? r : 1.0;       // LAPACK skips the scaling for a zero pivot
 #pragma unroll U
@@ -114,8 +115,13 @@ __device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const in
 // complex, split re/im storage
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void crecip(double pr, double pi, double& rr, double& ri) {
-    // 1 / (pr + i pi), Smith's formula (robust against overflow of pr^2 + pi^2)
-    if (fabs(pr) >= fabs(pi)) {
+    // 1 / (pr + i pi) = conj / |.|^2 with one reciprocal; Smith's formula (two divisions, robust
+    // against over/underflow of pr^2 + pi^2) only when |.|^2 leaves [1e-280, 1e280] (rare branch)
+    const double den = fma(pr, pr, pi * pi);
+    if (den >= 1e-280 && den <= 1e280) {
+        const double r = fast_rcp(den);
+        rr = pr * r; ri = -pi * r;
+    } else if (fabs(pr) >= fabs(pi)) {
         const double q = pi / pr, d = 1.0 / fma(pi, q, pr);
         rr = d; ri = -q * d;
     } else {

@@ -107,7 +107,7 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
                     max_diff = max_diff_new;
                 }
             }
-            const double rh = 1.0 / h;
+            const double rh = fast_rcp(h);
 #pragma unroll U
             for (int r = 0; r < N; ++r) J[r * N + i] = diff[r] * rh;
             if (max_diff < kNjDiffSmall * scale) fac *= 10.0;

@@ -18,6 +18,7 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/b200dae.h"
+#include "fastmath.cuh"
 #include "fd_jacobian.cuh"
 
 namespace b200dae {
@@ -40,17 +41,13 @@ struct RadauLaunch {
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-__device__ __forceinline__ double powi(double x, int k) {   // x ** k for small k >= 0
-    double r = 1.0;
-    for (int i = 0; i < k; ++i) r *= x;
-    return r;
-}
+__device__ __forceinline__ double powi(double x, int k) { return powi32(x, k); }   // 0 <= k < 32
 
 // predict_factor, radau.py:198-240 (KAPPA = 1).  inv_sp1 = 1 / (s + 1).
 template <int S>
 __device__ __forceinline__ double root_sp1(double x) {      // x ** (1 / (S + 1))
-    if constexpr (S == 3) return sqrt(sqrt(x));
-    else if constexpr (S == 7) return sqrt(sqrt(sqrt(x)));
+    if constexpr (S == 3) return fast_sqrt(fast_sqrt(x));
+    else if constexpr (S == 7) return fast_sqrt(fast_sqrt(fast_sqrt(x)));
     else return pow(x, 1.0 / (S + 1));
 }
 
@@ -58,13 +55,15 @@ template <int S>
 __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old, double err,
                                                  double err_old, bool have_old) {
     double mult = 1.0;
-    if (have_old && err != 0.0) mult = h_abs / h_abs_old * root_sp1<S>(err_old / err);
-    const double factor = fmin(1.0, mult) / root_sp1<S>(err);   // err == 0 -> inf -> 1 + pi/2
+    // err_old / err and h_abs / h_abs_old share one reciprocal each; err == 0 -> factor = inf -> 1 + pi/2
+    const double r_err = fast_rcp(err);
+    if (have_old && err != 0.0) mult = h_abs * fast_rcp(h_abs_old) * root_sp1<S>(err_old * r_err);
+    const double factor = fmin(1.0, mult) * root_sp1<S>(r_err);
     return 1.0 + atan(factor - 1.0);
 }
 
-template <class P, int S, int kThreads>
-__global__ void __launch_bounds__(kThreads)
+template <class P, int S, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 radau_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
     constexpr int U = Regime<N>::kUnroll;
@@ -167,7 +166,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     for (int j = 0; j < N; ++j) Yp[i][j] = yp[j];
             } else {
                 // extrapolate the previous collocation polynomial's derivative (radau.py:531,693)
-                const double rho = 1.0 / h_old;
+                const double rho = fast_rcp(h_old);
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
                     const double x = (fma(h, tb.C[i], t) - t_old) * rho;
@@ -185,18 +184,18 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 }
             }
 #pragma unroll U
-            for (int j = 0; j < N; ++j) inv_scale[j] = 1.0 / fma(fabs(y[j]), rtol, L.atol[j]);
+            for (int j = 0; j < N; ++j) inv_scale[j] = fast_rcp(fma(fabs(y[j]), rtol, L.atol[j]));
         }
         retry = false;
 
         // ---- phase F: iteration matrices and their LUs (radau.py:536-538) --------------------
         if (!lu_valid) {
-            bool fin = true;
+            FiniteAcc fin;
             const double cr = h * tb.mu_real;
 #pragma unroll U
             for (int k = 0; k < N * N; ++k) {
                 const double v = fma(cr, Jy[k], Jyp[k]);
-                fin = fin && finite_d(v);
+                fin.add(v);
                 LUr[k] = v;
             }
 #pragma unroll
@@ -205,12 +204,13 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
 #pragma unroll U
                 for (int k = 0; k < N * N; ++k) {
                     const double vr = fma(mr, Jy[k], Jyp[k]), vi = mi * Jy[k];
-                    fin = fin && finite_d(vr) && finite_d(vi);
+                    fin.add(vr);
+                    fin.add(vi);
                     LUcr[c][k] = vr;
                     LUci[c][k] = vi;
                 }
             }
-            if (!fin) { status = B200DAE_ST_NONFINITE; break; }   // lu_factor(check_finite=True) raises
+            if (!fin.all_finite()) { status = B200DAE_ST_NONFINITE; break; }   // lu_factor(check_finite=True) raises
             lu_factor<N>(LUr, pivr);
 #pragma unroll
             for (int c = 0; c < NCS; ++c) zlu_factor<N>(LUcr[c], LUci[c], pivc[c]);
@@ -232,19 +232,19 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     for (int l = 0; l < S; ++l) acc = fma(tb.A[i * S + l], Yp[l][j], acc);
                     Y[i][j] = fma(h, acc, y[j]);
                 }
-            double dY_norm_old = 0.0;
+            double inv_norm_old = 0.0;         // 1 / dY_norm of the previous iteration
             bool has_old = false;
             int k = 0;
             for (; k < newton_max_iter; ++k) {
-                bool fin = true;
+                FiniteAcc fin;
 #pragma unroll U
                 for (int i = 0; i < S; ++i) {
                     P::eval(fma(h, tb.C[i], t), Y[i], Yp[i], p, W[i]);
 #pragma unroll U
-                    for (int j = 0; j < N; ++j) fin = fin && finite_d(W[i][j]);
+                    for (int j = 0; j < N; ++j) fin.add(W[i][j]);
                 }
                 nfev += S;
-                if (!fin) break;                                   // radau.py:157-158
+                if (!fin.all_finite()) break;                      // radau.py:157-158
                 // G = -(TI @ F); real block, then the complex blocks (radau.py:160-174)
 #pragma unroll
                 for (int i = 0; i < S; ++i)
@@ -272,9 +272,10 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                         Yp[i][j] += acc;
                     }
                 // dY = h * A @ dYp; Y += dY; ||dY / scale||_rms over all s*n entries (radau.py:177-182)
-                double ss = 0.0;
+                double ssi[S];
 #pragma unroll
-                for (int i = 0; i < S; ++i)
+                for (int i = 0; i < S; ++i) {
+                    double ss = 0.0;
 #pragma unroll U
                     for (int j = 0; j < N; ++j) {
                         double acc = 0.0;
@@ -285,17 +286,23 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                         const double q = dY * inv_scale[j];
                         ss = fma(q, q, ss);
                     }
-                const double dY_norm = sqrt(ss * (1.0 / (S * N)));
-                if (has_old) { rate = dY_norm / dY_norm_old; have_rate = true; }
-                // quirk 2: the rate test breaks AFTER the update was applied
-                if (have_rate && (rate >= 1.0 ||
-                                  powi(rate, newton_max_iter - k) / (1.0 - rate) * dY_norm > L.newton_tol))
+                    ssi[i] = ss;
+                }
+                double ss = 0.0;
+#pragma unroll
+                for (int i = 0; i < S; ++i) ss += ssi[i];
+                const double dY_norm = fast_sqrt(ss * (1.0 / (S * N)));
+                // rate = dY_norm / dY_norm_old; the two tests of radau.py:186-191 share
+                // c = dY_norm / (1 - rate).  quirk 2: the rate test breaks AFTER the update.
+                if (has_old) { rate = dY_norm * inv_norm_old; have_rate = true; }
+                const double c = dY_norm * fast_rcp(1.0 - rate);
+                if (have_rate && (rate >= 1.0 || powi(rate, newton_max_iter - k) * c > L.newton_tol))
                     break;
-                if (dY_norm == 0.0 || (have_rate && rate / (1.0 - rate) * dY_norm < L.newton_tol)) {
+                if (dY_norm == 0.0 || (have_rate && rate * c < L.newton_tol)) {
                     converged = true;
                     break;
                 }
-                dY_norm_old = dY_norm;
+                inv_norm_old = fast_rcp(dY_norm);
                 has_old = true;
             }
             n_iter = (k == newton_max_iter) ? newton_max_iter : k + 1;
@@ -322,7 +329,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
             if (emb == 1) {
                 // implicit embedded method, one Newton iteration
                 double yph[N];
-                const double rmu = 1.0 / tb.mu_real;
+                const double rmu = fast_rcp(tb.mu_real);
 #pragma unroll U
                 for (int j = 0; j < N; ++j) {
                     double acc = 0.0;
@@ -332,10 +339,10 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 }
                 P::eval(t_new, Y[S - 1], yph, p, err);
                 ++nfev;
-                bool fin = true;
+                FiniteAcc fin;
 #pragma unroll U
-                for (int j = 0; j < N; ++j) fin = fin && finite_d(err[j]);
-                if (!fin) { status = B200DAE_ST_NONFINITE; break; }   // lu_solve(check_finite) raises
+                for (int j = 0; j < N; ++j) fin.add(err[j]);
+                if (!fin.all_finite()) { status = B200DAE_ST_NONFINITE; break; }   // lu_solve(check_finite) raises
                 lu_solve<N>(LUr, pivr, err);
                 ++nsolve;
                 const double sc = -h * tb.mu_real;
@@ -395,12 +402,12 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     e = fma(w, pow(fabs(y[j] - acc), (S + 1.0) / S), e);
                 }
                 const double sc = fma(fmax(fabs(y[j]), fabs(Y[S - 1][j])), rtol, L.atol[j]);
-                const double q = e / sc;
+                const double q = e * fast_rcp(sc);
                 ss = fma(q, q, ss);
             }
-            error_norm = sqrt(ss * (1.0 / N));
+            error_norm = fast_sqrt(ss * (1.0 / N));
         }
-        const double safety = 0.9 * (2 * newton_max_iter + 1) / (double)(2 * newton_max_iter + n_iter);
+        const double safety = 0.9 * (2 * newton_max_iter + 1) * fast_rcp((double)(2 * newton_max_iter + n_iter));
 
         if (error_norm > 1.0) {                    // reject (radau.py:598-603); quirk 8: J is kept
             factor = predict_factor<S>(hl, hl_old, error_norm, errl_old, havel_old);
@@ -444,7 +451,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
 
         // t_eval points passed by this step (dae.py:496-515; RadauDenseOutput radau.py:681-699)
         if (L.out.t_eval != nullptr) {
-            const double rho = 1.0 / h;
+            const double rho = fast_rcp(h);
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
                 if (!(dir > 0.0 ? te <= t_new : te >= t_new)) break;

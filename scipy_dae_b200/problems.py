@@ -42,6 +42,7 @@ class Problem:
     t_span: tuple
     doc: str = ""
     param_names: tuple = field(default_factory=tuple)
+    initial_batch: Callable = None   # optional vectorised initial(params[N, p]) -> (y0[N, n], yp0[N, n])
 
     def __call__(self, t, y, yp, *params):
         if not params:
@@ -65,6 +66,16 @@ def robertson_residual(t, y, yp, k1, k2, k3):
 def robertson_initial(params):
     k1 = params[0]
     return np.array([1.0, 0.0, 0.0]), np.array([-k1, k1, 0.0])
+
+
+def robertson_initial_batch(params):
+    N = params.shape[0]
+    y0 = np.zeros((N, 3))
+    y0[:, 0] = 1.0
+    yp0 = np.zeros((N, 3))
+    yp0[:, 0] = -params[:, 0]
+    yp0[:, 1] = params[:, 0]
+    return y0, yp0
 
 
 # --------------------------------------------------------------------------- #
@@ -275,6 +286,7 @@ def _register(p: Problem):
 ROBERTSON = _register(Problem(
     name="robertson", n=3, n_params=3, residual=robertson_residual,
     default_params=(0.04, 1e4, 3e7), initial=robertson_initial, t_span=(0.0, 1e7),
+    initial_batch=robertson_initial_batch,
     param_names=("k1", "k2", "k3"),
     doc="Robertson chemical kinetics as an index-1 DAE"))
 
@@ -323,7 +335,9 @@ def perturbed_params(problem, N: int, sigma: float, seed: int = 0) -> np.ndarray
 def initial_conditions(problem, params: np.ndarray):
     """Consistent ``(y0[N,n], yp0[N,n])`` for an ``(N, n_params)`` parameter array."""
     problem = get_problem(problem)
-    params = np.atleast_2d(params)
+    params = np.atleast_2d(np.asarray(params, dtype=float))
+    if problem.initial_batch is not None:
+        return problem.initial_batch(params)
     y0 = np.empty((params.shape[0], problem.n))
     yp0 = np.empty_like(y0)
     for i, p in enumerate(params):
