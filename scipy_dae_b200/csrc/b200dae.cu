@@ -33,25 +33,28 @@ typedef int (*bdf_launcher)(const BdfLaunch&, cudaStream_t);
 typedef int (*residual_launcher)(int64_t, int64_t, double, const double*, const double*,
                                  const double*, double*, cudaStream_t);
 
-static int tune_minb() {   // experiment hook: B200DAE_TUNE_MINB=2|3|4 (register cap of the hot kernel)
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("B200DAE_TUNE_MINB"); v = e ? atoi(e) : 0; }
-    return v;
-}
+// Launch shape of the Radau kernel per (problem size, stages).
+//   register regime (n <= 4): 64-thread blocks, the cold per-instance state in shared memory
+//   (when it fits the 48 KB static limit); for s = 3 the register cap is 168 so that 6 blocks =
+//   3 warps per scheduler are resident (measured on B200, 2^20 Robertson instances:
+//   255 regs/2 warps 18.9 ms, 168 regs/3 warps 15.6 ms, 128 regs/4 warps (spills) 17.7 ms).
+//   local-memory regime (n > 4): 64-thread blocks so the per-thread arrays stay L1-resident.
+template <class P, int S>
+struct RadauTune {
+    static constexpr int N = P::N, NCS = S / 2;
+    static constexpr bool kReg = Regime<N>::kReg;
+    static constexpr int kThreads = 64;
+    static constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
+    static constexpr bool kSharedCold = kReg && (kCold * kThreads * 8 <= 48 * 1024);
+    static constexpr int kMinBlocks = (kSharedCold && S <= 3) ? 6 : 1;
+};
 
 template <class P, int S>
 static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
-    constexpr int T = BlockSize<P>::value;
+    using Tn = RadauTune<P, S>;
+    constexpr int T = Tn::kThreads;
     const int64_t blocks = (L.N + T - 1) / T;
-    if constexpr (P::N == 3 && S == 3) {
-        const int mb = tune_minb();
-        if (mb == 3) radau_kernel<P, S, T, 3><<<(unsigned)blocks, T, 0, st>>>(L);
-        else if (mb == 4) radau_kernel<P, S, T, 4><<<(unsigned)blocks, T, 0, st>>>(L);
-        else if (mb == 5) radau_kernel<P, S, 64, 6><<<(unsigned)((L.N + 63) / 64), 64, 0, st>>>(L);
-        else radau_kernel<P, S, T, 1><<<(unsigned)blocks, T, 0, st>>>(L);
-    } else {
-        radau_kernel<P, S, T, 1><<<(unsigned)blocks, T, 0, st>>>(L);
-    }
+    radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold><<<(unsigned)blocks, T, 0, st>>>(L);
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
 }

@@ -124,7 +124,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
     while (status == B200DAE_ST_RUNNING) {
         // ---- phase J: FD Jacobian at the committed (t, y, yp) (base.py:297, bdf.py:330) ------
         if (need_jac) {
-            fd_jacobian<P>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
+            fd_jacobian<P, double*>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
             ++njev;
             need_jac = false;
         }

@@ -20,6 +20,16 @@
 
 namespace b200dae {
 
+// View of a per-thread vector that lives either in a local array (stride 1 -> registers after
+// unrolling) or in shared memory laid out [element][thread] (stride = threads per block, so the
+// 32 lanes of a warp hit 32 consecutive 8-byte words: conflict-free).
+template <bool SH, int STRIDE>
+struct Vec {
+    double* p;
+    __device__ __forceinline__ double& operator[](int k) const { return p[SH ? k * STRIDE : k]; }
+    __device__ __forceinline__ Vec operator+(int off) const { return Vec{p + (SH ? off * STRIDE : off)}; }
+};
+
 template <int N>
 struct Regime {
     static constexpr bool kReg = (N <= 4);
@@ -130,9 +140,8 @@ __device__ __forceinline__ void crecip(double pr, double pi, double& rr, double&
     }
 }
 
-template <int N>
-__device__ __forceinline__ void zlu_factor(double* __restrict__ ar, double* __restrict__ ai,
-                                           int* __restrict__ piv) {
+template <int N, class MR, class MI>
+__device__ __forceinline__ void zlu_factor(MR ar, MI ai, int* __restrict__ piv) {
     constexpr bool REG = Regime<N>::kReg;
     constexpr int U = Regime<N>::kUnroll;
 #pragma unroll U
@@ -188,10 +197,9 @@ __device__ __forceinline__ void zlu_factor(double* __restrict__ ar, double* __re
     }
 }
 
-template <int N>
-__device__ __forceinline__ void zlu_solve(const double* __restrict__ ar, const double* __restrict__ ai,
-                                          const int* __restrict__ piv, double* __restrict__ br,
-                                          double* __restrict__ bi) {
+template <int N, class MR, class MI>
+__device__ __forceinline__ void zlu_solve(MR ar, MI ai, const int* __restrict__ piv,
+                                          double* __restrict__ br, double* __restrict__ bi) {
     constexpr bool REG = Regime<N>::kReg;
     constexpr int U = Regime<N>::kUnroll;
 #pragma unroll U

@@ -55,6 +55,27 @@ __device__ __forceinline__ double fast_sqrt(double x) {
     return (xs > 0.0 && xs < INFINITY) ? g : ((x < 0.0) ? nan("") : x);
 }
 
+// sqrt(x) and 1/sqrt(x) from one refinement (the coupled iteration carries h ~ 1/(2 sqrt x)).
+// For x = 0 returns (0, inf); for x = inf (inf, 0); NaN / negative -> NaN.
+__device__ __forceinline__ double fast_sqrt_rsqrt(double x, double& rsq) {
+    const bool tiny = x < 1e-200;
+    const double xs = tiny ? x * 0x1p+600 : x;
+    const double r0 = rsqrt_seed(xs);
+    double g = xs * r0, h = 0.5 * r0;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g); h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    g = fma(g, e, g); h = fma(h, e, h);
+    const double d = fma(-g, g, xs);
+    g = fma(d, h, g);
+    e = fma(-h, g, 0.5);
+    h = fma(h, e, h);
+    const bool ok = (xs > 0.0 && xs < INFINITY);
+    rsq = ok ? (tiny ? 2.0 * h * 0x1p+300 : 2.0 * h) : ((x < 0.0) ? nan("") : r0);
+    g = tiny ? g * 0x1p-300 : g;
+    return ok ? g : ((x < 0.0) ? nan("") : x);
+}
+
 // x ** k for 0 <= k < 32 without a loop
 __device__ __forceinline__ double powi32(double x, int k) {
     const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8;

@@ -62,11 +62,10 @@ __device__ __forceinline__ void fd_column(double t, double* __restrict__ y, doub
 }
 
 // Jy and Jyp (row-major N*N) at (t, y, yp).  thr[i] = atol[i] / rtol.
-template <class P>
+template <class P, class V>
 __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, double* __restrict__ yp,
                                             const double* __restrict__ p, const double* __restrict__ thr,
-                                            double* __restrict__ factor_y, double* __restrict__ factor_yp,
-                                            double* __restrict__ Jy, double* __restrict__ Jyp) {
+                                            V factor_y, V factor_yp, V Jy, V Jyp) {
     constexpr int N = P::N;
     constexpr int U = Regime<N>::kUnroll;
     double f[N];
@@ -75,8 +74,8 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
     for (int which = 0; which < 2; ++which) {
         const bool wrt_yp = (which == 1);
         const double* x = wrt_yp ? yp : y;
-        double* factor = wrt_yp ? factor_yp : factor_y;
-        double* J = wrt_yp ? Jyp : Jy;
+        V factor = wrt_yp ? factor_yp : factor_y;
+        V J = wrt_yp ? Jyp : Jy;
 #pragma unroll U
         for (int i = 0; i < N; ++i) {
             const double xi = x[i];

@@ -62,7 +62,7 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
     return 1.0 + atan(factor - 1.0);
 }
 
-template <class P, int S, int kThreads, int kMinBlocks>
+template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 radau_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
@@ -79,12 +79,22 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
 #pragma unroll U
     for (int j = 0; j < N; ++j) { y[j] = L.y0[j * ld + inst]; yp[j] = L.yp0[j * ld + inst]; }
 
-    double Jy[N * N], Jyp[N * N], factor_y[N], factor_yp[N];
-    double LUr[N * N], LUcr[NCS > 0 ? NCS : 1][N * N], LUci[NCS > 0 ? NCS : 1][N * N];
+    // "Cold" per-instance state (touched once per step or per LU, not per Newton iteration):
+    // Jacobians, FD step factors, dense-output coefficients, complex LU factors.  With
+    // kSharedCold they live in shared memory [element][thread], which frees ~100 registers and
+    // lets a third warp per scheduler hide the 8.7-cycle DFMA latency.
+    constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
+    __shared__ double s_cold[kSharedCold ? kCold * kThreads : 1];
+    double r_cold[kSharedCold ? 1 : kCold];
+    using V = Vec<kSharedCold, kThreads>;
+    const V Jy{kSharedCold ? (s_cold + threadIdx.x) : r_cold};
+    const V Jyp = Jy + N * N, factor_y = Jyp + N * N, factor_yp = factor_y + N;
+    const V ZP = factor_yp + N;                  // [N][S], dense output of the last accepted step
+    const V LUcr0 = ZP + N * S, LUci0 = LUcr0 + NCS * N * N;
+    double LUr[N * N];
     int pivr[N], pivc[NCS > 0 ? NCS : 1][N];
     double Y[S][N], Yp[S][N], W[S][N], G[S][N];
-    double ZP[N][S];                 // dense output of the last accepted step
-    double inv_scale[N];
+    double h_inv_scale[N];           // h / scale of the current attempt
 #pragma unroll U
     for (int j = 0; j < N; ++j) factor_y[j] = factor_yp[j] = kNjInitFactor;
 
@@ -136,7 +146,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     while (status == B200DAE_ST_RUNNING) {
         // ---- phase J: finite-difference Jacobian at the current (t, y, yp) ----------------
         if (need_jac) {
-            fd_jacobian<P>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
+            fd_jacobian<P, V>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
             ++njev;
             need_jac = false;
         }
@@ -178,13 +188,13 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     for (int j = 0; j < N; ++j) {
                         double acc = 0.0;
 #pragma unroll
-                        for (int k = 0; k < S; ++k) acc = fma(ZP[j][k], w[k], acc);
+                        for (int k = 0; k < S; ++k) acc = fma(ZP[j * S + k], w[k], acc);
                         Yp[i][j] = acc;
                     }
                 }
             }
 #pragma unroll U
-            for (int j = 0; j < N; ++j) inv_scale[j] = fast_rcp(fma(fabs(y[j]), rtol, L.atol[j]));
+            for (int j = 0; j < N; ++j) h_inv_scale[j] = h * fast_rcp(fma(fabs(y[j]), rtol, L.atol[j]));
         }
         retry = false;
 
@@ -206,14 +216,14 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     const double vr = fma(mr, Jy[k], Jyp[k]), vi = mi * Jy[k];
                     fin.add(vr);
                     fin.add(vi);
-                    LUcr[c][k] = vr;
-                    LUci[c][k] = vi;
+                    (LUcr0 + c * N * N)[k] = vr;
+                    (LUci0 + c * N * N)[k] = vi;
                 }
             }
             if (!fin.all_finite()) { status = B200DAE_ST_NONFINITE; break; }   // lu_factor(check_finite=True) raises
             lu_factor<N>(LUr, pivr);
 #pragma unroll
-            for (int c = 0; c < NCS; ++c) zlu_factor<N>(LUcr[c], LUci[c], pivc[c]);
+            for (int c = 0; c < NCS; ++c) zlu_factor<N>(LUcr0 + c * N * N, LUci0 + c * N * N, pivc[c]);
             nlu += 1 + NCS;
             lu_valid = true;
         }
@@ -258,7 +268,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 lu_solve<N>(LUr, pivr, G[0]);
 #pragma unroll
                 for (int c = 0; c < NCS; ++c)
-                    zlu_solve<N>(LUcr[c], LUci[c], pivc[c], G[2 * c + 1], G[2 * c + 2]);
+                    zlu_solve<N>(LUcr0 + c * N * N, LUci0 + c * N * N, pivc[c], G[2 * c + 1], G[2 * c + 2]);
                 nsolve += 1 + NCS;
                 // dYp = T @ dW; Yp += dYp   (radau.py:176,179)
 #pragma unroll
@@ -281,9 +291,8 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                         double acc = 0.0;
 #pragma unroll
                         for (int l = 0; l < S; ++l) acc = fma(tb.A[i * S + l], W[l][j], acc);
-                        const double dY = h * acc;
-                        Y[i][j] += dY;
-                        const double q = dY * inv_scale[j];
+                        Y[i][j] = fma(h, acc, Y[i][j]);
+                        const double q = acc * h_inv_scale[j];      // dY / scale
                         ss = fma(q, q, ss);
                     }
                     ssi[i] = ss;
@@ -291,18 +300,21 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 double ss = 0.0;
 #pragma unroll
                 for (int i = 0; i < S; ++i) ss += ssi[i];
-                const double dY_norm = fast_sqrt(ss * (1.0 / (S * N)));
-                // rate = dY_norm / dY_norm_old; the two tests of radau.py:186-191 share
-                // c = dY_norm / (1 - rate).  quirk 2: the rate test breaks AFTER the update.
-                if (has_old) { rate = dY_norm * inv_norm_old; have_rate = true; }
-                const double c = dY_norm * fast_rcp(1.0 - rate);
-                if (have_rate && (rate >= 1.0 || powi(rate, newton_max_iter - k) * c > L.newton_tol))
-                    break;
-                if (dY_norm == 0.0 || (have_rate && rate * c < L.newton_tol)) {
+                double inv_norm;
+                const double dY_norm = fast_sqrt_rsqrt(ss * (1.0 / (S * N)), inv_norm);
+                if (has_old) {
+                    // rate = dY_norm / dY_norm_old; the two tests of radau.py:186-191 share
+                    // c = dY_norm / (1 - rate).  quirk 2: the rate test breaks AFTER the update.
+                    rate = dY_norm * inv_norm_old;
+                    have_rate = true;
+                    const double c = dY_norm * fast_rcp(1.0 - rate);
+                    if (rate >= 1.0 || powi(rate, newton_max_iter - k) * c > L.newton_tol) break;
+                    if (dY_norm == 0.0 || rate * c < L.newton_tol) { converged = true; break; }
+                } else if (dY_norm == 0.0) {
                     converged = true;
                     break;
                 }
-                inv_norm_old = fast_rcp(dY_norm);
+                inv_norm_old = inv_norm;
                 has_old = true;
             }
             n_iter = (k == newton_max_iter) ? newton_max_iter : k + 1;
@@ -442,7 +454,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 double acc = 0.0;
 #pragma unroll
                 for (int l = 0; l < S; ++l) acc = fma(z[l], tb.P[l * S + k], acc);
-                ZP[j][k] = acc;
+                ZP[j * S + k] = acc;
             }
         }
         t_old = t;
@@ -466,7 +478,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 for (int j = 0; j < N; ++j) {
                     double a = 0.0, b = 0.0;
 #pragma unroll
-                    for (int k = 0; k < S; ++k) { a = fma(ZP[j][k], pw[k], a); b = fma(ZP[j][k], dpw[k], b); }
+                    for (int k = 0; k < S; ++k) { a = fma(ZP[j * S + k], pw[k], a); b = fma(ZP[j * S + k], dpw[k], b); }
                     ye[j * ld] = a + y[j];
                     if (ype) ype[j * ld] = b;
                 }
