@@ -90,12 +90,12 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
         double e = 0.0;
 #pragma unroll U
         for (int j = 0; j < N; ++j) {
-            const double v = fabs(yp[j] / fmax(fabs(y[j]), L.thr[j]));
+            const double v = fabs(yp[j] * fast_rcp(fmax(fabs(y[j]), L.thr[j])));
             if (v > e || v != v) e = v;
         }
-        const double rh = e / sqrt(rtol) / 0.8;
+        const double rh = e * fast_rcp(fast_sqrt(rtol) * 0.8);
         h_abs = fmin(L.max_step, fabs(L.t_bound - L.t0));
-        if (h_abs * rh > 1.0) h_abs = 1.0 / rh;
+        if (h_abs * rh > 1.0) h_abs = fast_rcp(rh);
         h_abs = fmax(h_abs, 16.0 * kEps * fabs(L.t0));
     }
     for (int k = 0; k < kBdfRows * N; ++k) D[k] = 0.0;     // bdf.py:254-257

@@ -125,19 +125,15 @@ __device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const in
 // complex, split re/im storage
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void crecip(double pr, double pi, double& rr, double& ri) {
-    // 1 / (pr + i pi) = conj / |.|^2 with one reciprocal; Smith's formula (two divisions, robust
-    // against over/underflow of pr^2 + pi^2) only when |.|^2 leaves [1e-280, 1e280] (rare branch)
-    const double den = fma(pr, pr, pi * pi);
-    if (den >= 1e-280 && den <= 1e280) {
-        const double r = fast_rcp(den);
-        rr = pr * r; ri = -pi * r;
-    } else if (fabs(pr) >= fabs(pi)) {
-        const double q = pi / pr, d = 1.0 / fma(pi, q, pr);
-        rr = d; ri = -q * d;
-    } else {
-        const double q = pr / pi, d = 1.0 / fma(pr, q, pi);
-        rr = q * d; ri = -d;
-    }
+    // 1 / (pr + i pi) = conj / |.|^2 with one reciprocal.  When |.|^2 would leave [1e-280, 1e280]
+    // (pivots beyond 1e+-140: rare branch) the operands are first rescaled by a power of two,
+    // which is what Smith's formula guards against in LAPACK's zladiv.
+    double sc = 1.0;
+    const double m = fmax(fabs(pr), fabs(pi));
+    if (!(m >= 1e-140 && m <= 1e140)) sc = (m > 1.0) ? 0x1p-600 : ((m > 0.0) ? 0x1p+600 : 1.0);
+    const double a = pr * sc, b = pi * sc;
+    const double r = fast_rcp(fma(a, a, b * b)) * sc;
+    rr = a * r; ri = -b * r;
 }
 
 template <int N, class MR, class MI>

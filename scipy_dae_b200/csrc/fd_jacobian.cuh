@@ -89,22 +89,27 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
                 xp = fma(fac, y_scale, xi);
                 h = xp - xi;
             }
-            double diff[N], max_diff, scale;
-            fd_column<P>(t, y, yp, p, f, wrt_yp, i, xp, diff, max_diff, scale);
-            if (max_diff < kNjDiffReject * scale) {
-                const double new_fac = 10.0 * fac;
-                const double xp2 = fma(new_fac, y_scale, xi);
-                const double h_new = xp2 - xi;
-                double diff2[N], max_diff_new, scale_new;
-                fd_column<P>(t, y, yp, p, f, wrt_yp, i, xp2, diff2, max_diff_new, scale_new);
-                if (max_diff * scale_new < max_diff_new * scale) {
-                    fac = new_fac;
-                    h = h_new;
+            // first try with `fac`; if the difference drowns in round-off (SP/common.py:350-371)
+            // a second try with 10*fac replaces it when it resolves the column better.  Written
+            // as a 2-trip rolled loop so the residual evaluation is emitted once per column.
+            double diff[N], max_diff = 0.0, scale = 0.0;
+            double fac_try = fac, xp_try = xp, h_try = h;
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                double d2[N], md2, sc2;
+                fd_column<P>(t, y, yp, p, f, wrt_yp, i, xp_try, d2, md2, sc2);
+                if (attempt == 0 || max_diff * sc2 < md2 * scale) {
+                    fac = fac_try;
+                    h = h_try;
 #pragma unroll U
-                    for (int r = 0; r < N; ++r) diff[r] = diff2[r];
-                    scale = scale_new;
-                    max_diff = max_diff_new;
+                    for (int r = 0; r < N; ++r) diff[r] = d2[r];
+                    scale = sc2;
+                    max_diff = md2;
                 }
+                if (attempt == 1 || !(max_diff < kNjDiffReject * scale)) break;
+                fac_try = 10.0 * fac;
+                xp_try = fma(fac_try, y_scale, xi);
+                h_try = xp_try - xi;
             }
             const double rh = fast_rcp(h);
 #pragma unroll U

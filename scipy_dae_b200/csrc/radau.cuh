@@ -62,7 +62,11 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
     return 1.0 + atan(factor - 1.0);
 }
 
-template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold>
+// kLean: the launch uses the default error estimator (newton_iter_embedded = 1,
+// continuous_error_weight = 0) and asks for neither t_eval output nor a step trace.  Those options
+// are then compiled out, which shrinks the hot kernel (instruction-cache misses were 11 % of the
+// warp stalls of the all-options kernel).
+template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold, bool kLean>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 radau_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
@@ -108,12 +112,12 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         double e = 0.0;
 #pragma unroll U
         for (int j = 0; j < N; ++j) {
-            const double v = fabs(yp[j] / fmax(fabs(y[j]), L.thr[j]));
+            const double v = fabs(yp[j] * fast_rcp(fmax(fabs(y[j]), L.thr[j])));
             if (v > e || v != v) e = v;
         }
-        const double rh = e / sqrt(rtol) / 0.8;
+        const double rh = e * fast_rcp(fast_sqrt(rtol) * 0.8);
         h_abs = fmin(L.max_step, fabs(L.t_bound - L.t0));
-        if (h_abs * rh > 1.0) h_abs = 1.0 / rh;
+        if (h_abs * rh > 1.0) h_abs = fast_rcp(rh);
         h_abs = fmax(h_abs, 16.0 * kEps * fabs(L.t0));
     }
     double h_abs_old = 0.0, err_old = 0.0;
@@ -127,7 +131,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     int32_t nst = 0;                 // rows written to the step trace
     const int newton_max_iter = L.newton_max_iter;
 
-    if (L.out.t_steps != nullptr && L.out.steps_cap > 0) {
+    if (!kLean && L.out.t_steps != nullptr && L.out.steps_cap > 0) {
         L.out.t_steps[inst] = t;
 #pragma unroll U
         for (int j = 0; j < N; ++j) {
@@ -337,7 +341,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         // ---- phase E: embedded error estimate (radau.py:560-596) ---------------------------
         double err[N];
         {
-            const int emb = L.newton_iter_embedded;
+            const int emb = kLean ? 1 : L.newton_iter_embedded;
             if (emb == 1) {
                 // implicit embedded method, one Newton iteration
                 double yph[N];
@@ -402,7 +406,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         }
         double error_norm;
         {
-            const double w = L.cew;
+            const double w = kLean ? 0.0 : L.cew;
             double ss = 0.0;
 #pragma unroll U
             for (int j = 0; j < N; ++j) {
@@ -421,8 +425,11 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         }
         const double safety = 0.9 * (2 * newton_max_iter + 1) * fast_rcp((double)(2 * newton_max_iter + n_iter));
 
+        // one code site for predict_factor: the reject path always needs it, the accept path
+        // unless a factor is left over from a rejected attempt of this step (quirk 3)
+        const double pf = predict_factor<S>(hl, hl_old, error_norm, errl_old, havel_old);
         if (error_norm > 1.0) {                    // reject (radau.py:598-603); quirk 8: J is kept
-            factor = predict_factor<S>(hl, hl_old, error_norm, errl_old, havel_old);
+            factor = pf;
             have_factor = true;
             hl *= safety * factor;
             lu_valid = false;
@@ -433,7 +440,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         // ---- phase C: the step is accepted (radau.py:607-657) ---------------------------------
         const bool recompute_jac = (n_iter > 2) && have_rate && (rate > L.jac_rate);   // quirk 6
         // quirk 3: a factor left over from a rejected attempt is reused as is, without safety
-        if (!have_factor) factor = safety * predict_factor<S>(hl, hl_old, error_norm, errl_old, havel_old);
+        if (!have_factor) factor = safety * pf;
         if (!recompute_jac && L.db_lo <= factor && factor <= L.db_hi) factor = 1.0;   // quirk 5: LUs kept
         else lu_valid = false;
         need_jac = recompute_jac;
@@ -462,7 +469,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         have_sol = true;
 
         // t_eval points passed by this step (dae.py:496-515; RadauDenseOutput radau.py:681-699)
-        if (L.out.t_eval != nullptr) {
+        if (!kLean && L.out.t_eval != nullptr) {
             const double rho = fast_rcp(h);
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
@@ -490,7 +497,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
 #pragma unroll U
         for (int j = 0; j < N; ++j) { y[j] = Y[S - 1][j]; yp[j] = Yp[S - 1][j]; }
         ++nacc;
-        if (L.out.t_steps != nullptr && nst < L.out.steps_cap) {
+        if (!kLean && L.out.t_steps != nullptr && nst < L.out.steps_cap) {
             L.out.t_steps[(int64_t)nst * ld + inst] = t;
 #pragma unroll U
             for (int j = 0; j < N; ++j) {

@@ -20,6 +20,7 @@ CASES = [
     ("C2 robertson Radau3", "robertson", "Radau", 8192, 0.1, 1e-6, 1e-6, {}),
     ("C2 robertson Radau3 s0.5", "robertson", "Radau", 4096, 0.5, 1e-6, 1e-6, {}),
     ("robertson Radau5", "robertson", "Radau", 2048, 0.1, 1e-6, 1e-6, {"stages": 5}),
+    ("robertson Radau3 tight", "robertson", "Radau", 1024, 0.1, 1e-9, 1e-12, {}),
     ("robertson BDF", "robertson", "BDF", 4096, 0.1, 1e-6, 1e-6, {}),
     ("C3 akzo BDF", "akzo_nobel", "BDF", 2048, 0.05, 1e-8, 1e-8, {}),
     ("akzo Radau3", "akzo_nobel", "Radau", 1024, 0.05, 1e-8, 1e-8, {}),
@@ -58,6 +59,11 @@ def main():
                    acc_rel_diff_max=float(np.abs(dacc).max()), acc_within_5pct=float((np.abs(dacc) <= 0.05).mean()),
                    acc_mean_gpu=float(r.n_accepted[ok].mean()), acc_mean_ref=float(ref["n_accepted"][ok].mean()),
                    nfev_mean_gpu=float(r.nfev[ok].mean()), nfev_mean_ref=float(ref["nfev"][ok].mean()),
+                   njev_mean_gpu=float(r.njev[ok].mean()), njev_mean_ref=float(ref["njev"][ok].mean()),
+                   nlu_mean_gpu=float(r.nlu[ok].mean()), nlu_mean_ref=float(ref["nlu"][ok].mean()),
+                   nfail_mean_gpu=float(r.n_newton_fail[ok].mean()), nfail_mean_ref=float(ref["n_newton_fail"][ok].mean()),
+                   nrej_mean_gpu=float(r.n_err_rejected[ok].mean()), nrej_mean_ref=float(ref["n_err_rejected"][ok].mean()),
+                   niter_mean_gpu=float(r.n_newton_iter[ok].mean()), niter_mean_ref=float(ref["n_newton_iter"][ok].mean()),
                    gpu_s=round(tg, 3), cpu_s=round(tc, 3))
         rows.append(row)
         print(json.dumps(row), flush=True)
