@@ -1,20 +1,29 @@
 """Build recipe for libb200dae.so (explicit nvcc for sm_100a, in-tree so the .so travels with
-the repository snapshot to the GPU box)."""
+the repository snapshot to the GPU box).  One translation unit per registered problem, compiled
+in parallel, then linked."""
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libb200dae.so")
-SOURCES = ["b200dae.cu"]
-HEADERS = ["radau.cuh", "bdf.cuh", "fd_jacobian.cuh", "dense_lu.cuh", "fastmath.cuh", "problems.cuh",
-           os.path.join("..", "..", "include", "b200dae.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def headers():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "b200dae.h")]
 
 
 def find_nvcc() -> str:
@@ -27,19 +36,38 @@ def find_nvcc() -> str:
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps = sources() + headers()
     return os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/b200dae.cu -> scipy_dae_b200/libb200dae.so (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu -> scipy_dae_b200/libb200dae.so (cross-compiles without a GPU)."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS]
+    nvcc = find_nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    newest_header = max(os.path.getmtime(h) for h in headers())
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) >= max(os.path.getmtime(src), newest_header)):
+            return obj, ""
+        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", obj, src]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, sources()))
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.run(cmd, check=True)
+        for _, log in results:
+            if log:
+                print(log)
+    subprocess.run([nvcc, "-shared", "-o", LIB_PATH, *[o for o, _ in results]], check=True)
     return LIB_PATH
 
 

@@ -9,131 +9,20 @@
 #include <atomic>
 
 #include "../../include/b200dae.h"
-#include "bdf.cuh"
-#include "problems.cuh"
-#include "radau.cuh"
+#include "launchers.cuh"
 
 namespace b200dae {
 
 static thread_local char g_err[512] = "";
-static std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_launches{0};
 
 static int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
     snprintf(g_err, sizeof(g_err), fmt, a, b);
     return code;
 }
 
-// threads per block: register-regime kernels keep ~255 registers per thread live, so 128
-// threads x 2 blocks fill an SM's register file; the local-memory regime prefers fewer
-// threads per SM so that its per-thread arrays stay L1-resident.
-template <class P> struct BlockSize { static constexpr int value = Regime<P::N>::kReg ? 128 : 64; };
-
-typedef int (*radau_launcher)(const RadauLaunch&, cudaStream_t);
-typedef int (*bdf_launcher)(const BdfLaunch&, cudaStream_t);
-typedef int (*residual_launcher)(int64_t, int64_t, double, const double*, const double*,
-                                 const double*, double*, cudaStream_t);
-
-// Launch shape of the Radau kernel per (problem size, stages).
-//   register regime (n <= 4): 64-thread blocks, the cold per-instance state in shared memory
-//   (when it fits the 48 KB static limit); for s = 3 the register cap is 168 so that 6 blocks =
-//   3 warps per scheduler are resident (measured on B200, 2^20 Robertson instances:
-//   255 regs/2 warps 18.9 ms, 168 regs/3 warps 15.6 ms, 128 regs/4 warps (spills) 17.7 ms).
-//   local-memory regime (n > 4): 64-thread blocks so the per-thread arrays stay L1-resident.
-template <class P, int S>
-struct RadauTune {
-    static constexpr int N = P::N, NCS = S / 2;
-    static constexpr bool kReg = Regime<N>::kReg;
-    static constexpr int kThreads = 64;
-    static constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
-    static constexpr bool kSharedCold = kReg && (kCold * kThreads * 8 <= 48 * 1024);
-    static constexpr int kMinBlocks = (kSharedCold && S <= 3) ? 6 : 1;
-};
-
-template <class P, int S>
-static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
-    using Tn = RadauTune<P, S>;
-    constexpr int T = Tn::kThreads;
-    const int64_t blocks = (L.N + T - 1) / T;
-    const bool lean = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_eval == nullptr &&
-                      L.out.t_steps == nullptr;
-    if (lean) {
-        if constexpr (P::N == 3 && S == 3) {   // experiment hook: B200DAE_TUNE=7 -> 7 blocks (144 regs) per SM
-            static const int tune = getenv("B200DAE_TUNE") ? atoi(getenv("B200DAE_TUNE")) : 0;
-            if (tune == 7) {
-                radau_kernel<P, S, T, 7, Tn::kSharedCold, true><<<(unsigned)blocks, T, 0, st>>>(L);
-                g_launches.fetch_add(1);
-                return (int)cudaGetLastError();
-            }
-        }
-        radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true><<<(unsigned)blocks, T, 0, st>>>(L);
-    }
-    else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false><<<(unsigned)blocks, T, 0, st>>>(L);
-    g_launches.fetch_add(1);
-    return (int)cudaGetLastError();
-}
-
-template <class P>
-static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
-    constexpr int T = BlockSize<P>::value;
-    const int64_t blocks = (L.N + T - 1) / T;
-    bdf_kernel<P, T><<<(unsigned)blocks, T, 0, st>>>(L);
-    g_launches.fetch_add(1);
-    return (int)cudaGetLastError();
-}
-
-template <class P>
-__global__ void residual_kernel(int64_t N, int64_t ld, double t, const double* __restrict__ y,
-                                const double* __restrict__ yp, const double* __restrict__ params,
-                                double* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    double yy[P::N], yyp[P::N], pp[P::NP > 0 ? P::NP : 1], f[P::N];
-    for (int j = 0; j < P::N; ++j) { yy[j] = y[j * ld + i]; yyp[j] = yp[j * ld + i]; }
-    for (int j = 0; j < P::NP; ++j) pp[j] = params[j * ld + i];
-    P::eval(t, yy, yyp, pp, f);
-    for (int j = 0; j < P::N; ++j) out[j * ld + i] = f[j];
-}
-
-template <class P>
-static int launch_residual(int64_t N, int64_t ld, double t, const double* y, const double* yp,
-                           const double* params, double* out, cudaStream_t st) {
-    residual_kernel<P><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, ld, t, y, yp, params, out);
-    g_launches.fetch_add(1);
-    return (int)cudaGetLastError();
-}
-
-struct ProblemEntry {
-    const char* name;
-    int n, n_params;
-    radau_launcher radau[B200DAE_MAX_STAGES + 1];   // indexed by the number of stages
-    bdf_launcher bdf;
-    residual_launcher residual;
-};
-
-template <class P, bool S1, bool S5, bool S7>
-static ProblemEntry make_entry() {
-    ProblemEntry e;
-    memset(&e, 0, sizeof(e));
-    e.name = P::name();
-    e.n = P::N;
-    e.n_params = P::NP;
-    e.radau[3] = launch_radau<P, 3>;
-    if constexpr (S1) e.radau[1] = launch_radau<P, 1>;
-    if constexpr (S5) e.radau[5] = launch_radau<P, 5>;
-    if constexpr (S7) e.radau[7] = launch_radau<P, 7>;
-    e.bdf = launch_bdf<P>;
-    e.residual = launch_residual<P>;
-    return e;
-}
-
 static const ProblemEntry* registry(int* count) {
-    static const ProblemEntry table[] = {
-        // (problem; Radau stage counts compiled besides s = 3: s = 1, 5, 7)
-        make_entry<Robertson, true, true, true>(),
-        make_entry<AkzoNobel, false, true, false>(),
-        make_entry<Transamp, false, true, false>(),
-        make_entry<Andrews, false, true, false>(),
-    };
+    static const ProblemEntry table[] = {entry_robertson(), entry_akzo_nobel(), entry_transamp(), entry_andrews()};
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;
 }

@@ -1,0 +1,409 @@
+// bdf_group.cuh — variable-order BDF/NDF integration with G cooperating lanes per system.
+//
+// Same replacement scope and flattened control flow as bdf.cuh (BDFDAE._step_impl bdf.py:263-415,
+// solve_bdf_system bdf.py:32-64, change_D / compute_R bdf.py:14-29, BdfDenseOutput
+// bdf.py:422-548, solve_dae's loop dae.py:446-518) for n > 4.  Lane j owns component j: its
+// column of the backward-difference array D lives in registers (rows beyond the current order
+// are masked, not indexed), norms are butterfly all-reduces, the LU and the triangular solves
+// are the row-per-lane routines of group.cuh, the FD Jacobian runs its columns on n lanes at
+// once (radau_group.cuh: fd_jacobian_group).
+#pragma once
+#include <stdint.h>
+#include "../../include/b200dae.h"
+#include "bdf.cuh"
+#include "radau_group.cuh"
+
+namespace b200dae {
+
+template <int N, int G>
+struct BdfGroupLayout {
+    static constexpr int LD = N | 1;
+    static constexpr int kJ = N * LD;
+    static constexpr int kLU = N * LD + N + ((N * LD + N) & 1);
+    static constexpr int kFd = 3 * G * LD + ((3 * G * LD) & 1);
+    static constexpr int oJy = 0, oJyp = kJ, oLU = 2 * kJ, oWork = oLU + kLU;
+    static constexpr int oY = oWork + kFd, oYp = oY + LD, oF = oYp + LD;
+    static constexpr int oIdx = oF + LD + ((3 * LD) & 1);
+    static constexpr int kDoubles = oIdx + (G + 1) / 2 + ((oIdx + (G + 1) / 2) & 1);
+};
+
+// change_D (bdf.py:24-29) for one component: D[:order+1] <- (R U)^T D[:order+1], evaluated as
+// U^T (R^T D) with R generated column by column (bdf.py:14-21).
+__device__ __forceinline__ void change_D_lane(double (&D)[kBdfRows], int order, double factor,
+                                              const double* __restrict__ Umat) {
+    const int q = order + 1;
+    double E[kBdfQ];
+#pragma unroll
+    for (int j = 0; j < kBdfQ; ++j) {
+        double acc = D[0];
+        double r = 1.0;
+#pragma unroll
+        for (int l = 1; l < kBdfQ; ++l) {
+            r *= (j == 0) ? 0.0 : ((l - 1) - factor * j) * (1.0 / l);
+            if (l < q) acc = fma(r, D[l], acc);
+        }
+        E[j] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < kBdfQ; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < kBdfQ; ++l)
+            if (l < q) acc = fma(Umat[l * kBdfQ + i], E[l], acc);
+        if (i < q) D[i] = acc;
+    }
+}
+
+template <class P, int G, int kThreads>
+__global__ void __launch_bounds__(kThreads)
+bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
+    constexpr int N = P::N, NP = P::NP;
+    using Lay = BdfGroupLayout<N, G>;
+    constexpr int LD = Lay::LD;
+    static_assert(G >= N, "group must cover the components");
+    extern __shared__ __align__(16) double smem[];
+
+    const Group<G> g;
+    const int lane = g.lane;
+    const bool act = lane < N;
+    const int64_t inst = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
+    if (inst >= L.N) return;
+    const int64_t ld = L.ld;
+
+    double* sm = smem + (size_t)(threadIdx.x / G) * Lay::kDoubles;
+    double* sJy = sm + Lay::oJy;
+    double* sJyp = sm + Lay::oJyp;
+    double* sWork = sm + Lay::oWork;
+    double* sY = sm + Lay::oY;
+    double* sYp = sm + Lay::oYp;
+    double* sF = sm + Lay::oF;
+    double* sLU = sm + Lay::oLU;
+    int* sIdx = reinterpret_cast<int*>(sm + Lay::oIdx);
+
+    double p[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) p[j] = L.params[j * ld + inst];
+    const int jc = act ? lane : 0;
+    double y = act ? L.y0[jc * ld + inst] : 0.0;
+    double yp = act ? L.yp0[jc * ld + inst] : 0.0;
+    const double atol_j = L.atol[jc], thr_j = L.thr[jc];
+    double fac_y = kNjInitFactor, fac_yp = kNjInitFactor;
+
+    int perm = lane;
+    const double* rrow = sLU + jc * LD;
+
+    const double dir = L.dir, rtol = L.rtol;
+    double t = L.t0;
+    double h_abs;
+    if (L.first_step > 0.0) {
+        h_abs = L.first_step;
+    } else {                                               // select_initial_step, common.py:129-183
+        const double v = act ? fabs(yp * fast_rcp(fmax(fabs(y), thr_j))) : 0.0;
+        double e = g.max(v);
+        if (g.any(v != v)) e = nan("");
+        const double rh = e * fast_rcp(fast_sqrt(rtol) * 0.8);
+        h_abs = fmin(L.max_step, fabs(L.t_bound - L.t0));
+        if (h_abs * rh > 1.0) h_abs = fast_rcp(rh);
+        h_abs = fmax(h_abs, 16.0 * kEps * fabs(L.t0));
+    }
+    double D[kBdfRows];
+#pragma unroll
+    for (int i = 0; i < kBdfRows; ++i) D[i] = 0.0;         // bdf.py:254-257
+    D[0] = y;
+    D[1] = yp * h_abs * dir;
+    int order = 1, n_equal_steps = 0;
+    const int max_order = L.max_order;
+
+    bool need_jac = true, lu_valid = false, step_begin = true, retry = false, current_jac = false;
+    int32_t nfev = 0, njev = 0, nlu = 0, nsolve = 0, nacc = 0, nrej = 0, nfail = 0, niter = 0;
+    int32_t status = B200DAE_ST_RUNNING;
+    int64_t ie = 0;
+    int32_t nst = 0;
+
+    if (L.out.t_steps != nullptr && L.out.steps_cap > 0) {
+        if (lane == 0) L.out.t_steps[inst] = t;
+        if (act) {
+            if (L.out.y_steps) L.out.y_steps[lane * ld + inst] = y;
+            if (L.out.yp_steps) L.out.yp_steps[lane * ld + inst] = yp;
+        }
+        nst = 1;
+    }
+    if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; njev = 1; }
+
+    double hl = 0.0, min_step = 0.0, h = 0.0, t_new = 0.0, c = 0.0;
+    double y_predict = 0.0, psi = 0.0, inv_scale = 0.0, y_new = 0.0, yp_new = 0.0, d = 0.0;
+
+    while (status == B200DAE_ST_RUNNING) {
+        // ---- phase J (base.py:297, bdf.py:330) ------------------------------------------------
+        if (need_jac) {
+            fd_jacobian_group<P, G, LD>(g, t, y, yp, p, thr_j, fac_y, fac_yp, sJy, sJyp, sY, sYp, sF, sWork);
+            ++njev;
+            need_jac = false;
+        }
+        // ---- phase B (bdf.py:269-293) -----------------------------------------------------------
+        if (step_begin) {
+            min_step = 10.0 * fabs(nextafter(t, dir * INFINITY) - t);
+            if (h_abs > L.max_step) {
+                hl = L.max_step;
+                change_D_lane(D, order, L.max_step / h_abs, L.U);
+                n_equal_steps = 0;
+            } else if (h_abs < min_step) {
+                hl = min_step;
+                change_D_lane(D, order, min_step / h_abs, L.U);
+                n_equal_steps = 0;
+            } else {
+                hl = h_abs;
+            }
+            current_jac = false;
+            step_begin = false;
+        }
+        // ---- phase A (bdf.py:296-318) -------------------------------------------------------------
+        if (!retry) {
+            if (hl < min_step) { status = B200DAE_ST_TOO_SMALL_STEP; break; }
+            h = hl * dir;
+            t_new = t + h;
+            if (dir * (t_new - L.t_bound) > 0.0) {
+                t_new = L.t_bound;
+                change_D_lane(D, order, fabs(t_new - t) / hl, L.U);
+                n_equal_steps = 0;
+                lu_valid = false;
+            }
+            h = t_new - t;
+            hl = fabs(h);
+            const double rh = fast_rcp(h);
+            double acc = 0.0, ps = 0.0;
+#pragma unroll
+            for (int i = 0; i < kBdfQ; ++i)
+                if (i <= order) acc += D[i];
+#pragma unroll
+            for (int i = 1; i < kBdfQ; ++i)
+                if (i <= order) ps = fma(D[i], L.gamma[i], ps);
+            y_predict = acc;
+            inv_scale = fast_rcp(fma(rtol, fabs(acc), atol_j));
+            psi = ps * rh;
+            c = L.alpha[order] * rh;
+        }
+        retry = false;
+
+        // ---- phase F: LU of Jy + c*Jyp (bdf.py:320-321) ------------------------------------------
+        if (!lu_valid) {
+            bool fin = true;
+            double a[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const double jy = act ? sJy[jc * LD + k] : 0.0, jyp = act ? sJyp[jc * LD + k] : 0.0;
+                a[k] = fma(c, jyp, jy);
+                fin = fin && finite_d(a[k]);
+            }
+            if (!g.all(fin)) { status = B200DAE_ST_NONFINITE; break; }
+            group_lu_factor<N, LD>(g, a, perm, sLU, sIdx);
+            ++nlu;
+            lu_valid = true;
+        }
+
+        // ---- phase N (solve_bdf_system, bdf.py:32-64) ----------------------------------------------
+        bool converged = false;
+        int n_iter;
+        {
+            d = 0.0;
+            y_new = y_predict;
+            double inv_norm_old = 0.0;
+            bool has_old = false;
+            int k = 0;
+            for (; k < kBdfNewtonMaxIter; ++k) {
+                yp_new = fma(c, d, psi);
+                if (act) { sY[lane] = y_new; sYp[lane] = yp_new; }
+                g.sync();
+                if (lane == 0) P::eval(t_new, sY, sYp, p, sF);
+                g.sync();
+                double f = act ? sF[lane] : 0.0;
+                ++nfev;
+                if (!g.all(finite_d(f))) break;
+                f = -f;
+                group_lu_solve_real<N>(g, rrow, perm, f);           // f <- dy
+                ++nsolve;
+                const double q = f * inv_scale;
+                const double ss = g.sum(act ? q * q : 0.0);
+                const double dy_norm = fast_sqrt(ss * (1.0 / N));
+                double rate = 0.0;
+                if (has_old) rate = dy_norm * inv_norm_old;
+                const double cc = dy_norm * fast_rcp(1.0 - rate);
+                if (has_old && (rate >= 1.0 || powi(rate, kBdfNewtonMaxIter - k) * cc > L.newton_tol))
+                    break;                                        // BEFORE the update (bdf.py:52-53)
+                y_new += f;
+                d += f;
+                if (dy_norm == 0.0 || (has_old && rate * cc < L.newton_tol)) {
+                    converged = true;
+                    break;
+                }
+                inv_norm_old = fast_rcp(dy_norm);
+                has_old = true;
+            }
+            n_iter = (k == kBdfNewtonMaxIter) ? kBdfNewtonMaxIter : k + 1;
+            niter += n_iter;
+        }
+        if (!converged) {
+            ++nfail;
+            if (!current_jac) {
+                need_jac = true;
+                current_jac = true;
+                lu_valid = false;
+                retry = true;
+                continue;
+            }
+            hl *= 0.5;
+            change_D_lane(D, order, 0.5, L.U);
+            n_equal_steps = 0;
+            lu_valid = false;
+            continue;
+        }
+
+        // ---- phase E (bdf.py:342-355) ------------------------------------------------------------
+        const double safety = 0.9 * (2 * kBdfNewtonMaxIter + 1) * fast_rcp((double)(2 * kBdfNewtonMaxIter + n_iter));
+        double error_norm;
+        {
+            inv_scale = fast_rcp(fma(rtol, fabs(y_new), atol_j));
+            const double q = L.error_const[order] * d * inv_scale;
+            const double ss = g.sum(act ? q * q : 0.0);
+            error_norm = fast_sqrt(ss * (1.0 / N));
+        }
+        if (error_norm > 1.0) {
+            const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (order + 1)));
+            hl *= factor;
+            change_D_lane(D, order, factor, L.U);
+            n_equal_steps = 0;
+            ++nrej;
+            continue;
+        }
+
+        // ---- phase C (bdf.py:359-415) ------------------------------------------------------------
+        ++n_equal_steps;
+        t = t_new;
+        y = y_new;
+        yp = yp_new;
+        h_abs = hl;
+        ++nacc;
+        {
+            // D[order+2] = d - D[order+1]; D[order+1] = d; D[i] += D[i+1] for i = order..0
+            double Dn[kBdfRows];
+#pragma unroll
+            for (int i = 0; i < kBdfRows; ++i) {
+                double v = D[i];
+                if (i == order + 2) v = d - D[i - 1 >= 0 ? i - 1 : 0];
+                if (i == order + 1) v = d;
+                Dn[i] = v;
+            }
+#pragma unroll
+            for (int i = kBdfRows - 2; i >= 0; --i)
+                if (i <= order) Dn[i] += Dn[i + 1];
+#pragma unroll
+            for (int i = 0; i < kBdfRows; ++i) D[i] = Dn[i];
+        }
+
+        if (n_equal_steps >= order + 1) {
+            double norms[3];
+            norms[1] = error_norm;
+            double dm = 0.0, dp = 0.0;                   // D[order], D[order + 2]
+#pragma unroll
+            for (int i = 0; i < kBdfRows; ++i) {
+                if (i == order) dm = D[i];
+                if (i == order + 2) dp = D[i];
+            }
+            if (order > 1) {
+                const double q = L.error_const[order - 1] * dm * inv_scale;
+                norms[0] = sqrt(g.sum(act ? q * q : 0.0) * (1.0 / N));
+            } else {
+                norms[0] = INFINITY;
+            }
+            if (order < max_order) {
+                const double q = L.error_const[order + 1] * dp * inv_scale;
+                norms[2] = sqrt(g.sum(act ? q * q : 0.0) * (1.0 / N));
+            } else {
+                norms[2] = INFINITY;
+            }
+            double best = 0.0;
+            int arg = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double fc = pow(norms[i], -1.0 / (order + i));
+                if (i == 0 || (best == best && (fc > best || fc != fc))) { best = fc; arg = i; }
+            }
+            order += arg - 1;
+            const double factor = fmin(10.0, safety * best);
+            h_abs *= factor;
+            change_D_lane(D, order, factor, L.U);
+            n_equal_steps = 0;
+            lu_valid = false;
+        }
+
+        if (L.out.t_eval != nullptr) {                   // BdfDenseOutput, bdf.py:417-419, 525-548
+            const double hh = h_abs * dir;
+            while (ie < L.out.m) {
+                const double te = __ldg(L.out.t_eval + ie);
+                if (!(dir > 0.0 ? te <= t : te >= t)) break;
+                double ya = D[0], ypa = 0.0;
+                double fact = 1.0, hj = 1.0;
+#pragma unroll
+                for (int jj = 1; jj < kBdfQ; ++jj) {
+                    fact *= jj;
+                    hj *= hh;
+                    double fc = 1.0, dfac = 0.0;
+#pragma unroll
+                    for (int mm = 0; mm < jj; ++mm) {
+                        fc *= te - (t - mm * hh);
+                        double dprod = 1.0;
+#pragma unroll
+                        for (int i = 0; i < jj; ++i)
+                            if (i != mm) dprod *= te - (t - i * hh);
+                        dfac += dprod;
+                    }
+                    const double rden = 1.0 / (fact * hj);
+                    if (jj <= order) {
+                        ya = fma(D[jj], fc * rden, ya);
+                        ypa = fma(D[jj], dfac * rden, ypa);
+                    }
+                }
+                if (act) {
+                    L.out.y_eval[(ie * N + lane) * ld + inst] = ya;
+                    if (L.out.yp_eval) L.out.yp_eval[(ie * N + lane) * ld + inst] = ypa;
+                }
+                ++ie;
+            }
+        }
+        if (L.out.t_steps != nullptr && nst < L.out.steps_cap) {
+            if (lane == 0) L.out.t_steps[(int64_t)nst * ld + inst] = t;
+            if (act) {
+                if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + lane) * ld + inst] = y;
+                if (L.out.yp_steps) L.out.yp_steps[((int64_t)nst * N + lane) * ld + inst] = yp;
+            }
+            ++nst;
+        }
+        step_begin = true;
+        if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;
+        else if (L.max_steps > 0 && nacc >= L.max_steps) status = B200DAE_ST_MAX_STEPS;
+    }
+
+    if (act) {
+        L.out.y_final[lane * ld + inst] = y;
+        if (L.out.yp_final) L.out.yp_final[lane * ld + inst] = yp;
+    }
+    if (lane == 0) {
+        L.out.t_final[inst] = t;
+        L.out.status[inst] = status;
+        if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
+        if (L.out.n_steps) L.out.n_steps[inst] = nst;
+        if (L.out.counters) {
+            int32_t* cn = L.out.counters + inst;
+            cn[B200DAE_CNT_NFEV * ld] = nfev;
+            cn[B200DAE_CNT_NJEV * ld] = njev;
+            cn[B200DAE_CNT_NLU * ld] = nlu;
+            cn[B200DAE_CNT_NSOLVE * ld] = nsolve;
+            cn[B200DAE_CNT_ACCEPTED * ld] = nacc;
+            cn[B200DAE_CNT_ERR_REJECTED * ld] = nrej;
+            cn[B200DAE_CNT_NEWTON_FAIL * ld] = nfail;
+            cn[B200DAE_CNT_NEWTON_ITER * ld] = niter;
+        }
+    }
+}
+
+}  // namespace b200dae

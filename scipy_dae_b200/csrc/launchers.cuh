@@ -1,0 +1,175 @@
+// launchers.cuh — launch shapes and the per-problem dispatch entry (problem, stages) -> kernel.
+// Each problem is instantiated in its own translation unit (problem_*.cu) so the library builds
+// in parallel; b200dae.cu only holds the C-ABI and the registry.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/b200dae.h"
+#include "bdf.cuh"
+#include "bdf_group.cuh"
+#include "problems.cuh"
+#include "radau.cuh"
+#include "radau_group.cuh"
+
+namespace b200dae {
+
+extern std::atomic<int64_t> g_launches;
+
+typedef int (*radau_launcher)(const RadauLaunch&, cudaStream_t);
+typedef int (*bdf_launcher)(const BdfLaunch&, cudaStream_t);
+typedef int (*residual_launcher)(int64_t, int64_t, double, const double*, const double*,
+                                 const double*, double*, cudaStream_t);
+
+struct ProblemEntry {
+    const char* name;
+    int n, n_params;
+    radau_launcher radau[B200DAE_MAX_STAGES + 1];   // indexed by the number of stages
+    bdf_launcher bdf;
+    residual_launcher residual;
+};
+
+ProblemEntry entry_robertson();
+ProblemEntry entry_akzo_nobel();
+ProblemEntry entry_transamp();
+ProblemEntry entry_andrews();
+
+// threads per block: register-regime kernels keep ~255 registers per thread live, so 128
+// threads x 2 blocks fill an SM's register file; the local-memory regime prefers fewer
+// threads per SM so that its per-thread arrays stay L1-resident.
+template <class P> struct BlockSize { static constexpr int value = Regime<P::N>::kReg ? 128 : 64; };
+
+// Launch shape of the Radau kernel per (problem size, stages).
+//   register regime (n <= 4): 64-thread blocks, the cold per-instance state in shared memory
+//   (when it fits the 48 KB static limit); for s = 3 the register cap is 168 so that 6 blocks =
+//   3 warps per scheduler are resident (measured on B200, 2^20 Robertson instances:
+//   255 regs/2 warps 18.9 ms, 168 regs/3 warps 15.6 ms, 128 regs/4 warps (spills) 17.7 ms).
+//   local-memory regime (n > 4): 64-thread blocks so the per-thread arrays stay L1-resident.
+template <class P, int S>
+struct RadauTune {
+    static constexpr int N = P::N, NCS = S / 2;
+    static constexpr bool kReg = Regime<N>::kReg;
+    static constexpr int kThreads = 64;
+    static constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
+    static constexpr bool kSharedCold = kReg && (kCold * kThreads * 8 <= 48 * 1024);
+    static constexpr int kMinBlocks = (kSharedCold && S <= 3) ? 6 : 1;
+};
+
+// Group size of the cooperative kernels (group.cuh): the smallest power of two >= n (>= 8).
+template <int N> struct GroupSize { static constexpr int value = N <= 8 ? 8 : (N <= 16 ? 16 : 32); };
+
+// B200DAE_REGIME=thread forces the one-thread-per-system kernels for n > 4 (A/B measurements).
+static bool force_thread_regime() {
+    static const bool v = getenv("B200DAE_REGIME") && strcmp(getenv("B200DAE_REGIME"), "thread") == 0;
+    return v;
+}
+
+template <class P, int S>
+static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
+    constexpr int G = GroupSize<P::N>::value;
+    constexpr int T = (G == 32) ? 32 : 64;
+    using Lay = RadauGroupLayout<P::N, S, G>;
+    constexpr size_t smem = (size_t)(T / G) * Lay::kDoubles * sizeof(double);
+    static_assert(smem <= 227 * 1024, "per-block shared memory");
+    auto kern = radau_group_kernel<P, S, G, T>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (rc != cudaSuccess) return (int)rc;
+        attr_set = true;
+    }
+    const int64_t blocks = (L.N * G + T - 1) / T;
+    kern<<<(unsigned)blocks, T, smem, st>>>(L);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <class P, int S>
+static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
+    if constexpr (!Regime<P::N>::kReg) {
+        if (!force_thread_regime()) return launch_radau_group<P, S>(L, st);
+    }
+    using Tn = RadauTune<P, S>;
+    constexpr int T = Tn::kThreads;
+    const int64_t blocks = (L.N + T - 1) / T;
+    const bool lean = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_eval == nullptr &&
+                      L.out.t_steps == nullptr;
+    if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true><<<(unsigned)blocks, T, 0, st>>>(L);
+    else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false><<<(unsigned)blocks, T, 0, st>>>(L);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <class P>
+static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
+    constexpr int G = GroupSize<P::N>::value;
+    constexpr int T = (G == 32) ? 32 : 64;
+    using Lay = BdfGroupLayout<P::N, G>;
+    constexpr size_t smem = (size_t)(T / G) * Lay::kDoubles * sizeof(double);
+    static_assert(smem <= 227 * 1024, "per-block shared memory");
+    auto kern = bdf_group_kernel<P, G, T>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (rc != cudaSuccess) return (int)rc;
+        attr_set = true;
+    }
+    const int64_t blocks = (L.N * G + T - 1) / T;
+    kern<<<(unsigned)blocks, T, smem, st>>>(L);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <class P>
+static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
+    if constexpr (!Regime<P::N>::kReg) {
+        if (!force_thread_regime()) return launch_bdf_group<P>(L, st);
+    }
+    constexpr int T = BlockSize<P>::value;
+    const int64_t blocks = (L.N + T - 1) / T;
+    bdf_kernel<P, T><<<(unsigned)blocks, T, 0, st>>>(L);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <class P>
+__global__ void residual_kernel(int64_t N, int64_t ld, double t, const double* __restrict__ y,
+                                const double* __restrict__ yp, const double* __restrict__ params,
+                                double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double yy[P::N], yyp[P::N], pp[P::NP > 0 ? P::NP : 1], f[P::N];
+    for (int j = 0; j < P::N; ++j) { yy[j] = y[j * ld + i]; yyp[j] = yp[j * ld + i]; }
+    for (int j = 0; j < P::NP; ++j) pp[j] = params[j * ld + i];
+    P::eval(t, yy, yyp, pp, f);
+    for (int j = 0; j < P::N; ++j) out[j * ld + i] = f[j];
+}
+
+template <class P>
+static int launch_residual(int64_t N, int64_t ld, double t, const double* y, const double* yp,
+                           const double* params, double* out, cudaStream_t st) {
+    residual_kernel<P><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, ld, t, y, yp, params, out);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <class P, bool S1, bool S5, bool S7>
+static ProblemEntry make_entry() {
+    ProblemEntry e;
+    memset(&e, 0, sizeof(e));
+    e.name = P::name();
+    e.n = P::N;
+    e.n_params = P::NP;
+    e.radau[3] = launch_radau<P, 3>;
+    if constexpr (S1) e.radau[1] = launch_radau<P, 1>;
+    if constexpr (S5) e.radau[5] = launch_radau<P, 5>;
+    if constexpr (S7) e.radau[7] = launch_radau<P, 7>;
+    e.bdf = launch_bdf<P>;
+    e.residual = launch_residual<P>;
+    return e;
+}
+
+}  // namespace b200dae
