@@ -10,7 +10,8 @@ import os
 from .constants import CRadauTables
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200dae.so")
+# B200DAE_LIB selects an alternative build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("B200DAE_LIB") or os.path.join(HERE, "libb200dae.so")
 
 NUM_COUNTERS = 8
 COUNTER_NAMES = ("nfev", "njev", "nlu", "nsolve", "n_accepted", "n_err_rejected",

@@ -24,13 +24,15 @@ struct BdfGroupLayout {
     static constexpr int oJy = 0, oJyp = kJ, oLU = 2 * kJ, oWork = oLU + kLU;
     static constexpr int oY = oWork + kFd, oYp = oY + LD, oF = oYp + LD;
     static constexpr int oIdx = oF + LD + ((3 * LD) & 1);
-    static constexpr int kDoubles = oIdx + (G + 1) / 2 + ((oIdx + (G + 1) / 2) & 1);
+    static constexpr int oPar = oIdx + (G + 1) / 2;
+    __host__ __device__ static constexpr int doubles(int np) { return oPar + np + ((oPar + np) & 1); }
 };
 
 // change_D (bdf.py:24-29) for one component: D[:order+1] <- (R U)^T D[:order+1], evaluated as
 // U^T (R^T D) with R generated column by column (bdf.py:14-21).
-__device__ __forceinline__ void change_D_lane(double (&D)[kBdfRows], int order, double factor,
-                                              const double* __restrict__ Umat) {
+// Not inlined: six call sites; the array travels through the local stack (9 loads + 9 stores).
+static __device__ __noinline__ void change_D_lane(double* __restrict__ D, int order, double factor,
+                                           const double* __restrict__ Umat) {
     const int q = order + 1;
     double E[kBdfQ];
 #pragma unroll
@@ -54,8 +56,18 @@ __device__ __forceinline__ void change_D_lane(double (&D)[kBdfRows], int order, 
     }
 }
 
-template <class P, int G, int kThreads>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void change_D_call(double (&D)[kBdfRows], int order, double factor,
+                                              const double* __restrict__ Umat) {
+    double tmp[kBdfRows];
+#pragma unroll
+    for (int i = 0; i < kBdfRows; ++i) tmp[i] = D[i];
+    change_D_lane(tmp, order, factor, Umat);
+#pragma unroll
+    for (int i = 0; i < kBdfRows; ++i) D[i] = tmp[i];
+}
+
+template <class P, int G, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     constexpr int N = P::N, NP = P::NP;
     using Lay = BdfGroupLayout<N, G>;
@@ -70,7 +82,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     if (inst >= L.N) return;
     const int64_t ld = L.ld;
 
-    double* sm = smem + (size_t)(threadIdx.x / G) * Lay::kDoubles;
+    double* sm = smem + (size_t)(threadIdx.x / G) * Lay::doubles(NP);
     double* sJy = sm + Lay::oJy;
     double* sJyp = sm + Lay::oJyp;
     double* sWork = sm + Lay::oWork;
@@ -80,9 +92,9 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     double* sLU = sm + Lay::oLU;
     int* sIdx = reinterpret_cast<int*>(sm + Lay::oIdx);
 
-    double p[NP > 0 ? NP : 1];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) p[j] = L.params[j * ld + inst];
+    double* p = sm + Lay::oPar;
+    for (int j = lane; j < NP; j += G) p[j] = L.params[j * ld + inst];
+    g.sync();
     const int jc = act ? lane : 0;
     double y = act ? L.y0[jc * ld + inst] : 0.0;
     double yp = act ? L.yp0[jc * ld + inst] : 0.0;
@@ -145,11 +157,11 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             min_step = 10.0 * fabs(nextafter(t, dir * INFINITY) - t);
             if (h_abs > L.max_step) {
                 hl = L.max_step;
-                change_D_lane(D, order, L.max_step / h_abs, L.U);
+                change_D_call(D, order, L.max_step / h_abs, L.U);
                 n_equal_steps = 0;
             } else if (h_abs < min_step) {
                 hl = min_step;
-                change_D_lane(D, order, min_step / h_abs, L.U);
+                change_D_call(D, order, min_step / h_abs, L.U);
                 n_equal_steps = 0;
             } else {
                 hl = h_abs;
@@ -164,7 +176,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             t_new = t + h;
             if (dir * (t_new - L.t_bound) > 0.0) {
                 t_new = L.t_bound;
-                change_D_lane(D, order, fabs(t_new - t) / hl, L.U);
+                change_D_call(D, order, fabs(t_new - t) / hl, L.U);
                 n_equal_steps = 0;
                 lu_valid = false;
             }
@@ -214,7 +226,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
                 yp_new = fma(c, d, psi);
                 if (act) { sY[lane] = y_new; sYp[lane] = yp_new; }
                 g.sync();
-                if (lane == 0) P::eval(t_new, sY, sYp, p, sF);
+                if (lane == 0) eval_shared<P>(t_new, sY, sYp, p, sF);
                 g.sync();
                 double f = act ? sF[lane] : 0.0;
                 ++nfev;
@@ -252,7 +264,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
                 continue;
             }
             hl *= 0.5;
-            change_D_lane(D, order, 0.5, L.U);
+            change_D_call(D, order, 0.5, L.U);
             n_equal_steps = 0;
             lu_valid = false;
             continue;
@@ -270,7 +282,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         if (error_norm > 1.0) {
             const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (order + 1)));
             hl *= factor;
-            change_D_lane(D, order, factor, L.U);
+            change_D_call(D, order, factor, L.U);
             n_equal_steps = 0;
             ++nrej;
             continue;
@@ -331,7 +343,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             order += arg - 1;
             const double factor = fmin(10.0, safety * best);
             h_abs *= factor;
-            change_D_lane(D, order, factor, L.U);
+            change_D_call(D, order, factor, L.U);
             n_equal_steps = 0;
             lu_valid = false;
         }

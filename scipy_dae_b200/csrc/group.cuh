@@ -55,6 +55,7 @@ struct Group {
     }
     __device__ __forceinline__ bool all(bool p) const { return __all_sync(mask, p) != 0; }
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(mask, p); }
     __device__ __forceinline__ int rmax(int v) const { return __reduce_max_sync(mask, v); }
     __device__ __forceinline__ unsigned rmax(unsigned v) const { return __reduce_max_sync(mask, v); }
     __device__ __forceinline__ int rmin(int v) const { return __reduce_min_sync(mask, v); }
@@ -66,11 +67,29 @@ template <class Grp>
 __device__ __forceinline__ bool pivot_search(const Grp& g, bool cand, double v, int pos, int& ppos) {
     const int hi = cand ? __double2hiint(v) : -1;
     const int mhi = g.rmax(hi);
-    const unsigned lo = (cand && hi == mhi) ? (unsigned)__double2loint(v) : 0u;
-    const unsigned mlo = g.rmax(lo);
-    const bool match = cand && hi == mhi && lo == mlo;
-    ppos = g.rmin(match ? pos : (1 << 20));
-    return match && pos == ppos;
+    bool match = cand && hi == mhi;
+#ifdef B200DAE_SLOW_PIVOT
+    {
+        const unsigned lo = match ? (unsigned)__double2loint(v) : 0u;
+        const unsigned mlo = g.rmax(lo);
+        match = match && lo == mlo;
+        ppos = g.rmin(match ? pos : (1 << 20));
+        return match && pos == ppos;
+    }
+#endif
+    unsigned b = g.ballot(match);
+    if (b & (b - 1u)) {                                 // several lanes share the high word (rare)
+        const unsigned lo = match ? (unsigned)__double2loint(v) : 0u;
+        const unsigned mlo = g.rmax(lo);
+        match = match && lo == mlo;
+        b = g.ballot(match);
+        if (b & (b - 1u)) {                             // exact ties: LAPACK takes the first position
+            ppos = g.rmin(match ? pos : (1 << 20));
+            return match && pos == ppos;
+        }
+    }
+    ppos = __shfl_sync(g.mask, pos, __ffs(b) - 1);
+    return match;
 }
 
 // Real LU.  a[0..N-1] = row `lane` of the matrix (lanes >= N: ignored).  On return

@@ -15,6 +15,10 @@
 #include "radau.cuh"
 #include "radau_group.cuh"
 
+#ifndef B200DAE_GROUP_MINBLOCKS
+#define B200DAE_GROUP_MINBLOCKS(G) ((G) == 32 ? 1 : 6)
+#endif
+
 namespace b200dae {
 
 extern std::atomic<int64_t> g_launches;
@@ -72,9 +76,11 @@ static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
     constexpr int G = GroupSize<P::N>::value;
     constexpr int T = (G == 32) ? 32 : 64;
     using Lay = RadauGroupLayout<P::N, S, G>;
-    constexpr size_t smem = (size_t)(T / G) * Lay::kDoubles * sizeof(double);
+    constexpr size_t smem = (size_t)(T / G) * Lay::doubles(P::NP) * sizeof(double);
     static_assert(smem <= 227 * 1024, "per-block shared memory");
-    auto kern = radau_group_kernel<P, S, G, T>;
+    // sub-warp groups: cap the registers at 168 so that six 64-thread blocks (12 warps) share an SM
+    constexpr int MB = B200DAE_GROUP_MINBLOCKS(G);
+    auto kern = radau_group_kernel<P, S, G, T, MB>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -108,9 +114,10 @@ static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
     constexpr int G = GroupSize<P::N>::value;
     constexpr int T = (G == 32) ? 32 : 64;
     using Lay = BdfGroupLayout<P::N, G>;
-    constexpr size_t smem = (size_t)(T / G) * Lay::kDoubles * sizeof(double);
+    constexpr size_t smem = (size_t)(T / G) * Lay::doubles(P::NP) * sizeof(double);
     static_assert(smem <= 227 * 1024, "per-block shared memory");
-    auto kern = bdf_group_kernel<P, G, T>;
+    constexpr int MB = B200DAE_GROUP_MINBLOCKS(G);
+    auto kern = bdf_group_kernel<P, G, T, MB>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -64,17 +64,21 @@ struct Transamp {
         const double UF = 0.026, ALPHA = 0.99, R = 9000.0;
         const double C1 = 1e-6, C2 = 2e-6, C3 = 3e-6, C4 = 4e-6, C5 = 5e-6;
         const double Ub = p[0], R0 = p[1], beta = p[2];
+        // divisions by the constants UF, R and by R0 are multiplications by reciprocals here
+        // (<= 1 ulp from the quotient; an IEEE FP64 division is ~50 instructions on sm_100a)
+        const double rUF = 1.0 / UF, rR = 1.0 / R, rR0 = 1.0 / R0;
         const double Ue = 0.1 * sin(200.0 * 3.14159265358979323846 * t);
-        const double g23 = beta * (exp((y[1] - y[2]) / UF) - 1.0);
-        const double g56 = beta * (exp((y[4] - y[5]) / UF) - 1.0);
-        const double f0 = -Ue / R0 + y[0] / R0;
-        const double f1 = -Ub / R + y[1] * (2.0 / R) - (ALPHA - 1.0) * g23;
-        const double f2 = -g23 + y[2] / R;
-        const double f3 = -Ub / R + y[3] / R + ALPHA * g23;
-        const double f4 = -Ub / R + y[4] * (2.0 / R) - (ALPHA - 1.0) * g56;
-        const double f5 = -g56 + y[5] / R;
-        const double f6 = -Ub / R + y[6] / R + ALPHA * g56;
-        const double f7 = y[7] / R;
+        const double g23 = beta * (exp((y[1] - y[2]) * rUF) - 1.0);
+        const double g56 = beta * (exp((y[4] - y[5]) * rUF) - 1.0);
+        const double UbR = Ub * rR;
+        const double f0 = (y[0] - Ue) * rR0;
+        const double f1 = -UbR + y[1] * (2.0 * rR) - (ALPHA - 1.0) * g23;
+        const double f2 = -g23 + y[2] * rR;
+        const double f3 = -UbR + y[3] * rR + ALPHA * g23;
+        const double f4 = -UbR + y[4] * (2.0 * rR) - (ALPHA - 1.0) * g56;
+        const double f5 = -g56 + y[5] * rR;
+        const double f6 = -UbR + y[6] * rR + ALPHA * g56;
+        const double f7 = y[7] * rR;
         out[0] = (-C1 * yp[0] + C1 * yp[1]) - f0;
         out[1] = (C1 * yp[0] - C1 * yp[1]) - f1;
         out[2] = (-C2 * yp[2]) - f2;
@@ -122,9 +126,13 @@ struct Andrews {
         sincos(q[4], &sin_de, &cos_de);
         sincos(q[5], &sin_Om, &cos_Om);
         sincos(q[6], &sin_ep, &cos_ep);
-        sincos(q[0] + q[1], &sin_be_Th, &cos_be_Th);
-        sincos(q[3] + q[4], &sin_Ph_de, &cos_Ph_de);
-        sincos(q[5] + q[6], &sin_Om_ep, &cos_Om_ep);
+        // angle sums by the addition theorems (3 of the 10 sincos of the NumPy twin)
+        sin_be_Th = fma(sin_be, cos_Th, cos_be * sin_Th);
+        cos_be_Th = fma(cos_be, cos_Th, -sin_be * sin_Th);
+        sin_Ph_de = fma(sin_Phi, cos_de, cos_Phi * sin_de);
+        cos_Ph_de = fma(cos_Phi, cos_de, -sin_Phi * sin_de);
+        sin_Om_ep = fma(sin_Om, cos_ep, cos_Om * sin_ep);
+        cos_Om_ep = fma(cos_Om, cos_ep, -sin_Om * sin_ep);
 
         const double M00 = m1 * ra * ra + m2 * (rr * rr - 2 * da * rr * cos_Th + da * da) + I1 + I2;
         const double M01 = m2 * (da * da - da * rr * cos_Th) + I2;

@@ -28,7 +28,7 @@
 namespace b200dae {
 
 template <int N, int S, int G>
-struct RadauGroupLayout {
+struct RadauGroupLayout {   // offsets in doubles inside one group's shared-memory block
     static constexpr int NCS = S / 2;
     static constexpr int LD = N | 1;                       // odd leading dimension: conflict-free rows
     static constexpr int LDC = N | 1;                      // in double2 units
@@ -43,8 +43,26 @@ struct RadauGroupLayout {
     static constexpr int oWork = oLUr + kLUr;
     static constexpr int oY = oWork + kWork, oYp = oY + kVec, oF = oYp + kVec;
     static constexpr int oIdx = oF + kVec + ((3 * kVec) & 1);        // G ints
-    static constexpr int kDoubles = oIdx + (G + 1) / 2 + ((oIdx + (G + 1) / 2) & 1);   // keep groups 16 B aligned
+    static constexpr int oPar = oIdx + (G + 1) / 2;                  // NP parameters (appended by the kernel)
+    __host__ __device__ static constexpr int doubles(int np) { return oPar + np + ((oPar + np) & 1); }   // keep groups 16 B aligned
 };
+
+// Residual call of the cooperative kernels (all pointers point into shared memory).  Small
+// functors are inlined at the four call sites; a large one (Andrews) declares itself
+// __noinline__ and then exists once per kernel.  A __noinline__ wrapper for every functor was
+// tried (it shrinks the transistor-amplifier kernel from 94 to 70 KB) and is kept behind
+// -DB200DAE_NOINLINE_EVAL, but with it the amplifier ensembles fail after t = 7e-4 on sm_100a
+// (nvcc 12.9) while the inlined build of the same source is correct, so it is off.
+#ifdef B200DAE_NOINLINE_EVAL
+#define B200DAE_EVAL_ATTR __noinline__
+#else
+#define B200DAE_EVAL_ATTR __forceinline__
+#endif
+template <class P>
+__device__ B200DAE_EVAL_ATTR void eval_shared(double t, const double* y, const double* yp, const double* p,
+                                         double* out) {
+    P::eval(t, y, yp, p, out);
+}
 
 // Forward-difference Jacobians, columns in parallel (lane c = column c = perturbed entry c).
 // Per column exactly the arithmetic of fd_jacobian.cuh / scipy num_jac.
@@ -60,7 +78,7 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
     const bool act = c < N;
     if (act) { sy[c] = yj; syp[c] = ypj; }
     g.sync();
-    if (c == 0) P::eval(t, sy, syp, p, sf);
+    if (c == 0) eval_shared<P>(t, sy, syp, p, sf);
     g.sync();
     double* xc = scratch + c * (3 * LD);
     double* fbuf0 = xc + LD;
@@ -89,7 +107,7 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
             for (int attempt = 0; attempt < 2; ++attempt) {
                 double* fnew = attempt ? fbuf1 : fbuf0;
                 xc[c] = xp_try;
-                P::eval(t, wrt_yp ? sy : xc, wrt_yp ? xc : syp, p, fnew);
+                eval_shared<P>(t, wrt_yp ? sy : xc, wrt_yp ? xc : syp, p, fnew);
                 double best = -1.0, f_at = 0.0, fn_at = 0.0, d_at = 0.0;
                 for (int r = 0; r < N; ++r) {
                     const double fr = sf[r], fn = fnew[r];
@@ -124,8 +142,8 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
     g.sync();
 }
 
-template <class P, int S, int G, int kThreads>
-__global__ void __launch_bounds__(kThreads)
+template <class P, int S, int G, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
     using Lay = RadauGroupLayout<N, S, G>;
@@ -141,7 +159,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     const int64_t ld = L.ld;
     const b200dae_radau_tables& tb = L.tb;
 
-    double* sm = smem + (size_t)(threadIdx.x / G) * Lay::kDoubles;
+    double* sm = smem + (size_t)(threadIdx.x / G) * Lay::doubles(NP);
     double* sJy = sm + Lay::oJy;
     double* sJyp = sm + Lay::oJyp;
     double* sWork = sm + Lay::oWork;
@@ -153,9 +171,9 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     double2* sCplx = reinterpret_cast<double2*>(sWork);
 
     // ---- per-instance state: scalars replicated in every lane, vectors one component per lane --
-    double p[NP > 0 ? NP : 1];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) p[j] = L.params[j * ld + inst];
+    double* p = sm + Lay::oPar;                            // per-instance parameters, shared by the group
+    for (int j = lane; j < NP; j += G) p[j] = L.params[j * ld + inst];
+    g.sync();
     const int jc = act ? lane : 0;                        // clamped component index for loads
     double y = act ? L.y0[jc * ld + inst] : 0.0;
     double yp = act ? L.yp0[jc * ld + inst] : 0.0;
@@ -316,7 +334,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                     for (int i = 0; i < S; ++i) { sY[i * LD + lane] = Y[i]; sYp[i * LD + lane] = Yp[i]; }
                 }
                 g.sync();
-                if (lane < S) P::eval(fma(h, tb.C[lane], t), sY + lane * LD, sYp + lane * LD, p, sF + lane * LD);
+                if (lane < S) eval_shared<P>(fma(h, tb.C[lane], t), sY + lane * LD, sYp + lane * LD, p, sF + lane * LD);
                 g.sync();
                 bool fin = true;
 #pragma unroll
@@ -424,7 +442,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                     const double yph = (emb == 1) ? yph0 : fma(yh, rhm, yph0);
                     if (act) { sY[lane] = yh; sYp[lane] = yph; }
                     g.sync();
-                    if (lane == 0) P::eval(t_new, sY, sYp, p, sF);
+                    if (lane == 0) eval_shared<P>(t_new, sY, sYp, p, sF);
                     g.sync();
                     e = act ? sF[lane] : 0.0;
                     ++nfev;
