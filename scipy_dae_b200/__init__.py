@@ -4,8 +4,9 @@ Importing the package does not need a GPU; calling a solver does, and fails loud
 libb200dae.so (the sm_100a CUDA library) is missing — there is no CPU fallback.
 """
 from .batched import BatchedDaeResult, solve_dae_batched, device_residual
+from .host_pipeline import solve_dae_batched_host, alloc_host_result, HostResultBuffers
 from .problems import PROBLEMS, Problem, get_problem, perturbed_params, initial_conditions
 
-__all__ = ["solve_dae_batched", "BatchedDaeResult", "device_residual", "PROBLEMS", "Problem",
+__all__ = ["solve_dae_batched", "solve_dae_batched_host", "alloc_host_result", "HostResultBuffers", "BatchedDaeResult", "device_residual", "PROBLEMS", "Problem",
            "get_problem", "perturbed_params", "initial_conditions"]
 __version__ = "0.1.0"

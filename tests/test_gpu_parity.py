@@ -181,3 +181,49 @@ def test_full_size_properties():
     y0b, yp0b = initial_conditions("robertson", params2)
     r2 = solve_dae_batched("robertson", (0.0, 1e7), y0b, yp0b, params2, rtol=1e-6, atol=1e-6)
     assert torch.equal(r2.y_final[N // 2 + 3], r.y_final[17])
+
+
+def test_host_pipeline_matches_device_call():
+    """solve_dae_batched_host (chunked, multi-stream, pinned buffers) returns bit-identical
+    per-instance results to one solve_dae_batched call, for ragged chunkings too."""
+    from scipy_dae_b200 import (solve_dae_batched, solve_dae_batched_host, alloc_host_result,
+                                perturbed_params, initial_conditions)
+    N = 5000
+    params = perturbed_params("robertson", N, 0.1, seed=5)
+    y0, yp0 = initial_conditions("robertson", params)
+    ref = solve_dae_batched("robertson", (0.0, 1e7), y0, yp0, params, rtol=1e-6, atol=1e-6).numpy()
+    out = alloc_host_result(N, 3)
+    for chunks in (1, 3, 7):
+        r = solve_dae_batched_host("robertson", (0.0, 1e7), y0, yp0, params, rtol=1e-6, atol=1e-6,
+                                   chunks=chunks, out=out)
+        assert np.array_equal(r.y_final.numpy(), ref.y_final)
+        assert np.array_equal(r.yp_final.numpy(), ref.yp_final)
+        assert np.array_equal(r.status.numpy(), ref.status)
+        assert np.array_equal(r.nfev.numpy(), ref.nfev) and np.array_equal(r.n_accepted.numpy(), ref.n_accepted)
+    bad = y0.copy(); bad[17, 1] = np.inf
+    with pytest.raises(ValueError, match="must be finite"):
+        solve_dae_batched_host("robertson", (0.0, 1.0), bad, yp0, params, rtol=1e-6, atol=1e-6, chunks=4)
+
+
+def test_group_and_thread_regimes_agree():
+    """n > 4 systems run on the cooperative group-per-system kernels by default; the
+    one-thread-per-system kernels (B200DAE_REGIME=thread, read once per process) implement the
+    same arithmetic, so a subprocess run must agree to rounding."""
+    import subprocess, sys, os, json
+    code = (
+        "import json,sys; sys.path.insert(0, %r);"
+        "from scipy_dae_b200 import solve_dae_batched, perturbed_params, initial_conditions, get_problem;"
+        "pr=get_problem('transamp'); p=perturbed_params('transamp',16,0.02,seed=2); y0,yp0=initial_conditions('transamp',p);"
+        "r=solve_dae_batched('transamp',pr.t_span,y0,yp0,p,method='Radau',rtol=1e-10,atol=1e-6).numpy();"
+        "print(json.dumps(dict(y=r.y_final.tolist(), acc=r.n_accepted.tolist(), st=r.status.tolist())))"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for regime in ("group", "thread"):
+        env = dict(os.environ, B200DAE_REGIME=regime)
+        o = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+        outs.append(json.loads(o.stdout.strip().splitlines()[-1]))
+    a, b = outs
+    assert a["st"] == b["st"] == [0] * 16
+    ya, yb = np.array(a["y"]), np.array(b["y"])
+    assert (np.abs(ya - yb) <= 4.0 * np.maximum(10 * 1e-10 * np.abs(yb), 1e-6)).all()
+    assert (np.abs(np.array(a["acc"]) - np.array(b["acc"])) <= 0.05 * np.array(b["acc"]) + 2).all()
