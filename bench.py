@@ -51,13 +51,16 @@ def parse_args():
     ap.add_argument("--instances", type=int, default=1 << 20, help="instances per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--jac", default="fd", choices=["fd", "analytic"],
+                    help="fd = finite-difference Jacobian (the headline, jac=None in the reference); "
+                         "analytic = the functor's analytic Jacobians (a `jac` callable in the reference)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline chunks of the host-facing call")
     return ap.parse_args()
 
 
-def workload_config(n_per_gpu, n_gpus):
+def workload_config(n_per_gpu, n_gpus, jac="fd"):
     return {"workload": f"robertson_dae_ensemble_N{n_per_gpu}_per_gpu", "problem": "robertson",
-            "method": "Radau IIA s=3, FD Jacobian", "rtol": 1e-6, "atol": 1e-6, "t_span": [0.0, 1e7],
+            "method": "Radau IIA s=3, " + ("FD Jacobian" if jac == "fd" else "analytic Jacobian"), "rtol": 1e-6, "atol": 1e-6, "t_span": [0.0, 1e7],
             "instances_per_gpu": n_per_gpu, "instances_total": n_per_gpu * n_gpus,
             "param_perturbation": "k*exp(0.1*U(-1,1)), default_rng(seed=rank)",
             "t_eval": None, "parallelism": f"instance-sharded x{n_gpus}, no collective",
@@ -68,11 +71,11 @@ def workload_config(n_per_gpu, n_gpus):
 # algorithmic flop model (DESIGN.md "Roofline"): counted from the per-instance
 # work counters the kernel returns, not from hardware
 # --------------------------------------------------------------------------------------------
-def algorithmic_flops(cnt: dict, n: int, s: int, c_f: int) -> float:
+def algorithmic_flops(cnt: dict, n: int, s: int, c_f: int, fd: int = 1) -> float:
     """cnt: dict of SUMS over instances of nfev, njev, nlu, nsolve, n_newton_iter, n_accepted."""
     ncs = s // 2
     n_lu_sets = cnt["nlu"] / (1 + ncs)
-    n_f = cnt["nfev"] + cnt["njev"] * (2 * n + 1)            # every residual evaluation incl. FD columns
+    n_f = cnt["nfev"] + cnt["njev"] * (2 * n + 1) * fd       # every residual evaluation incl. FD columns
     it = cnt["n_newton_iter"]
     solves_real = it + cnt["n_accepted"] + cnt.get("n_err_rejected", 0)   # + error-estimate solves
     solves_cplx = it * ncs
@@ -81,7 +84,7 @@ def algorithmic_flops(cnt: dict, n: int, s: int, c_f: int) -> float:
     fl += n_lu_sets * (2 * n * n + ncs * 4 * n * n)                        # matrix assembly
     fl += solves_real * 2 * n * n + solves_cplx * 8 * n * n                # triangular solves
     fl += it * (3 * 2 * s * s * n + 8 * s * n)                             # TI/T/A transforms, updates, norm
-    fl += cnt["njev"] * 2 * n * 2 * n                                      # FD quotients
+    fl += cnt["njev"] * 2 * n * 2 * n * fd                                 # FD quotients
     return float(fl)
 
 
@@ -259,7 +262,8 @@ def main():
     out.status, out.counters = status.data_ptr(), counters.data_ptr()
     ro = _lib.RadauOpts(rtol=WORKLOAD["rtol"], max_step=float("inf"), first_step=0.0,
                         continuous_error_weight=0.0, jac_recompute_rate=1e-3, deadband_lo=1.0,
-                        deadband_hi=1.2, newton_max_iter=0, newton_iter_embedded=1, max_steps=0)
+                        deadband_hi=1.2, newton_max_iter=0, newton_iter_embedded=1, max_steps=0,
+                        analytic_jac=1 if args.jac == "analytic" else 0)
     tb = radau_tables_c(s)
     atol = (ctypes.c_double * n)(*([WORKLOAD["atol"]] * n))
     stream = torch.cuda.current_stream(dev)
@@ -312,7 +316,8 @@ def main():
     def e2e_step():
         return solve_dae_batched_host("robertson", WORKLOAD["t_span"], h_y0, h_yp0, h_params, method="Radau",
                                       rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], device=dev,
-                                      chunks=args.e2e_chunks, out=host_out)
+                                      chunks=args.e2e_chunks, out=host_out,
+                                      jac="analytic" if args.jac == "analytic" else None)
 
     for _ in range(2):
         e2e_step()
@@ -336,7 +341,7 @@ def main():
     csum = counters.to(torch.int64).sum(dim=1).cpu().numpy()
     cnt = dict(nfev=csum[0], njev=csum[1], nlu=csum[2], nsolve=csum[3], n_accepted=csum[4],
                n_err_rejected=csum[5], n_newton_fail=csum[6], n_newton_iter=csum[7])
-    flops_per_launch = algorithmic_flops(cnt, n, s, 15)
+    flops_per_launch = algorithmic_flops(cnt, n, s, 15, fd=0 if args.jac == "analytic" else 1)
     bytes_per_launch = compulsory_bytes(n, npar) * Nper
 
     # ---- FP64 pipe peak of THIS device (MEASURED_PEAKS.json has no FP64 figure) ----------------------
@@ -384,7 +389,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(Nper, world),
+            "data": "synthetic", "config": workload_config(Nper, world, args.jac),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
                     "timer": "host perf_counter bracketed by cuda synchronize",

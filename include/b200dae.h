@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200DAE_VERSION 100
+#define B200DAE_VERSION 101
 #define B200DAE_MAX_STAGES 7
 #define B200DAE_MAX_ORDER 6
 #define B200DAE_MAX_N 32
@@ -98,6 +98,10 @@ typedef struct b200dae_radau_opts {
     int32_t newton_max_iter;         /* <= 0: 7 + int((s-3)*2.5) */
     int32_t newton_iter_embedded;    /* 1 */
     int64_t max_steps;               /* <= 0: no cap; otherwise stop after this many accepted steps */
+    int32_t analytic_jac;            /* 0: jac=None, finite differences (base.py:250-297);
+                                        1: the functor's analytic Jacobians = a `jac` callable
+                                        (base.py:299-331); compiled for stages = 3 */
+    int32_t reserved;
 } b200dae_radau_opts;
 
 /* keyword arguments of BDFDAE.__init__ (bdf.py:224-227) */
@@ -108,6 +112,8 @@ typedef struct b200dae_bdf_opts {
     int32_t max_order;               /* 1..6, default 5 */
     int32_t ndf_strategy;            /* 0 "stability", 1 "efficiency", 2 plain BDF (bdf.py:242-247) */
     int64_t max_steps;
+    int32_t analytic_jac;            /* as in b200dae_radau_opts */
+    int32_t reserved;
 } b200dae_bdf_opts;
 
 /* Output block shared by both integrators.  Any pointer may be NULL (that output is skipped),

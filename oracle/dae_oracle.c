@@ -276,6 +276,7 @@ void orc_num_jac(orc_residual_fn fn, int n, const double *p, double t, const dou
 /* ------------------------------------------------------------------------- */
 typedef struct {
     orc_residual_fn fn;
+    orc_jacobian_fn jacfn;   /* NULL: finite differences (jac=None) */
     int n;
     const double *p;
     double rtol;
@@ -295,9 +296,16 @@ static void count_fun(base_state *b, double t, const double *y, const double *yp
 }
 
 /* jac_wrapped, base.py:264-295 (FD residual calls are not counted in nfev) */
+static int g_analytic_jac = 0;
+void orc_set_analytic_jac(int on) { g_analytic_jac = on; }
+
 static void fd_jacobian(base_state *b, double t, const double *y, const double *yp)
 {
     b->cnt[ORC_CNT_NJEV] += 1;
+    if (b->jacfn) {                                         /* callable jac, base.py:299-331 */
+        b->jacfn(t, y, yp, b->p, b->Jy, b->Jyp);
+        return;
+    }
     b->fn(t, y, yp, b->p, b->ftmp);
     orc_num_jac(b->fn, b->n, b->p, t, y, yp, b->ftmp, 0, b->rtol, b->atol, b->factor_y, b->Jy);
     orc_num_jac(b->fn, b->n, b->p, t, y, yp, b->ftmp, 1, b->rtol, b->atol, b->factor_yp, b->Jyp);
@@ -638,6 +646,7 @@ static void base_init(base_state *b, orc_residual_fn fn, int n, const double *p,
 {
     memset(b, 0, sizeof(*b));
     b->fn = fn; b->n = n; b->p = p; b->rtol = rtol; b->atol = atol;
+    b->jacfn = g_analytic_jac ? orc_jacobian_of(fn) : 0;
     b->t = t0; b->t_bound = t_bound; b->max_step = max_step;
     b->dir = (t_bound != t0) ? ((t_bound > t0) ? 1.0 : -1.0) : 1.0;         /* base.py:214 */
     b->y = malloc(sizeof(double) * n); b->yp = malloc(sizeof(double) * n);

@@ -105,6 +105,17 @@ int orc_solve_bdf(orc_residual_fn fn, int n, const double *p,
                   double *y_final, double *yp_final, double *t_final, int64_t *counters,
                   double *t_steps, double *y_steps, int64_t steps_cap, int64_t *n_steps);
 
+/* analytic Jacobian (the reference's `jac=` callable, base.py:299-331): Jy, Jyp row-major n*n */
+typedef void (*orc_jacobian_fn)(double t, const double *y, const double *yp, const double *p,
+                                double *Jy, double *Jyp);
+/* 1: the solvers call the problem's analytic Jacobian instead of num_jac (process-wide switch,
+ * read when an instance starts; problems without one keep the FD Jacobian) */
+void orc_set_analytic_jac(int on);
+orc_jacobian_fn orc_problem_jacobian(int problem_id);
+orc_jacobian_fn orc_jacobian_of(orc_residual_fn fn);
+int orc_problem_jac_eval(int problem_id, double t, const double *y, const double *yp,
+                         const double *p, double *Jy, double *Jyp);
+
 /* problem registry (oracle/problems.c) */
 int orc_problem_lookup(const char *name, int *n, int *n_params);
 orc_residual_fn orc_problem_residual(int problem_id);

@@ -64,6 +64,9 @@ def run_instance(problem, params, y0, yp0, t_span, method, rtol, atol, t_eval, o
                  record_steps=False):
     for k in _cnt:
         _cnt[k] = 0
+    options = dict(options)
+    if options.get("jac") == "analytic":     # the problem's analytic Jacobians as the `jac` callable
+        options["jac"] = problem.jacobian
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         # pass 1: t_eval=None => sol.t are the step ends => accepted count, final state
@@ -209,6 +212,22 @@ def cases():
     yield dict(name="andrews_radau3_ens", problem="andrews",
                params=perturbed_params("andrews", 4, 0.05, 2), method="Radau",
                rtol=1e-6, atol=1e-6, options=dict(stages=3))
+    # --- row N2 of SURVEY §8f: analytic Jacobian callables (base.py:299-331)
+    yield dict(name="robertson_radau3_jac", problem="robertson",
+               params=perturbed_params("robertson", 16, 0.1, 0), method="Radau",
+               rtol=1e-6, atol=1e-6, options=dict(jac="analytic"), t_eval=np.logspace(-5, 7, 13))
+    yield dict(name="robertson_bdf_jac", problem="robertson",
+               params=perturbed_params("robertson", 8, 0.1, 0), method="BDF",
+               rtol=1e-6, atol=1e-6, options=dict(jac="analytic"))
+    yield dict(name="akzo_bdf_jac", problem="akzo_nobel",
+               params=perturbed_params("akzo_nobel", 8, 0.05, 0), method="BDF",
+               rtol=1e-8, atol=1e-8, options=dict(jac="analytic"))
+    yield dict(name="akzo_radau3_jac", problem="akzo_nobel",
+               params=perturbed_params("akzo_nobel", 8, 0.05, 0), method="Radau",
+               rtol=1e-8, atol=1e-8, options=dict(jac="analytic"))
+    yield dict(name="transamp_radau3_jac", problem="transamp",
+               params=perturbed_params("transamp", 4, 0.02, 1), method="Radau",
+               rtol=1e-10, atol=1e-6, options=dict(jac="analytic"))
     # backward integration (direction = -1) of a non-stiff stretch
     yield dict(name="robertson_radau3_backward", problem="robertson",
                params=rob_nom, method="Radau", rtol=1e-6, atol=1e-8, t_span=(1e-3, 0.0),

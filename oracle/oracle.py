@@ -95,6 +95,18 @@ def residual(name, t, y, yp, params):
     return out
 
 
+def jacobian(name, t, y, yp, params):
+    pid, n, _ = problem_id(name)
+    y = np.ascontiguousarray(y, dtype=float)
+    yp = np.ascontiguousarray(yp, dtype=float)
+    p = np.ascontiguousarray(params, dtype=float)
+    Jy, Jyp = np.empty((n, n)), np.empty((n, n))
+    rc = lib().orc_problem_jac_eval(ctypes.c_int(pid), ctypes.c_double(t), _p(y), _p(yp), _p(p), _p(Jy), _p(Jyp))
+    if rc != 0:
+        raise ValueError(f"oracle has no analytic Jacobian for {name!r}")
+    return Jy, Jyp
+
+
 def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, atol=1e-6,
                    t_eval=None, nthreads=1, max_steps=0, **options):
     """N instances through the C oracle.  Arrays are AoS on the host: params[N,p], y0[N,n]."""
@@ -107,6 +119,9 @@ def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, 
     atol_v = np.ascontiguousarray(np.broadcast_to(np.asarray(atol, dtype=float), (n,)))
     t0, t_bound = map(float, t_span)
 
+    jac = options.pop("jac", None)
+    if jac not in (None, "analytic"):
+        raise ValueError("oracle: jac must be None (finite differences) or 'analytic'")
     ropts = bopts = tb = None
     if method == "Radau":
         s = int(options.pop("stages", 3))
@@ -146,6 +161,7 @@ def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, 
     status = np.zeros(N, dtype=np.int32)
     counters = np.zeros((N, 8), dtype=np.int64)
 
+    lib().orc_set_analytic_jac(ctypes.c_int(1 if jac == "analytic" else 0))
     rc = lib().orc_solve_ensemble(
         ctypes.c_int(pid), ctypes.c_int(mcode), ctypes.c_int64(N),
         _p(params), _p(y0), _p(yp0), ctypes.c_double(t0), ctypes.c_double(t_bound), _p(atol_v),
@@ -155,6 +171,7 @@ def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, 
         _p(te), ctypes.c_int64(m), _p(ye), _p(ype), _p(nev, ctypes.c_int64),
         _p(y_final), _p(yp_final), _p(t_final), _p(status, ctypes.c_int32),
         _p(counters, ctypes.c_int64), ctypes.c_int(nthreads))
+    lib().orc_set_analytic_jac(ctypes.c_int(0))
     if rc != 0:
         raise RuntimeError(f"orc_solve_ensemble returned {rc}")
     out = dict(status=status, t_final=t_final, y_final=y_final, yp_final=yp_final,

@@ -170,15 +170,90 @@ static void andrews(double t, const double *y, const double *yp, const double *p
     }
 }
 
+/* ---- analytic Jacobians (the reference's `jac=` callable, base.py:299-331), row-major n*n;
+ * twins of problems.py: robertson_jacobian, akzo_jacobian, transamp_jacobian ---- */
+static void robertson_jac(double t, const double *y, const double *yp, const double *p,
+                          double *Jy, double *Jyp)
+{
+    (void)t; (void)yp;
+    double k1 = p[0], k2 = p[1], k3 = p[2];
+    memset(Jy, 0, sizeof(double) * 9); memset(Jyp, 0, sizeof(double) * 9);
+    Jy[0] = k1;  Jy[1] = -k2 * y[2];                 Jy[2] = -k2 * y[1];
+    Jy[3] = -k1; Jy[4] = k2 * y[2] + 2.0 * k3 * y[1]; Jy[5] = k2 * y[1];
+    Jy[6] = 1.0; Jy[7] = 1.0;                        Jy[8] = 1.0;
+    Jyp[0] = 1.0; Jyp[4] = 1.0;
+}
+
+static void akzo_nobel_jac(double t, const double *y, const double *yp, const double *p,
+                           double *Jy, double *Jyp)
+{
+    (void)t; (void)yp;
+    double k1 = p[0], k2 = p[1], k3 = p[2], k4 = p[3], kbig = p[4], kla = p[5], ks = p[6];
+    double sq = sqrt(y[1]), hsq = 0.5 / sq;
+    double y0c = y[0] * y[0] * y[0];
+    double r1_0 = 4.0 * k1 * y0c * sq, r1_1 = k1 * (y0c * y[0]) * hsq;
+    double r2_2 = k2 * y[3], r2_3 = k2 * y[2];
+    double kk = k2 / kbig;
+    double r3_0 = kk * y[4], r3_4 = kk * y[0];
+    double r4_0 = k3 * (y[3] * y[3]), r4_3 = 2.0 * k3 * y[0] * y[3];
+    double r5_1 = k4 * (y[5] * y[5]) * hsq, r5_5 = 2.0 * k4 * y[5] * sq;
+    double df[36];
+    memset(df, 0, sizeof(df)); memset(Jyp, 0, sizeof(double) * 36);
+#define DF(i, j) df[(i) * 6 + (j)]
+    DF(0, 0) = -2.0 * r1_0 - r3_0 - r4_0; DF(0, 1) = -2.0 * r1_1; DF(0, 2) = r2_2;
+    DF(0, 3) = r2_3 - r4_3; DF(0, 4) = -r3_4;
+    DF(1, 0) = -0.5 * r1_0 - r4_0; DF(1, 1) = -0.5 * r1_1 - 0.5 * r5_1 - kla;
+    DF(1, 3) = -r4_3; DF(1, 5) = -0.5 * r5_5;
+    DF(2, 0) = r1_0 + r3_0; DF(2, 1) = r1_1; DF(2, 2) = -r2_2; DF(2, 3) = -r2_3; DF(2, 4) = r3_4;
+    DF(3, 0) = r3_0 - 2.0 * r4_0; DF(3, 2) = -r2_2; DF(3, 3) = -r2_3 - 2.0 * r4_3; DF(3, 4) = r3_4;
+    DF(4, 0) = -r3_0; DF(4, 1) = r5_1; DF(4, 2) = r2_2; DF(4, 3) = r2_3; DF(4, 4) = -r3_4; DF(4, 5) = r5_5;
+    DF(5, 0) = ks * y[3]; DF(5, 3) = ks * y[0]; DF(5, 5) = -1.0;
+#undef DF
+    for (int k = 0; k < 36; ++k) Jy[k] = -df[k];
+    for (int i = 0; i < 5; ++i) Jyp[i * 6 + i] = 1.0;
+}
+
+static void transamp_jac(double t, const double *y, const double *yp, const double *p,
+                         double *Jy, double *Jyp)
+{
+    (void)t; (void)yp;
+    const double UF = 0.026, a = 0.99, R = 9000.0;
+    const double C1 = 1e-6, C2 = 2e-6, C3 = 3e-6, C4 = 4e-6, C5 = 5e-6;
+    double R0 = p[1], beta = p[2];
+    double e23 = beta * exp((y[1] - y[2]) / UF) / UF;
+    double e56 = beta * exp((y[4] - y[5]) / UF) / UF;
+    double df[64];
+    memset(df, 0, sizeof(df)); memset(Jyp, 0, sizeof(double) * 64);
+#define DF(i, j) df[(i) * 8 + (j)]
+#define M(i, j) Jyp[(i) * 8 + (j)]
+    DF(0, 0) = 1.0 / R0;
+    DF(1, 1) = 2.0 / R - (a - 1.0) * e23; DF(1, 2) = (a - 1.0) * e23;
+    DF(2, 1) = -e23; DF(2, 2) = e23 + 1.0 / R;
+    DF(3, 1) = a * e23; DF(3, 2) = -a * e23; DF(3, 3) = 1.0 / R;
+    DF(4, 4) = 2.0 / R - (a - 1.0) * e56; DF(4, 5) = (a - 1.0) * e56;
+    DF(5, 4) = -e56; DF(5, 5) = e56 + 1.0 / R;
+    DF(6, 4) = a * e56; DF(6, 5) = -a * e56; DF(6, 6) = 1.0 / R;
+    DF(7, 7) = 1.0 / R;
+    M(0, 0) = -C1; M(0, 1) = C1; M(1, 0) = C1; M(1, 1) = -C1;
+    M(2, 2) = -C2;
+    M(3, 3) = -C3; M(3, 4) = C3; M(4, 3) = C3; M(4, 4) = -C3;
+    M(5, 5) = -C4;
+    M(6, 6) = -C5; M(6, 7) = C5; M(7, 6) = C5; M(7, 7) = -C5;
+#undef DF
+#undef M
+    for (int k = 0; k < 64; ++k) Jy[k] = -df[k];
+}
+
 static const struct {
     const char *name;
     int n, n_params;
     orc_residual_fn fn;
+    orc_jacobian_fn jac;
 } REGISTRY[] = {
-    {"robertson", 3, 3, robertson},
-    {"akzo_nobel", 6, 7, akzo_nobel},
-    {"transamp", 8, 3, transamp},
-    {"andrews", 26, 2, andrews},
+    {"robertson", 3, 3, robertson, robertson_jac},
+    {"akzo_nobel", 6, 7, akzo_nobel, akzo_nobel_jac},
+    {"transamp", 8, 3, transamp, transamp_jac},
+    {"andrews", 26, 2, andrews, 0},
 };
 #define N_PROBLEMS ((int)(sizeof(REGISTRY) / sizeof(REGISTRY[0])))
 
@@ -205,6 +280,28 @@ orc_residual_fn orc_problem_residual(int problem_id)
 {
     if (problem_id < 0 || problem_id >= N_PROBLEMS) return 0;
     return REGISTRY[problem_id].fn;
+}
+
+orc_jacobian_fn orc_problem_jacobian(int problem_id)
+{
+    if (problem_id < 0 || problem_id >= N_PROBLEMS) return 0;
+    return REGISTRY[problem_id].jac;
+}
+
+orc_jacobian_fn orc_jacobian_of(orc_residual_fn fn)
+{
+    for (int i = 0; i < N_PROBLEMS; ++i)
+        if (REGISTRY[i].fn == fn) return REGISTRY[i].jac;
+    return 0;
+}
+
+int orc_problem_jac_eval(int problem_id, double t, const double *y, const double *yp,
+                         const double *p, double *Jy, double *Jyp)
+{
+    orc_jacobian_fn jf = orc_problem_jacobian(problem_id);
+    if (!jf) return -1;
+    jf(t, y, yp, p, Jy, Jyp);
+    return 0;
 }
 
 /* residual evaluation exported for tests (checks the C twin against problems.py) */

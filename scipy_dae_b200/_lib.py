@@ -38,13 +38,15 @@ class RadauOpts(ctypes.Structure):
                 ("jac_recompute_rate", ctypes.c_double),
                 ("deadband_lo", ctypes.c_double), ("deadband_hi", ctypes.c_double),
                 ("newton_max_iter", ctypes.c_int32), ("newton_iter_embedded", ctypes.c_int32),
-                ("max_steps", ctypes.c_int64)]
+                ("max_steps", ctypes.c_int64), ("analytic_jac", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
 
 
 class BdfOpts(ctypes.Structure):
     _fields_ = [("rtol", ctypes.c_double), ("max_step", ctypes.c_double),
                 ("first_step", ctypes.c_double), ("max_order", ctypes.c_int32),
-                ("ndf_strategy", ctypes.c_int32), ("max_steps", ctypes.c_int64)]
+                ("ndf_strategy", ctypes.c_int32), ("max_steps", ctypes.c_int64),
+                ("analytic_jac", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class Outputs(ctypes.Structure):
@@ -99,8 +101,8 @@ def load():
     L.b200dae_fp64_peak_kernel.argtypes = [ctypes.c_int, ctypes.c_int, i64, vp, vp]
     L.b200dae_selftest_fastmath.restype = ctypes.c_int
     L.b200dae_selftest_fastmath.argtypes = [i64, vp, vp, vp, vp]
-    if L.b200dae_version() != 100:
-        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 100")
+    if L.b200dae_version() != 101:
+        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 101")
     _lib = L
     return L
 
@@ -108,7 +110,7 @@ def load():
 def check(rc: int):
     if rc != 0:
         msg = load().b200dae_last_error().decode(errors="replace")
-        if rc == -1:
+        if rc in (-1, -2):
             raise ValueError(msg)
         raise B200DaeError(f"libb200dae error {rc}: {msg}")
 

@@ -37,9 +37,11 @@ MESSAGES = {0: "The solver successfully reached the end of the integration inter
 _RADAU_KEYS = ("stages", "max_step", "continuous_error_weight", "first_step", "newton_max_iter",
                "jac_recompute_rate", "newton_iter_embedded", "controller_deadband")
 _BDF_KEYS = ("max_step", "first_step", "max_order", "NDF_strategy")
-# accepted for signature compatibility; the device path always uses the FD Jacobian of the
-# registered functor (jac=None in the reference) and dense per-instance LUs
-_IGNORED_NONE_KEYS = ("jac", "jac_sparsity", "vectorized")
+# accepted for signature compatibility: dense per-instance LUs only, no Python callables.
+# `jac` is None (finite differences, the reference's jac=None) or "analytic" / True: the analytic
+# Jacobians registered with the device functor, i.e. what the reference does with a `jac`
+# callable (base.py:299-331).
+_IGNORED_NONE_KEYS = ("jac_sparsity", "vectorized")
 
 
 @dataclass
@@ -243,12 +245,20 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
 
         # ---- options -----------------------------------------------------------------------
         opts = dict(options)
+        jac = opts.pop("jac", None)
+        if jac is True or jac == "analytic":
+            analytic_jac = 1
+        elif jac is None or jac is False:
+            analytic_jac = 0
+        else:
+            raise NotImplementedError(
+                "`jac` must be None (finite differences) or 'analytic' (the Jacobians registered with "
+                "the device functor): a Python callable cannot run inside the device step loop.")
         for k in _IGNORED_NONE_KEYS:
             v = opts.pop(k, None)
             if v not in (None, False):
                 raise NotImplementedError(
-                    f"`{k}` is not supported on the device path: the Jacobian of a registered "
-                    "functor is formed by finite differences (jac=None in the reference).")
+                    f"`{k}` is not supported on the device path (dense per-instance Jacobians).")
         max_step = float(opts.pop("max_step", np.inf))
         if max_step <= 0:
             raise ValueError("`max_step` must be positive.")
@@ -276,7 +286,7 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
                 deadband_lo=float(db[0]), deadband_hi=float(db[1]),
                 newton_max_iter=int(nmi) if nmi is not None else 0,
                 newton_iter_embedded=int(opts.pop("newton_iter_embedded", 1)),
-                max_steps=int(max_steps))
+                max_steps=int(max_steps), analytic_jac=analytic_jac)
             _warn_extraneous(opts)
             tb = radau_tables_c(stages)
             rc = L.b200dae_solve_radau(pid, N, ld, y0_d.data_ptr(), yp0_d.data_ptr(), p_ptr,
@@ -286,7 +296,8 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
             ndf = opts.pop("NDF_strategy", "stability")
             bo = _lib.BdfOpts(rtol=rtol, max_step=max_step, first_step=first_step or 0.0,
                               max_order=int(opts.pop("max_order", 5)),
-                              ndf_strategy=NDF_STRATEGIES.get(ndf, 2), max_steps=int(max_steps))
+                              ndf_strategy=NDF_STRATEGIES.get(ndf, 2), max_steps=int(max_steps),
+                              analytic_jac=analytic_jac)
             if bo.max_order == 6:
                 warnings.warn("Choosing `max_order = 6` is not recomended due to its poor "
                               "stability properties.", stacklevel=2)

@@ -181,6 +181,7 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
                                                   : 7 + (int)((s - 3) * 2.5);  // radau.py:440-441
     L.newton_iter_embedded = opts->newton_iter_embedded;
     L.max_steps = opts->max_steps;
+    L.analytic_jac = opts->analytic_jac;
     L.N = N;
     L.ld = ld;
     L.y0 = y0;
@@ -188,6 +189,8 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
     L.params = params;
     L.out = normalise(out);
     rc = e->radau[s](L, (cudaStream_t)stream);
+    if (rc == kErrNoJac)
+        return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s' (stages=%lld)", e->name, s);
     if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
     return 0;
 }
@@ -230,6 +233,7 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
     fill_U(L.U);
     L.max_order = opts->max_order;
     L.max_steps = opts->max_steps;
+    L.analytic_jac = opts->analytic_jac;
     L.N = N;
     L.ld = ld;
     L.y0 = y0;
@@ -237,6 +241,8 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
     L.params = params;
     L.out = normalise(out);
     rc = e->bdf(L, (cudaStream_t)stream);
+    if (rc == kErrNoJac)
+        return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s'%s", e->name);
     if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
     return 0;
 }

@@ -29,6 +29,7 @@ struct BdfLaunch {
     double U[kBdfQ * kBdfQ];   // compute_R(6, 1): its leading blocks are compute_R(order, 1)
     int32_t max_order;
     int64_t max_steps;
+    int32_t analytic_jac;       // host-side dispatch only (kJac template parameter)
     int64_t N, ld;
     const double *y0, *yp0, *params;
     b200dae_outputs out;
@@ -59,7 +60,7 @@ __device__ __noinline__ void change_D(double* __restrict__ D, int order, double 
         }
 }
 
-template <class P, int kThreads>
+template <class P, int kThreads, bool kJac = false>
 __global__ void __launch_bounds__(kThreads)
 bdf_kernel(const __grid_constant__ BdfLaunch L) {
     constexpr int N = P::N, NP = P::NP;
@@ -124,7 +125,8 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
     while (status == B200DAE_ST_RUNNING) {
         // ---- phase J: FD Jacobian at the committed (t, y, yp) (base.py:297, bdf.py:330) ------
         if (need_jac) {
-            fd_jacobian<P, double*>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
+            if constexpr (kJac) analytic_jacobian<P, N>(t, y, yp, p, (double*)Jy, (double*)Jyp);
+            else fd_jacobian<P, double*>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
             ++njev;
             need_jac = false;
         }

@@ -66,7 +66,7 @@ __device__ __forceinline__ void change_D_call(double (&D)[kBdfRows], int order, 
     for (int i = 0; i < kBdfRows; ++i) D[i] = tmp[i];
 }
 
-template <class P, int G, int kThreads, int kMinBlocks>
+template <class P, int G, int kThreads, int kMinBlocks, bool kJac = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     constexpr int N = P::N, NP = P::NP;
@@ -148,7 +148,8 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     while (status == B200DAE_ST_RUNNING) {
         // ---- phase J (base.py:297, bdf.py:330) ------------------------------------------------
         if (need_jac) {
-            fd_jacobian_group<P, G, LD>(g, t, y, yp, p, thr_j, fac_y, fac_yp, sJy, sJyp, sY, sYp, sF, sWork);
+            if constexpr (kJac) analytic_jacobian_group<P, LD>(g, t, y, yp, p, sJy, sJyp, sY, sYp);
+            else fd_jacobian_group<P, G, LD>(g, t, y, yp, p, thr_j, fac_y, fac_yp, sJy, sJyp, sY, sYp, sF, sWork);
             ++njev;
             need_jac = false;
         }

@@ -61,6 +61,28 @@ __device__ __forceinline__ void fd_column(double t, double* __restrict__ y, doub
     if (f_at != f_at || fn_at != fn_at) scale = nan("");
 }
 
+// Analytic Jacobians from the functor (the reference's `jac=` callable path, base.py:299-331):
+// zero both matrices, let the functor fill its structural non-zeros.  `V` is any indexable view
+// with row-major N x N entries at stride `LD`.
+template <class V, int LD>
+struct MatRef {
+    V v;
+    __device__ __forceinline__ double& operator()(int r, int c) const { return v[r * LD + c]; }
+};
+
+template <class P, int LD, class V>
+__device__ __forceinline__ void analytic_jacobian(double t, const double* __restrict__ y,
+                                                  const double* __restrict__ yp,
+                                                  const double* __restrict__ p, V Jy, V Jyp) {
+    constexpr int N = P::N;
+    constexpr int U = Regime<N>::kUnroll;
+#pragma unroll U
+    for (int r = 0; r < N; ++r)
+#pragma unroll U
+        for (int c = 0; c < N; ++c) { Jy[r * LD + c] = 0.0; Jyp[r * LD + c] = 0.0; }
+    P::jac(t, y, yp, p, MatRef<V, LD>{Jy}, MatRef<V, LD>{Jyp});
+}
+
 // Jy and Jyp (row-major N*N) at (t, y, yp).  thr[i] = atol[i] / rtol.
 template <class P, class V>
 __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, double* __restrict__ yp,

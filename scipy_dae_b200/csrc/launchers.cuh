@@ -71,7 +71,9 @@ static bool force_thread_regime() {
     return v;
 }
 
-template <class P, int S>
+constexpr int kErrNoJac = -77;    // analytic Jacobian requested but not compiled for (problem, stages)
+
+template <class P, int S, bool J = false>
 static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
     constexpr int G = GroupSize<P::N>::value;
     constexpr int T = (G == 32) ? 32 : 64;
@@ -80,7 +82,7 @@ static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
     static_assert(smem <= 227 * 1024, "per-block shared memory");
     // sub-warp groups: cap the registers at 168 so that six 64-thread blocks (12 warps) share an SM
     constexpr int MB = B200DAE_GROUP_MINBLOCKS(G);
-    auto kern = radau_group_kernel<P, S, G, T, MB>;
+    auto kern = radau_group_kernel<P, S, G, T, MB, J>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -95,21 +97,40 @@ static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
 
 template <class P, int S>
 static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
+    // analytic-Jacobian kernels are compiled for s = 3 of the problems that provide jac()
+    constexpr bool kJacOk = P::kHasJac && S == 3;
+    if (L.analytic_jac && !kJacOk) return kErrNoJac;
     if constexpr (!Regime<P::N>::kReg) {
-        if (!force_thread_regime()) return launch_radau_group<P, S>(L, st);
+        if (!force_thread_regime()) {
+            if constexpr (kJacOk) {
+                if (L.analytic_jac) return launch_radau_group<P, S, true>(L, st);
+            }
+            return launch_radau_group<P, S, false>(L, st);
+        }
+        if (L.analytic_jac) return kErrNoJac;
     }
     using Tn = RadauTune<P, S>;
     constexpr int T = Tn::kThreads;
     const int64_t blocks = (L.N + T - 1) / T;
     const bool lean = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_eval == nullptr &&
                       L.out.t_steps == nullptr;
-    if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true><<<(unsigned)blocks, T, 0, st>>>(L);
-    else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false><<<(unsigned)blocks, T, 0, st>>>(L);
+    bool done = false;
+    if constexpr (kJacOk && Regime<P::N>::kReg) {
+        if (L.analytic_jac) {
+            if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, true><<<(unsigned)blocks, T, 0, st>>>(L);
+            else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false, true><<<(unsigned)blocks, T, 0, st>>>(L);
+            done = true;
+        }
+    }
+    if (!done) {
+        if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true><<<(unsigned)blocks, T, 0, st>>>(L);
+        else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false><<<(unsigned)blocks, T, 0, st>>>(L);
+    }
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
 }
 
-template <class P>
+template <class P, bool J = false>
 static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
     constexpr int G = GroupSize<P::N>::value;
     constexpr int T = (G == 32) ? 32 : 64;
@@ -117,7 +138,7 @@ static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
     constexpr size_t smem = (size_t)(T / G) * Lay::doubles(P::NP) * sizeof(double);
     static_assert(smem <= 227 * 1024, "per-block shared memory");
     constexpr int MB = B200DAE_GROUP_MINBLOCKS(G);
-    auto kern = bdf_group_kernel<P, G, T, MB>;
+    auto kern = bdf_group_kernel<P, G, T, MB, J>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -132,12 +153,23 @@ static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
 
 template <class P>
 static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
+    if (L.analytic_jac && !P::kHasJac) return kErrNoJac;
     if constexpr (!Regime<P::N>::kReg) {
-        if (!force_thread_regime()) return launch_bdf_group<P>(L, st);
+        if (!force_thread_regime()) {
+            if constexpr (P::kHasJac) {
+                if (L.analytic_jac) return launch_bdf_group<P, true>(L, st);
+            }
+            return launch_bdf_group<P, false>(L, st);
+        }
+        if (L.analytic_jac) return kErrNoJac;
     }
     constexpr int T = BlockSize<P>::value;
     const int64_t blocks = (L.N + T - 1) / T;
-    bdf_kernel<P, T><<<(unsigned)blocks, T, 0, st>>>(L);
+    bool done = false;
+    if constexpr (P::kHasJac && Regime<P::N>::kReg) {
+        if (L.analytic_jac) { bdf_kernel<P, T, true><<<(unsigned)blocks, T, 0, st>>>(L); done = true; }
+    }
+    if (!done) bdf_kernel<P, T><<<(unsigned)blocks, T, 0, st>>>(L);
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
 }

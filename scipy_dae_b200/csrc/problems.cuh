@@ -8,6 +8,9 @@
 //
 // A functor provides  N (state size), NP (parameters per instance), name, and
 //   static __device__ void eval(double t, const double* y, const double* yp, const double* p, double* out)
+// and optionally (kHasJac) the analytic Jacobians of the reference's `jac=` callable (base.py:299-331)
+//   template <class M> static __device__ void jac(t, y, yp, p, M Jy, M Jyp)
+// where M(r, c) is a reference to entry (r, c) of a matrix the caller has zeroed.
 // All indexing is static so that, after inlining into a fully unrolled caller, every array
 // lives in registers.
 #pragma once
@@ -27,6 +30,16 @@ struct Robertson {
         out[0] = yp[0] - (-k1 * y[0] + r23);
         out[1] = yp[1] - (k1 * y[0] - r23 - k3 * y[1] * y[1]);
         out[2] = y[0] + y[1] + y[2] - 1.0;
+    }
+    static constexpr bool kHasJac = true;      // reference: examples/daes/robertson.py:38-47
+    template <class M>
+    __device__ __forceinline__ static void jac(double, const double* y, const double*, const double* p,
+                                               M Jy, M Jyp) {
+        const double k1 = p[0], k2 = p[1], k3 = p[2];
+        Jy(0, 0) = k1;  Jy(0, 1) = -k2 * y[2];                     Jy(0, 2) = -k2 * y[1];
+        Jy(1, 0) = -k1; Jy(1, 1) = fma(2.0 * k3, y[1], k2 * y[2]); Jy(1, 2) = k2 * y[1];
+        Jy(2, 0) = 1.0; Jy(2, 1) = 1.0;                            Jy(2, 2) = 1.0;
+        Jyp(0, 0) = 1.0; Jyp(1, 1) = 1.0;
     }
 };
 
@@ -52,6 +65,29 @@ struct AkzoNobel {
         out[3] = yp[3] - (-r2 + r3 - 2.0 * r4);
         out[4] = yp[4] - (r2 - r3 + r5);
         out[5] = -(ks * y[0] * y[3] - y[5]);
+    }
+    static constexpr bool kHasJac = true;      // reference: examples/daes/akzo_nobel.py:52-103
+    template <class M>
+    __device__ __forceinline__ static void jac(double, const double* y, const double*, const double* p,
+                                               M Jy, M Jyp) {
+        const double k1 = p[0], k2 = p[1], k3 = p[2], k4 = p[3], kbig = p[4], kla = p[5], ks = p[6];
+        const double sq = sqrt(y[1]), hsq = 0.5 / sq;
+        const double y0c = y[0] * y[0] * y[0];
+        const double r1_0 = 4.0 * k1 * y0c * sq, r1_1 = k1 * (y0c * y[0]) * hsq;
+        const double r2_2 = k2 * y[3], r2_3 = k2 * y[2];
+        const double kk = k2 / kbig;
+        const double r3_0 = kk * y[4], r3_4 = kk * y[0];
+        const double r4_0 = k3 * (y[3] * y[3]), r4_3 = 2.0 * k3 * y[0] * y[3];
+        const double r5_1 = k4 * (y[5] * y[5]) * hsq, r5_5 = 2.0 * k4 * y[5] * sq;
+        Jy(0, 0) = -(-2.0 * r1_0 - r3_0 - r4_0); Jy(0, 1) = 2.0 * r1_1; Jy(0, 2) = -r2_2;
+        Jy(0, 3) = -(r2_3 - r4_3); Jy(0, 4) = r3_4;
+        Jy(1, 0) = -(-0.5 * r1_0 - r4_0); Jy(1, 1) = -(-0.5 * r1_1 - 0.5 * r5_1 - kla);
+        Jy(1, 3) = r4_3; Jy(1, 5) = 0.5 * r5_5;
+        Jy(2, 0) = -(r1_0 + r3_0); Jy(2, 1) = -r1_1; Jy(2, 2) = r2_2; Jy(2, 3) = r2_3; Jy(2, 4) = -r3_4;
+        Jy(3, 0) = -(r3_0 - 2.0 * r4_0); Jy(3, 2) = r2_2; Jy(3, 3) = -(-r2_3 - 2.0 * r4_3); Jy(3, 4) = -r3_4;
+        Jy(4, 0) = r3_0; Jy(4, 1) = -r5_1; Jy(4, 2) = -r2_2; Jy(4, 3) = -r2_3; Jy(4, 4) = r3_4; Jy(4, 5) = -r5_5;
+        Jy(5, 0) = -ks * y[3]; Jy(5, 3) = -ks * y[0]; Jy(5, 5) = 1.0;
+        Jyp(0, 0) = 1.0; Jyp(1, 1) = 1.0; Jyp(2, 2) = 1.0; Jyp(3, 3) = 1.0; Jyp(4, 4) = 1.0;
     }
 };
 
@@ -88,6 +124,30 @@ struct Transamp {
         out[6] = (-C5 * yp[6] + C5 * yp[7]) - f6;
         out[7] = (C5 * yp[6] - C5 * yp[7]) - f7;
     }
+    static constexpr bool kHasJac = true;      // F = M yp - f(t, y):  Jyp = M,  Jy = -df/dy
+    template <class M>
+    __device__ __forceinline__ static void jac(double, const double* y, const double*, const double* p,
+                                               M Jy, M Jyp) {
+        const double UF = 0.026, a = 0.99, R = 9000.0;
+        const double C1 = 1e-6, C2 = 2e-6, C3 = 3e-6, C4 = 4e-6, C5 = 5e-6;
+        const double R0 = p[1], beta = p[2];
+        const double rUF = 1.0 / UF, rR = 1.0 / R;
+        const double e23 = beta * exp((y[1] - y[2]) * rUF) * rUF;
+        const double e56 = beta * exp((y[4] - y[5]) * rUF) * rUF;
+        Jy(0, 0) = -1.0 / R0;
+        Jy(1, 1) = -(2.0 * rR - (a - 1.0) * e23); Jy(1, 2) = -(a - 1.0) * e23;
+        Jy(2, 1) = e23; Jy(2, 2) = -(e23 + rR);
+        Jy(3, 1) = -a * e23; Jy(3, 2) = a * e23; Jy(3, 3) = -rR;
+        Jy(4, 4) = -(2.0 * rR - (a - 1.0) * e56); Jy(4, 5) = -(a - 1.0) * e56;
+        Jy(5, 4) = e56; Jy(5, 5) = -(e56 + rR);
+        Jy(6, 4) = -a * e56; Jy(6, 5) = a * e56; Jy(6, 6) = -rR;
+        Jy(7, 7) = -rR;
+        Jyp(0, 0) = -C1; Jyp(0, 1) = C1; Jyp(1, 0) = C1; Jyp(1, 1) = -C1;
+        Jyp(2, 2) = -C2;
+        Jyp(3, 3) = -C3; Jyp(3, 4) = C3; Jyp(4, 3) = C3; Jyp(4, 4) = -C3;
+        Jyp(5, 5) = -C4;
+        Jyp(6, 6) = -C5; Jyp(6, 7) = C5; Jyp(7, 6) = C5; Jyp(7, 7) = -C5;
+    }
 };
 
 // Andrews' squeezer, stabilised index-1 form, n = 26: y = (q[7], u[7], la[6], mu[6]),
@@ -96,6 +156,7 @@ struct Andrews {
     static constexpr int N = 26, NP = 2;
     static constexpr const char* name() { return "andrews"; }
     static constexpr int kFlops = 520;
+    static constexpr bool kHasJac = false;     // FD Jacobian only (as examples/daes/andrews.py)
     __device__ __noinline__ static void eval(double, const double* y, const double* yp,
                                              const double* p, double* out) {
         const double m1 = 0.04325, m2 = 0.00365, m3 = 0.02373, m4 = 0.00706, m5 = 0.07050,

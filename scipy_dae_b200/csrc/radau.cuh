@@ -34,6 +34,7 @@ struct RadauLaunch {
     double thr[B200DAE_MAX_N];  // atol / rtol (num_jac threshold, base.py:277)
     int32_t newton_max_iter, newton_iter_embedded;
     int64_t max_steps;
+    int32_t analytic_jac;       // host-side dispatch only (kJac template parameter)
     int64_t N, ld;
     const double *y0, *yp0, *params;
     b200dae_outputs out;
@@ -66,7 +67,7 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
 // continuous_error_weight = 0) and asks for neither t_eval output nor a step trace.  Those options
 // are then compiled out, which shrinks the hot kernel (instruction-cache misses were 11 % of the
 // warp stalls of the all-options kernel).
-template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold, bool kLean>
+template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold, bool kLean, bool kJac = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 radau_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
@@ -150,7 +151,8 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     while (status == B200DAE_ST_RUNNING) {
         // ---- phase J: finite-difference Jacobian at the current (t, y, yp) ----------------
         if (need_jac) {
-            fd_jacobian<P, V>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
+            if constexpr (kJac) analytic_jacobian<P, N>(t, y, yp, p, Jy, Jyp);   // jac=callable, base.py:299-331
+            else fd_jacobian<P, V>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
             ++njev;
             need_jac = false;
         }

@@ -142,7 +142,26 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
     g.sync();
 }
 
-template <class P, int S, int G, int kThreads, int kMinBlocks>
+// Analytic Jacobians (jac=callable, base.py:299-331): the state is staged in shared memory, the
+// lanes zero the matrices together, lane 0 lets the functor fill the structural non-zeros.
+template <class P, int LD, class Grp>
+__device__ __forceinline__ void analytic_jacobian_group(const Grp& g, double t, double yj, double ypj,
+                                                        const double* __restrict__ p,
+                                                        double* __restrict__ sJy, double* __restrict__ sJyp,
+                                                        double* __restrict__ sy, double* __restrict__ syp) {
+    constexpr int N = P::N;
+    const int c = g.lane;
+    if (c < N) {
+        sy[c] = yj;
+        syp[c] = ypj;
+        for (int r = 0; r < N; ++r) { sJy[r * LD + c] = 0.0; sJyp[r * LD + c] = 0.0; }
+    }
+    g.sync();
+    if (c == 0) P::jac(t, sy, syp, p, MatRef<double*, LD>{sJy}, MatRef<double*, LD>{sJyp});
+    g.sync();
+}
+
+template <class P, int S, int G, int kThreads, int kMinBlocks, bool kJac = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
@@ -235,7 +254,8 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     while (status == B200DAE_ST_RUNNING) {
         // ---- phase J ----------------------------------------------------------------------
         if (need_jac) {
-            fd_jacobian_group<P, G, LD>(g, t, y, yp, p, thr_j, fac_y, fac_yp, sJy, sJyp, sY, sYp, sF, sWork);
+            if constexpr (kJac) analytic_jacobian_group<P, LD>(g, t, y, yp, p, sJy, sJyp, sY, sYp);
+            else fd_jacobian_group<P, G, LD>(g, t, y, yp, p, thr_j, fac_y, fac_yp, sJy, sJyp, sY, sYp, sF, sWork);
             ++njev;
             need_jac = false;
         }

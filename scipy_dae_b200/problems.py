@@ -43,6 +43,7 @@ class Problem:
     doc: str = ""
     param_names: tuple = field(default_factory=tuple)
     initial_batch: Callable = None   # optional vectorised initial(params[N, p]) -> (y0[N, n], yp0[N, n])
+    jacobian: Callable = None        # optional analytic jac(t, y, yp, *params) -> (Jy[n, n], Jyp[n, n])
 
     def __call__(self, t, y, yp, *params):
         if not params:
@@ -61,6 +62,15 @@ def robertson_residual(t, y, yp, k1, k2, k3):
         y2p - (k1 * y1 - k2 * y2 * y3 - k3 * y2 * y2),
         y1 + y2 + y3 - 1,
     ])
+
+
+def robertson_jacobian(t, y, yp, k1, k2, k3):
+    """(dF/dy, dF/dy') of robertson_residual (reference: examples/daes/robertson.py:38-47)."""
+    Jy = np.array([[k1, -k2 * y[2], -k2 * y[1]],
+                   [-k1, k2 * y[2] + 2.0 * k3 * y[1], k2 * y[1]],
+                   [1.0, 1.0, 1.0]])
+    Jyp = np.diag([1.0, 1.0, 0.0])
+    return Jy, Jyp
 
 
 def robertson_initial(params):
@@ -112,6 +122,32 @@ def akzo_residual(t, y, yp, k1, k2, k3, k4, kbig, kla, ks):
     return out
 
 
+def akzo_jacobian(t, y, yp, k1, k2, k3, k4, kbig, kla, ks):
+    """(dF/dy, dF/dy') of akzo_residual (reference: examples/daes/akzo_nobel.py:52-103)."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sq = np.sqrt(y[1])
+        hsq = 0.5 / sq
+    y0c = y[0] * y[0] * y[0]
+    r1_0, r1_1 = 4.0 * k1 * y0c * sq, k1 * (y0c * y[0]) * hsq
+    r2_2, r2_3 = k2 * y[3], k2 * y[2]
+    kk = k2 / kbig
+    r3_0, r3_4 = kk * y[4], kk * y[0]
+    r4_0, r4_3 = k3 * (y[3] * y[3]), 2.0 * k3 * y[0] * y[3]
+    r5_1, r5_5 = k4 * (y[5] * y[5]) * hsq, 2.0 * k4 * y[5] * sq
+    df = np.zeros((6, 6))
+    df[0, 0] = -2.0 * r1_0 - r3_0 - r4_0; df[0, 1] = -2.0 * r1_1; df[0, 2] = r2_2
+    df[0, 3] = r2_3 - r4_3; df[0, 4] = -r3_4
+    df[1, 0] = -0.5 * r1_0 - r4_0; df[1, 1] = -0.5 * r1_1 - 0.5 * r5_1 - kla
+    df[1, 3] = -r4_3; df[1, 5] = -0.5 * r5_5
+    df[2, 0] = r1_0 + r3_0; df[2, 1] = r1_1; df[2, 2] = -r2_2; df[2, 3] = -r2_3; df[2, 4] = r3_4
+    df[3, 0] = r3_0 - 2.0 * r4_0; df[3, 2] = -r2_2; df[3, 3] = -r2_3 - 2.0 * r4_3; df[3, 4] = r3_4
+    df[4, 0] = -r3_0; df[4, 1] = r5_1; df[4, 2] = r2_2; df[4, 3] = r2_3; df[4, 4] = -r3_4; df[4, 5] = r5_5
+    df[5, 0] = ks * y[3]; df[5, 3] = ks * y[0]; df[5, 5] = -1.0
+    Jy = -df
+    Jyp = np.diag([1.0, 1.0, 1.0, 1.0, 1.0, 0.0])
+    return Jy, Jyp
+
+
 def akzo_initial(params):
     ks = params[6]
     y0 = np.array([0.444, 0.00123, 0.0, 0.007, 0.0, ks * 0.444 * 0.007])
@@ -155,6 +191,30 @@ def transamp_residual(t, y, yp, Ub, R0, beta):
         C5 * yp[6] - C5 * yp[7],
     ])
     return My - f
+
+
+def transamp_jacobian(t, y, yp, Ub, R0, beta):
+    """(dF/dy, dF/dy') of transamp_residual: F = M yp - f(t, y), so Jyp = M and Jy = -df/dy."""
+    C1, C2, C3, C4, C5 = 1e-6, 2e-6, 3e-6, 4e-6, 5e-6
+    R, a = TA_R, TA_ALPHA
+    e23 = beta * np.exp((y[1] - y[2]) / TA_UF) / TA_UF
+    e56 = beta * np.exp((y[4] - y[5]) / TA_UF) / TA_UF
+    df = np.zeros((8, 8))
+    df[0, 0] = 1.0 / R0
+    df[1, 1] = 2.0 / R - (a - 1.0) * e23; df[1, 2] = (a - 1.0) * e23
+    df[2, 1] = -e23; df[2, 2] = e23 + 1.0 / R
+    df[3, 1] = a * e23; df[3, 2] = -a * e23; df[3, 3] = 1.0 / R
+    df[4, 4] = 2.0 / R - (a - 1.0) * e56; df[4, 5] = (a - 1.0) * e56
+    df[5, 4] = -e56; df[5, 5] = e56 + 1.0 / R
+    df[6, 4] = a * e56; df[6, 5] = -a * e56; df[6, 6] = 1.0 / R
+    df[7, 7] = 1.0 / R
+    M = np.zeros((8, 8))
+    M[0, 0] = -C1; M[0, 1] = C1; M[1, 0] = C1; M[1, 1] = -C1
+    M[2, 2] = -C2
+    M[3, 3] = -C3; M[3, 4] = C3; M[4, 3] = C3; M[4, 4] = -C3
+    M[5, 5] = -C4
+    M[6, 6] = -C5; M[6, 7] = C5; M[7, 6] = C5; M[7, 7] = -C5
+    return -df, M
 
 
 def transamp_initial(params):
@@ -286,20 +346,21 @@ def _register(p: Problem):
 ROBERTSON = _register(Problem(
     name="robertson", n=3, n_params=3, residual=robertson_residual,
     default_params=(0.04, 1e4, 3e7), initial=robertson_initial, t_span=(0.0, 1e7),
-    initial_batch=robertson_initial_batch,
+    initial_batch=robertson_initial_batch, jacobian=robertson_jacobian,
     param_names=("k1", "k2", "k3"),
     doc="Robertson chemical kinetics as an index-1 DAE"))
 
 AKZO_NOBEL = _register(Problem(
     name="akzo_nobel", n=6, n_params=7, residual=akzo_residual,
     default_params=(18.7, 0.58, 0.09, 0.42, 34.4, 3.3, 115.83),
-    initial=akzo_initial, t_span=(0.0, 180.0),
+    initial=akzo_initial, t_span=(0.0, 180.0), jacobian=akzo_jacobian,
     param_names=("k1", "k2", "k3", "k4", "kbig", "kla", "ks"),
     doc="Akzo Nobel chemical reaction, index 1"))
 
 TRANSAMP = _register(Problem(
     name="transamp", n=8, n_params=3, residual=transamp_residual,
     default_params=(6.0, 1000.0, 1e-6), initial=transamp_initial, t_span=(0.0, 0.2),
+    jacobian=transamp_jacobian,
     param_names=("Ub", "R0", "beta"),
     doc="Two-transistor amplifier (IVP test set 'transamp'), index 1"))
 
