@@ -84,6 +84,17 @@ __device__ __forceinline__ void analytic_jacobian(double t, const double* __rest
 }
 
 // Jy and Jyp (row-major N*N) at (t, y, yp).  thr[i] = atol[i] / rtol.
+//
+// Tried and rejected (round 1, B200): a branch-free form for n <= 4 that evaluates both attempts
+// of every column and picks by selects (one basic block of 4n residual evaluations).  It is
+// algorithmically identical (checked against this form on 20 000 random states), but it spilled
+// at the 168-register cap and ran 16.6 ms instead of 15.3 ms per 2^20 Robertson solves, and the
+// different FMA contraction of the inlined residuals moved the step sequences (config 1: nfev
+// 914 instead of the reference's 911; +6 % accepted steps on the vector-atol golden).  The FD
+// phase is latency-bound (29 % of the solve time for 15 % of the instructions: with the analytic
+// Jacobian the same launch takes 10.9 ms); the second attempt is not rare either: a column of
+// Jyp that belongs to an algebraic variable has diff = 0 and always takes it (16.4 % of the
+// Robertson columns, counted with the CPU oracle).
 template <class P, class V>
 __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, double* __restrict__ yp,
                                             const double* __restrict__ p, const double* __restrict__ thr,

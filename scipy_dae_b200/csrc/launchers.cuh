@@ -15,6 +15,9 @@
 #include "radau.cuh"
 #include "radau_group.cuh"
 
+#ifndef B200DAE_REG_MINBLOCKS
+#define B200DAE_REG_MINBLOCKS 6
+#endif
 #ifndef B200DAE_GROUP_MINBLOCKS
 #define B200DAE_GROUP_MINBLOCKS(G) ((G) == 32 ? 1 : 6)
 #endif
@@ -59,7 +62,7 @@ struct RadauTune {
     static constexpr int kThreads = 64;
     static constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
     static constexpr bool kSharedCold = kReg && (kCold * kThreads * 8 <= 48 * 1024);
-    static constexpr int kMinBlocks = (kSharedCold && S <= 3) ? 6 : 1;
+    static constexpr int kMinBlocks = (kSharedCold && S <= 3) ? B200DAE_REG_MINBLOCKS : 1;
 };
 
 // Group size of the cooperative kernels (group.cuh): the smallest power of two >= n (>= 8).
