@@ -179,6 +179,32 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld,
                       const b200dae_bdf_opts *opts,
                       const b200dae_outputs *out, void *stream);
 
+/* consistent_initial_conditions(fun, t0, y0, yp0, jac, fixed_y0, fixed_yp0, rtol, atol,
+ * newton_maxiter, chord_iter, safety) for N instances at once (common.py:186-258 with
+ * solve_underdetermined_system :269-372 and qrank :261-266).  y0 / yp0 [n][ld] are DEVICE arrays
+ * updated in place; atol[n], fixed_y[n], fixed_yp[n] (0 / 1 masks, NULL = nothing fixed) and opts
+ * are HOST.  Per-instance outcome in status[]: the reference raises RuntimeError("Convergence
+ * failed.") / ValueError("Too many fixed components, ...") / ValueError("Index greater than
+ * one.") where this writes NOCONV / TOO_MANY_FIXED / INDEX_GT_ONE.  f_out [n][ld] (may be NULL)
+ * receives the final residual, n_iter [ld] (may be NULL) the number of chord iterations. */
+#define B200DAE_CIC_OK 0
+#define B200DAE_CIC_NOCONV (-1)
+#define B200DAE_CIC_TOO_MANY_FIXED (-2)
+#define B200DAE_CIC_INDEX_GT_ONE (-3)
+typedef struct b200dae_cic_opts {
+    double rtol;                 /* 1e-8 */
+    double safety;               /* 0.5, in (0, 1] */
+    int32_t newton_maxiter;      /* 10 */
+    int32_t chord_iter;          /* 3 */
+    int32_t analytic_jac;        /* 0: approx_derivative("2-point") (jac=None); 1: functor Jacobians */
+    int32_t reserved;
+} b200dae_cic_opts;
+int b200dae_consistent_ic(int problem_id, int64_t N, int64_t ld, double t0,
+                          double *y0, double *yp0, const double *params, const double *atol,
+                          const int32_t *fixed_y, const int32_t *fixed_yp,
+                          const b200dae_cic_opts *opts,
+                          double *f_out, int32_t *status, int32_t *n_iter, void *stream);
+
 /* Number of kernels launched by this library since load (bench.py's "gpu_launches" claim). */
 int64_t b200dae_launch_count(void);
 

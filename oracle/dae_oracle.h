@@ -137,6 +137,18 @@ int orc_solve_ensemble(int problem_id, int method, int64_t N,
                        double *y_final, double *yp_final, double *t_final,
                        int32_t *status, int64_t *counters, int nthreads);
 
+/* consistent_initial_conditions (common.py:186-372), oracle/cic_oracle.c.
+ * status: 0 converged, -1 "Convergence failed." (RuntimeError), -2 "Too many fixed components",
+ * -3 "Index greater than one." (ValueErrors of solve_underdetermined_system). */
+int orc_consistent_ic(orc_residual_fn fn, orc_jacobian_fn jac_fn, int n, const double *p, double t0,
+                      double *y0, double *yp0, const int *fixed_y, const int *fixed_yp,
+                      double rtol, const double *atol, int newton_maxiter, int chord_iter,
+                      double safety, double *f_out, int *n_iter_out);
+int orc_consistent_ic_ensemble(int problem_id, int use_analytic_jac, int64_t N, const double *params,
+                               double t0, double *y0, double *yp0, const int *fixed_y, const int *fixed_yp,
+                               double rtol, const double *atol, int newton_maxiter, int chord_iter,
+                               double safety, double *f_out, int32_t *status, int32_t *n_iter);
+
 /* Building blocks exported for unit tests */
 double orc_select_initial_step(int n, double t0, const double *y0, const double *yp0,
                                double t_bound, double rtol, const double *atol, double max_step);

@@ -46,7 +46,7 @@ class BdfOpts(ctypes.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, f) for f in ("dae_oracle.c", "problems.c", "dae_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("dae_oracle.c", "cic_oracle.c", "problems.c", "dae_oracle.h")]
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
         return LIB_PATH
@@ -182,3 +182,34 @@ def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, 
         out["y_eval"] = ye      # [N, m, n]
         out["yp_eval"] = ype
     return out
+
+
+CIC_MESSAGES = {0: "converged", -1: "Convergence failed.", -2: "Too many fixed components",
+                -3: "Index greater than one."}
+
+
+def consistent_initial_conditions(problem, t0, y0, yp0, params, jac=None, fixed_y0=None, fixed_yp0=None,
+                                  rtol=1e-8, atol=1e-8, newton_maxiter=10, chord_iter=3, safety=0.5):
+    """N instances of the reference's consistent_initial_conditions (common.py:186-258) through the
+    C oracle.  Returns dict(y0[N,n], yp0[N,n], f[N,n], status[N], n_iter[N])."""
+    pid, n, npar = problem_id(problem)
+    params = np.ascontiguousarray(np.atleast_2d(params), dtype=float)
+    y0 = np.array(np.atleast_2d(y0), dtype=float, order="C")
+    yp0 = np.array(np.atleast_2d(yp0), dtype=float, order="C")
+    N = y0.shape[0]
+    assert params.shape == (N, npar) and y0.shape == (N, n) and yp0.shape == (N, n)
+    fy = np.zeros(n, dtype=np.int32); fyp = np.zeros(n, dtype=np.int32)
+    if fixed_y0 is not None:
+        fy[np.asarray(fixed_y0, dtype=int)] = 1
+    if fixed_yp0 is not None:
+        fyp[np.asarray(fixed_yp0, dtype=int)] = 1
+    atol_v = np.ascontiguousarray(np.broadcast_to(np.asarray(atol, dtype=float), (n,)))
+    f = np.empty((N, n)); status = np.zeros(N, dtype=np.int32); n_iter = np.zeros(N, dtype=np.int32)
+    rc = lib().orc_consistent_ic_ensemble(
+        ctypes.c_int(pid), ctypes.c_int(1 if jac == "analytic" else 0), ctypes.c_int64(N), _p(params),
+        ctypes.c_double(float(t0)), _p(y0), _p(yp0), _p(fy, ctypes.c_int32), _p(fyp, ctypes.c_int32),
+        ctypes.c_double(float(rtol)), _p(atol_v), ctypes.c_int(newton_maxiter), ctypes.c_int(chord_iter),
+        ctypes.c_double(float(safety)), _p(f), _p(status, ctypes.c_int32), _p(n_iter, ctypes.c_int32))
+    if rc != 0:
+        raise RuntimeError(f"orc_consistent_ic_ensemble returned {rc}")
+    return dict(y0=y0, yp0=yp0, f=f, status=status, n_iter=n_iter)

@@ -21,7 +21,7 @@ ST_FINISHED, ST_TOO_SMALL_STEP, ST_NONFINITE, ST_MAX_STEPS, ST_RUNNING = 0, -1, 
 EXPORTS = ("b200dae_version", "b200dae_last_error", "b200dae_num_problems",
            "b200dae_problem_lookup", "b200dae_problem_name", "b200dae_residual",
            "b200dae_solve_radau", "b200dae_solve_bdf", "b200dae_launch_count",
-           "b200dae_fp64_peak_kernel", "b200dae_selftest_fastmath")
+           "b200dae_fp64_peak_kernel", "b200dae_selftest_fastmath", "b200dae_consistent_ic")
 
 
 class B200DaeLibraryError(ImportError):
@@ -46,6 +46,12 @@ class BdfOpts(ctypes.Structure):
     _fields_ = [("rtol", ctypes.c_double), ("max_step", ctypes.c_double),
                 ("first_step", ctypes.c_double), ("max_order", ctypes.c_int32),
                 ("ndf_strategy", ctypes.c_int32), ("max_steps", ctypes.c_int64),
+                ("analytic_jac", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class CicOpts(ctypes.Structure):
+    _fields_ = [("rtol", ctypes.c_double), ("safety", ctypes.c_double),
+                ("newton_maxiter", ctypes.c_int32), ("chord_iter", ctypes.c_int32),
                 ("analytic_jac", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
@@ -97,6 +103,9 @@ def load():
     L.b200dae_solve_bdf.restype = ctypes.c_int
     L.b200dae_solve_bdf.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, dbl, dbl, dblp,
                                     ctypes.POINTER(BdfOpts), ctypes.POINTER(Outputs), vp]
+    L.b200dae_consistent_ic.restype = ctypes.c_int
+    L.b200dae_consistent_ic.argtypes = [ctypes.c_int, i64, i64, dbl, vp, vp, vp, dblp, i32p, i32p,
+                                        ctypes.POINTER(CicOpts), vp, vp, vp, vp]
     L.b200dae_fp64_peak_kernel.restype = ctypes.c_int
     L.b200dae_fp64_peak_kernel.argtypes = [ctypes.c_int, ctypes.c_int, i64, vp, vp]
     L.b200dae_selftest_fastmath.restype = ctypes.c_int

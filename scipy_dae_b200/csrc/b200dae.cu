@@ -247,6 +247,49 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
     return 0;
 }
 
+int b200dae_consistent_ic(int problem_id, int64_t N, int64_t ld, double t0, double* y0, double* yp0,
+                          const double* params, const double* atol, const int32_t* fixed_y,
+                          const int32_t* fixed_yp, const b200dae_cic_opts* opts, double* f_out,
+                          int32_t* status, int32_t* n_iter, void* stream) {
+    const ProblemEntry* e = find_problem(problem_id);
+    if (!e) return fail(B200DAE_ENOPROBLEM, "unknown problem id%s (%lld)", "", problem_id);
+    if (N < 0 || ld < N) return fail(B200DAE_EINVAL, "need 0 <= N <= ld%s (N=%lld)", "", (long long)N);
+    if (N > 0 && (!y0 || !yp0 || !status || (e->n_params > 0 && !params)))
+        return fail(B200DAE_EINVAL, "y0 / yp0 / params / status must not be NULL%s", "");
+    if (!atol || !opts) return fail(B200DAE_EINVAL, "atol[n] and opts must not be NULL%s", "");
+    if (!(opts->rtol > 0)) return fail(B200DAE_EINVAL, "Relative tolerance must be a positive scalar.%s", "");
+    if (!(opts->safety > 0 && opts->safety <= 1)) return fail(B200DAE_EINVAL, "safety factor has to be in (0, 1]%s", "");
+    if (opts->newton_maxiter < 0 || opts->chord_iter < 0) return fail(B200DAE_EINVAL, "iteration counts must be >= 0%s", "");
+    CicLaunch L;
+    memset(&L, 0, sizeof(L));
+    for (int j = 0; j < e->n; ++j) {
+        if (!(atol[j] > 0)) return fail(B200DAE_EINVAL, "Absolute tolerance must be positive.%s", "");
+        L.atol[j] = atol[j];
+        L.fixed_y[j] = fixed_y ? (fixed_y[j] != 0) : 0;
+        L.fixed_yp[j] = fixed_yp ? (fixed_yp[j] != 0) : 0;
+    }
+    if (N == 0) return 0;
+    L.t0 = t0;
+    L.rtol = opts->rtol;
+    L.safety = opts->safety;
+    L.newton_maxiter = opts->newton_maxiter;
+    L.chord_iter = opts->chord_iter;
+    L.analytic_jac = opts->analytic_jac;
+    L.N = N;
+    L.ld = ld;
+    L.y0 = y0;
+    L.yp0 = yp0;
+    L.params = params;
+    L.f_out = f_out;
+    L.status = status;
+    L.n_iter = n_iter;
+    const int rc = e->cic(L, (cudaStream_t)stream);
+    if (rc == kErrNoJac)
+        return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s'%s", e->name);
+    if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
 int b200dae_selftest_fastmath(int64_t n, const double* x, double* rcp_out, double* sqrt_out, void* stream) {
     if (n < 0 || !x || !rcp_out || !sqrt_out) return fail(B200DAE_EINVAL, "bad selftest arguments%s", "");
     if (n == 0) return 0;

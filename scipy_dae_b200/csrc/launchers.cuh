@@ -11,6 +11,7 @@
 #include "../../include/b200dae.h"
 #include "bdf.cuh"
 #include "bdf_group.cuh"
+#include "cic.cuh"
 #include "problems.cuh"
 #include "radau.cuh"
 #include "radau_group.cuh"
@@ -28,6 +29,7 @@ extern std::atomic<int64_t> g_launches;
 
 typedef int (*radau_launcher)(const RadauLaunch&, cudaStream_t);
 typedef int (*bdf_launcher)(const BdfLaunch&, cudaStream_t);
+typedef int (*cic_launcher)(const CicLaunch&, cudaStream_t);
 typedef int (*residual_launcher)(int64_t, int64_t, double, const double*, const double*,
                                  const double*, double*, cudaStream_t);
 
@@ -37,6 +39,7 @@ struct ProblemEntry {
     radau_launcher radau[B200DAE_MAX_STAGES + 1];   // indexed by the number of stages
     bdf_launcher bdf;
     residual_launcher residual;
+    cic_launcher cic;
 };
 
 ProblemEntry entry_robertson();
@@ -198,6 +201,19 @@ static int launch_residual(int64_t N, int64_t ld, double t, const double* y, con
     return (int)cudaGetLastError();
 }
 
+template <class P>
+static int launch_cic(const CicLaunch& L, cudaStream_t st) {
+    if (L.analytic_jac && !P::kHasJac) return kErrNoJac;
+    const unsigned blocks = (unsigned)((L.N + 31) / 32);
+    bool done = false;
+    if constexpr (P::kHasJac) {
+        if (L.analytic_jac) { cic_kernel<P, true><<<blocks, 32, 0, st>>>(L); done = true; }
+    }
+    if (!done) cic_kernel<P, false><<<blocks, 32, 0, st>>>(L);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
 template <class P, bool S1, bool S5, bool S7>
 static ProblemEntry make_entry() {
     ProblemEntry e;
@@ -211,6 +227,7 @@ static ProblemEntry make_entry() {
     if constexpr (S7) e.radau[7] = launch_radau<P, 7>;
     e.bdf = launch_bdf<P>;
     e.residual = launch_residual<P>;
+    e.cic = launch_cic<P>;
     return e;
 }
 
