@@ -88,6 +88,18 @@ def algorithmic_flops(cnt: dict, n: int, s: int, c_f: int, fd: int = 1) -> float
     return float(fl)
 
 
+def ncu_traffic(n_per_gpu: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/), per launch, if it was taken at this batch size."""
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "r01_headline_traffic.json")))
+    except (OSError, ValueError):
+        return None
+    if int(d.get("instances", -1)) != int(n_per_gpu):
+        return None
+    return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+
+
 def compulsory_bytes(n: int, n_params: int) -> int:
     """HBM bytes one instance must move without t_eval: params, y0, yp0 in; y, yp, t, status, 8 counters out."""
     return 8 * (n_params + 2 * n) + 8 * (2 * n + 1) + 4 + 4 * 8
@@ -398,14 +410,14 @@ def main():
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64",
-                "kernel": "radau_kernel<Robertson,3,128>",
+                "kernel": "radau_kernel<Robertson,3,64 threads,6 blocks/SM,lean>",
                 "achieved": ach_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                 "frac": ach_tflops / fp64_peak_tflops,
                 "peak_source": "DFMA-chain microbenchmark run in this process (b200dae_fp64_peak_kernel); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "flops_per_launch": flops_per_launch, "flops_per_solve": flops_per_launch / Nper,
                 "kernel_ms": kernel_s * 1e3,
-                "traffic": None,
+                "traffic": ncu_traffic(Nper),
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "bytes_per_launch": bytes_per_launch,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
