@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--jac", default="fd", choices=["fd", "analytic"],
                     help="fd = finite-difference Jacobian (the headline, jac=None in the reference); "
                          "analytic = the functor's analytic Jacobians (a `jac` callable in the reference)")
+    ap.add_argument("--e2e-no-graph", action="store_true",
+                    help="queue the host pipeline eagerly instead of replaying its CUDA graph")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline chunks of the host-facing call")
     return ap.parse_args()
 
@@ -160,6 +162,25 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index: int):
+    """Run this rank (and allocate its pinned buffers) on the CPUs NVML reports as local to the
+    GPU: host<->device copies from the far socket were 2-4x slower and erratic in the e2e timing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cpus local to gpu {index}"
+    except Exception as exc:            # noqa: BLE001 - measurement hygiene only
+        return f"unchanged ({type(exc).__name__})"
+    return "unchanged"
+
+
 def cpu_port_run(params, y0, yp0, nthreads):
     from oracle import oracle as O
     t = time.perf_counter()
@@ -242,6 +263,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: scipy_dae_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    affinity = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -328,7 +350,7 @@ def main():
     def e2e_step():
         return solve_dae_batched_host("robertson", WORKLOAD["t_span"], h_y0, h_yp0, h_params, method="Radau",
                                       rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], device=dev,
-                                      chunks=args.e2e_chunks, out=host_out,
+                                      chunks=args.e2e_chunks, out=host_out, use_graph=not args.e2e_no_graph,
                                       jac="analytic" if args.jac == "analytic" else None)
 
     for _ in range(2):
@@ -405,7 +427,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
                     "timer": "host perf_counter bracketed by cuda synchronize",
-                    "api": f"solve_dae_batched_host(chunks={args.e2e_chunks}), pinned host inputs and outputs"},
+                    "api": f"solve_dae_batched_host(chunks={args.e2e_chunks}, use_graph={not args.e2e_no_graph}), "
+                           "pinned host inputs and outputs",
+                    "ms_each": [round(x, 3) for x in e2e_ms], "cpu_affinity": affinity},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": {

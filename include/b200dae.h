@@ -30,10 +30,11 @@
 extern "C" {
 #endif
 
-#define B200DAE_VERSION 101
+#define B200DAE_VERSION 102
 #define B200DAE_MAX_STAGES 7
 #define B200DAE_MAX_ORDER 6
 #define B200DAE_MAX_N 32
+#define B200DAE_MAX_EVENTS 4
 
 /* library-level error codes (return values) */
 #define B200DAE_OK 0
@@ -50,6 +51,8 @@ extern "C" {
 #define B200DAE_ST_MAX_STEPS (-3)     /* opts.max_steps accepted steps done, t_bound not reached
                                          (resumable; no reference equivalent) */
 #define B200DAE_ST_RUNNING 1          /* only ever seen in a state block between resumed launches */
+#define B200DAE_ST_EVENT 2            /* a terminal event stopped the integration (solve_dae status 1,
+                                         "A termination event occurred.", dae.py:484-487) */
 
 /* rows of counters[8][ld] (int32).  nfev/njev/nlu are DaeSolver.nfev/njev/nlu (base.py:180-182),
  * nsolve is DaeSolver._nlusove (base.py:183); the rest are derived in the reference by wrapping
@@ -116,6 +119,31 @@ typedef struct b200dae_bdf_opts {
     int32_t reserved;
 } b200dae_bdf_opts;
 
+/* Events of solve_dae (dae.py:30-109, 426-490).  A Python event callable cannot run inside the
+ * device step loop; the device offers THRESHOLD events g_k(t, y, y') = x[component_k] - value_k,
+ * x = y (of_yp = 0) or y' (of_yp = 1), with the attributes of a solve_dae event function:
+ * direction (> 0 only - to +, < 0 only + to -, 0 both) and terminal (max_events <= 0: never
+ * terminal, 1: `terminal = True`, k: `terminal = k`, i.e. stop at the k-th occurrence).  Roots are
+ * located on the step's dense output with Brent's method, xtol = rtol = 4 EPS (dae.py:30-55).
+ * HOST struct; the output pointers inside are DEVICE:
+ *   t_events [n_events][cap][ld], y_events / yp_events [n_events][cap][n][ld],
+ *   n_found [n_events][ld] (occurrences seen; only the first `cap` are stored). */
+typedef struct b200dae_event_spec {
+    int32_t n_events;
+    int32_t of_yp[B200DAE_MAX_EVENTS];
+    int32_t component[B200DAE_MAX_EVENTS];
+    double value[B200DAE_MAX_EVENTS];
+    int32_t direction[B200DAE_MAX_EVENTS];
+    int32_t max_events[B200DAE_MAX_EVENTS];
+} b200dae_event_spec;
+
+typedef struct b200dae_events {
+    b200dae_event_spec spec;
+    int64_t cap;
+    double *t_events, *y_events, *yp_events;
+    int32_t *n_found;
+} b200dae_events;
+
 /* Output block shared by both integrators.  Any pointer may be NULL (that output is skipped),
  * except y_final/t_final/status.
  *   y_final, yp_final [n][ld]   state at t_final            (solver.y / solver.yp after the loop)
@@ -142,6 +170,7 @@ typedef struct b200dae_outputs {
     int64_t steps_cap;
     double *t_steps, *y_steps, *yp_steps;
     int32_t *n_steps;
+    const b200dae_events *events;   /* HOST pointer, NULL = no events */
 } b200dae_outputs;
 
 int b200dae_version(void);

@@ -671,6 +671,138 @@ static int eval_reached(double te, double t, double dir)
     return dir > 0 ? (te <= t) : (te >= t);
 }
 
+
+/* ------------------------------------------------------------------------- */
+/* events (dae.py:30-109, 426-490): threshold events g(t, y, yp) = x[component] - value on   */
+/* x = y or yp; sign-change detection = scipy find_active_events, root = scipy brentq with    */
+/* xtol = rtol = 4 EPS on the step's dense output, terminal handling = handle_events          */
+/* ------------------------------------------------------------------------- */
+typedef void (*dense_fn)(const void *st, double t, double *y, double *yp);
+
+typedef struct {
+    const orc_events *spec;
+    int64_t cap;
+    double *t_events, *y_events, *yp_events;     /* [ne][cap], [ne][cap][n] */
+    int32_t *n_found;                            /* [ne] */
+    double g[ORC_MAX_EVENTS];
+    int64_t count[ORC_MAX_EVENTS];
+} event_ctx;
+
+static __thread event_ctx *tl_ev = NULL;
+
+static double event_value(const orc_events *e, int k, const double *y, const double *yp)
+{
+    return (e->of_yp[k] ? yp[e->component[k]] : y[e->component[k]]) - e->value[k];
+}
+
+/* scipy/optimize/Zeros/brentq.c (maxiter = 100); f(t) = event k on the dense output */
+static double brentq_event(const orc_events *e, int k, dense_fn dense, const void *st, int n,
+                           double xa, double xb, double *ytmp, double *yptmp)
+{
+    const double xtol = 4 * EPS, rtol = 4 * EPS;
+    double xpre = xa, xcur = xb, xblk = 0., fpre, fcur, fblk = 0., spre = 0., scur = 0., sbis, delta, stry, dpre, dblk;
+    (void)n;
+    dense(st, xpre, ytmp, yptmp); fpre = event_value(e, k, ytmp, yptmp);
+    dense(st, xcur, ytmp, yptmp); fcur = event_value(e, k, ytmp, yptmp);
+    if (fpre == 0) return xpre;
+    if (fcur == 0) return xcur;
+    if (signbit(fpre) == signbit(fcur)) return NAN;                          /* ValueError in scipy */
+    for (int i = 0; i < 100; ++i) {
+        if (fpre != 0 && fcur != 0 && (signbit(fpre) != signbit(fcur))) {
+            xblk = xpre; fblk = fpre; spre = scur = xcur - xpre;
+        }
+        if (fabs(fblk) < fabs(fcur)) {
+            xpre = xcur; xcur = xblk; xblk = xpre;
+            fpre = fcur; fcur = fblk; fblk = fpre;
+        }
+        delta = (xtol + rtol * fabs(xcur)) / 2;
+        sbis = (xblk - xcur) / 2;
+        if (fcur == 0 || fabs(sbis) < delta) return xcur;
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            if (xpre == xblk) {
+                stry = -fcur * (xcur - xpre) / (fcur - fpre);                /* secant */
+            } else {
+                dpre = (fpre - fcur) / (xpre - xcur);                        /* inverse quadratic */
+                dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            double lim = fmin(fabs(spre), 3 * fabs(sbis) - delta);
+            if (2 * fabs(stry) < lim) { spre = scur; scur = stry; }
+            else { spre = sbis; scur = sbis; }
+        } else {
+            spre = sbis; scur = sbis;
+        }
+        xpre = xcur; fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur;
+        else xcur += (sbis > 0 ? delta : -delta);
+        dense(st, xcur, ytmp, yptmp); fcur = event_value(e, k, ytmp, yptmp);
+    }
+    return xcur;
+}
+
+/* After an accepted step [t_old, t]: dae.py:466-490.  Returns 1 when a terminal event fired;
+ * then *t_stop, y_stop, yp_stop hold the event point that replaces the step end. */
+static int handle_events_step(event_ctx *c, dense_fn dense, const void *st, int n, double t_old,
+                              double t, const double *y, const double *yp, double dir,
+                              double *t_stop, double *y_stop, double *yp_stop)
+{
+    const orc_events *e = c->spec;
+    int ne = e->n_events, act[ORC_MAX_EVENTS], na = 0;
+    double gnew[ORC_MAX_EVENTS], roots[ORC_MAX_EVENTS];
+    double *ytmp = malloc(sizeof(double) * n), *yptmp = malloc(sizeof(double) * n);
+    for (int k = 0; k < ne; ++k) {
+        gnew[k] = event_value(e, k, y, yp);
+        int up = (c->g[k] <= 0) && (gnew[k] >= 0), down = (c->g[k] >= 0) && (gnew[k] <= 0);
+        int d = e->direction[k];
+        if ((up && d > 0) || (down && d < 0) || ((up || down) && d == 0)) act[na++] = k;
+    }
+    int terminate = 0;
+    if (na > 0) {
+        int any_term = 0;
+        for (int a = 0; a < na; ++a) {
+            int k = act[a];
+            c->count[k] += 1;
+            roots[a] = brentq_event(e, k, dense, st, n, t_old, t, ytmp, yptmp);
+        }
+        for (int a = 0; a < na; ++a)
+            if (e->max_events[act[a]] > 0 && c->count[act[a]] >= e->max_events[act[a]]) any_term = 1;
+        int nrec = na;
+        if (any_term) {
+            /* stable sort by root in the direction of integration, cut after the first terminal one */
+            for (int i = 1; i < na; ++i)
+                for (int j = i; j > 0; --j) {
+                    int swap = dir > 0 ? (roots[j] < roots[j - 1]) : (-roots[j] < -roots[j - 1]);
+                    if (!swap) break;
+                    double tr = roots[j]; roots[j] = roots[j - 1]; roots[j - 1] = tr;
+                    int ti = act[j]; act[j] = act[j - 1]; act[j - 1] = ti;
+                }
+            for (int a = 0; a < na; ++a)
+                if (e->max_events[act[a]] > 0 && c->count[act[a]] >= e->max_events[act[a]]) { nrec = a + 1; break; }
+            terminate = 1;
+        }
+        for (int a = 0; a < nrec; ++a) {
+            int k = act[a];
+            dense(st, roots[a], ytmp, yptmp);
+            int32_t idx = c->n_found[k];
+            if (idx < c->cap) {
+                c->t_events[k * c->cap + idx] = roots[a];
+                memcpy(c->y_events + (k * c->cap + idx) * n, ytmp, sizeof(double) * n);
+                memcpy(c->yp_events + (k * c->cap + idx) * n, yptmp, sizeof(double) * n);
+            }
+            c->n_found[k] = idx + 1;
+        }
+        if (terminate) {
+            *t_stop = roots[nrec - 1];
+            dense(st, *t_stop, y_stop, yp_stop);
+        }
+    }
+    for (int k = 0; k < ne; ++k) c->g[k] = gnew[k];
+    free(ytmp); free(yptmp);
+    return terminate;
+}
+
+static void radau_dense_void(const void *st, double t, double *y, double *yp) { radau_dense_eval((const radau_state *)st, t, y, yp); }
+
 int orc_solve_radau(orc_residual_fn fn, int n, const double *p,
                     double t0, double t_bound, const double *y0, const double *yp0,
                     const double *atol, const orc_radau_opts *o, const orc_radau_tables *tb,
@@ -718,8 +850,19 @@ int orc_solve_radau(orc_residual_fn fn, int n, const double *p,
     if (n == 0 || t0 == t_bound) {
         /* base.py:376-381: degenerate, finishes immediately */
     } else {
+        event_ctx *ec = tl_ev;
+        if (ec) for (int k = 0; k < ec->spec->n_events; ++k) ec->g[k] = event_value(ec->spec, k, y0, yp0);
         for (;;) {
+            double t_prev = b->t;
             if (!radau_step(&st)) { status = st.status; break; }
+            if (ec) {
+                double ts;
+                if (handle_events_step(ec, radau_dense_void, &st, n, t_prev, b->t, b->y, b->yp, b->dir,
+                                       &ts, st.tmpn, st.tmpn2)) {
+                    b->t = ts; memcpy(b->y, st.tmpn, sizeof(double) * n); memcpy(b->yp, st.tmpn2, sizeof(double) * n);
+                    status = 1;                                             /* dae.py:484-487 */
+                }
+            }
             if (t_steps && nsteps < steps_cap) {
                 t_steps[nsteps] = b->t; memcpy(y_steps + nsteps * n, b->y, sizeof(double) * n); ++nsteps;
             }
@@ -727,6 +870,7 @@ int orc_solve_radau(orc_residual_fn fn, int n, const double *p,
                 radau_dense_eval(&st, t_eval[ie], y_eval + ie * n, yp_eval + ie * n);
                 ++ie;
             }
+            if (status == 1) break;
             if (b->dir * (b->t - b->t_bound) >= 0) break;                   /* base.py:389-390 */
             if (o->max_steps > 0 && counters[ORC_CNT_ACCEPTED] >= o->max_steps) { status = -3; break; }
         }
@@ -998,6 +1142,8 @@ static void bdf_dense_eval(const bdf_state *st, double t, double *y, double *yp)
     }
 }
 
+static void bdf_dense_void(const void *st, double t, double *y, double *yp) { bdf_dense_eval((const bdf_state *)st, t, y, yp); }
+
 int orc_solve_bdf(orc_residual_fn fn, int n, const double *p,
                   double t0, double t_bound, const double *y0, const double *yp0,
                   const double *atol, const orc_bdf_opts *o,
@@ -1050,8 +1196,19 @@ int orc_solve_bdf(orc_residual_fn fn, int n, const double *p,
         t_steps[0] = t0; memcpy(y_steps, y0, sizeof(double) * n); nsteps = 1;
     }
     if (!(n == 0 || t0 == t_bound)) {
+        event_ctx *ec = tl_ev;
+        if (ec) for (int k = 0; k < ec->spec->n_events; ++k) ec->g[k] = event_value(ec->spec, k, y0, yp0);
         for (;;) {
+            double t_prev = b->t;
             if (!bdf_step(&st)) { status = st.status; break; }
+            if (ec) {
+                double ts;
+                if (handle_events_step(ec, bdf_dense_void, &st, n, t_prev, b->t, b->y, b->yp, b->dir,
+                                       &ts, st.tmp, st.f)) {
+                    b->t = ts; memcpy(b->y, st.tmp, sizeof(double) * n); memcpy(b->yp, st.f, sizeof(double) * n);
+                    status = 1;
+                }
+            }
             if (t_steps && nsteps < steps_cap) {
                 t_steps[nsteps] = b->t; memcpy(y_steps + nsteps * n, b->y, sizeof(double) * n); ++nsteps;
             }
@@ -1059,6 +1216,7 @@ int orc_solve_bdf(orc_residual_fn fn, int n, const double *p,
                 bdf_dense_eval(&st, t_eval[ie], y_eval + ie * n, yp_eval + ie * n);
                 ++ie;
             }
+            if (status == 1) break;
             if (b->dir * (b->t - b->t_bound) >= 0) break;
             if (o->max_steps > 0 && counters[ORC_CNT_ACCEPTED] >= o->max_steps) { status = -3; break; }
         }
@@ -1088,6 +1246,8 @@ typedef struct {
     double *y_eval, *yp_eval, *y_final, *yp_final, *t_final;
     int64_t *n_eval_valid, *counters;
     int32_t *status;
+    const orc_events *ev; int64_t ev_cap;
+    double *t_events, *y_events, *yp_events; int32_t *n_found;     /* [N][ne][cap]([n]), [N][ne] */
     int64_t next;
     pthread_mutex_t lock;
 } ens_job;
@@ -1111,6 +1271,20 @@ static void *ens_worker(void *arg)
             int64_t nev = 0;
             int64_t mm = (ye && ype) ? J->m : 0;
             int st;
+            event_ctx ec;
+            if (J->ev && J->ev->n_events > 0) {
+                int ne = J->ev->n_events;
+                memset(&ec, 0, sizeof(ec));
+                ec.spec = J->ev; ec.cap = J->ev_cap;
+                ec.t_events = J->t_events + i * ne * J->ev_cap;
+                ec.y_events = J->y_events + i * ne * J->ev_cap * n;
+                ec.yp_events = J->yp_events + i * ne * J->ev_cap * n;
+                ec.n_found = J->n_found + i * ne;
+                for (int k = 0; k < ne; ++k) ec.n_found[k] = 0;
+                tl_ev = &ec;
+            } else {
+                tl_ev = NULL;
+            }
             if (J->method == 0)
                 st = orc_solve_radau(fn, n, J->params + i * J->np, J->t0, J->t_bound,
                                      J->y0 + i * n, J->yp0 + i * n, J->atol, J->ropts, J->tb,
@@ -1123,11 +1297,25 @@ static void *ens_worker(void *arg)
                                    J->t_eval, mm, ye, ype, &nev,
                                    J->y_final + i * n, J->yp_final + i * n, J->t_final + i,
                                    J->counters + i * ORC_NUM_COUNTERS, NULL, NULL, 0, NULL);
+            tl_ev = NULL;
             J->status[i] = st;
             if (J->n_eval_valid) J->n_eval_valid[i] = nev;
         }
     }
     return NULL;
+}
+
+static const orc_events *g_ev = NULL;
+static int64_t g_ev_cap = 0;
+static double *g_t_events = NULL, *g_y_events = NULL, *g_yp_events = NULL;
+static int32_t *g_n_found = NULL;
+
+/* events for the NEXT orc_solve_ensemble call (NULL spec switches them off again) */
+void orc_set_events(const orc_events *spec, int64_t cap, double *t_events, double *y_events,
+                    double *yp_events, int32_t *n_found)
+{
+    g_ev = spec; g_ev_cap = cap; g_t_events = t_events; g_y_events = y_events;
+    g_yp_events = yp_events; g_n_found = n_found;
 }
 
 int orc_solve_ensemble(int problem_id, int method, int64_t N,
@@ -1148,6 +1336,8 @@ int orc_solve_ensemble(int problem_id, int method, int64_t N,
     J.t0 = t0; J.t_bound = t_bound; J.ropts = ropts; J.tb = tb; J.bopts = bopts; J.m = m;
     J.y_eval = y_eval; J.yp_eval = yp_eval; J.y_final = y_final; J.yp_final = yp_final;
     J.t_final = t_final; J.n_eval_valid = n_eval_valid; J.counters = counters; J.status = status;
+    J.ev = g_ev; J.ev_cap = g_ev_cap; J.t_events = g_t_events; J.y_events = g_y_events;
+    J.yp_events = g_yp_events; J.n_found = g_n_found;
     J.next = 0;
     pthread_mutex_init(&J.lock, NULL);
     if (nthreads < 1) nthreads = 1;

@@ -105,6 +105,23 @@ int orc_solve_bdf(orc_residual_fn fn, int n, const double *p,
                   double *y_final, double *yp_final, double *t_final, int64_t *counters,
                   double *t_steps, double *y_steps, int64_t steps_cap, int64_t *n_steps);
 
+/* Threshold events g_k(t, y, yp) = x[component_k] - value_k, x = y (of_yp = 0) or yp (of_yp = 1);
+ * direction / terminal as the attributes of a solve_dae event function (dae.py:226-247):
+ * max_events <= 0 = never terminal, 1 = `terminal = True`, k = `terminal = k`. */
+#define ORC_MAX_EVENTS 4
+typedef struct orc_events {
+    int32_t n_events;
+    int32_t of_yp[ORC_MAX_EVENTS];
+    int32_t component[ORC_MAX_EVENTS];
+    double value[ORC_MAX_EVENTS];
+    int32_t direction[ORC_MAX_EVENTS];
+    int32_t max_events[ORC_MAX_EVENTS];
+} orc_events;
+/* outputs: t_events[N][ne][cap], y_events / yp_events[N][ne][cap][n], n_found[N][ne];
+ * instance status 1 = a terminal event stopped the integration (solve_dae status 1) */
+void orc_set_events(const orc_events *spec, int64_t cap, double *t_events, double *y_events,
+                    double *yp_events, int32_t *n_found);
+
 /* analytic Jacobian (the reference's `jac=` callable, base.py:299-331): Jy, Jyp row-major n*n */
 typedef void (*orc_jacobian_fn)(double t, const double *y, const double *yp, const double *p,
                                 double *Jy, double *Jyp);

@@ -65,6 +65,16 @@ def run_instance(problem, params, y0, yp0, t_span, method, rtol, atol, t_eval, o
     for k in _cnt:
         _cnt[k] = 0
     options = dict(options)
+    ev_spec = options.pop("events", None)
+    ev_cap = options.pop("event_cap", 16)
+    if ev_spec:                               # threshold events as the reference's event callables
+        def make(e):
+            j, c, of_yp = int(e["component"]), float(e["value"]), e.get("of", "y") == "yp"
+            fn = (lambda t, y, yp, *a: yp[j] - c) if of_yp else (lambda t, y, yp, *a: y[j] - c)
+            fn.direction = float(e.get("direction", 0))
+            fn.terminal = e.get("terminal", False)
+            return fn
+        options["events"] = [make(e) for e in ev_spec]
     if options.get("jac") == "analytic":     # the problem's analytic Jacobians as the `jac` callable
         options["jac"] = problem.jacobian
     with warnings.catch_warnings():
@@ -83,6 +93,15 @@ def run_instance(problem, params, y0, yp0, t_span, method, rtol, atol, t_eval, o
     if record_steps:
         out["t_steps"] = sol.t
         out["y_steps"] = sol.y
+    if ev_spec:
+        ne = len(ev_spec)
+        te = np.full((ne, ev_cap), np.nan); yev = np.full((ne, ev_cap, problem.n), np.nan)
+        ypev = np.full((ne, ev_cap, problem.n), np.nan); nf = np.zeros(ne, dtype=np.int64)
+        for k in range(ne):
+            nf[k] = len(sol.t_events[k])
+            for i in range(min(nf[k], ev_cap)):
+                te[k, i] = sol.t_events[k][i]; yev[k, i] = sol.y_events[k][i]; ypev[k, i] = sol.yp_events[k][i]
+        out.update(t_events=te, y_events=yev, yp_events=ypev, n_events_found=nf)
     if t_eval is not None:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -129,6 +148,9 @@ def run_case(name, problem, params, method, rtol, atol, t_span=None, t_eval=None
     if record_steps:
         arrays["t_steps"] = res[0]["t_steps"]
         arrays["y_steps"] = res[0]["y_steps"]
+    if "t_events" in res[0]:
+        for key in ("t_events", "y_events", "yp_events", "n_events_found"):
+            arrays[key] = np.stack([r[key] for r in res])
     meta = dict(case=name, problem=problem.name, method=method, rtol=rtol,
                 atol=atol if np.isscalar(atol) else list(atol), t_span=list(t_span),
                 options=options, N=N, reference="JonasBreuling/scipy_dae v0.1.0 (/root/reference)",
@@ -212,6 +234,30 @@ def cases():
     yield dict(name="andrews_radau3_ens", problem="andrews",
                params=perturbed_params("andrews", 4, 0.05, 2), method="Radau",
                rtol=1e-6, atol=1e-6, options=dict(stages=3))
+    # --- row N3 of SURVEY §8f: events (dae.py:30-109, 426-490) as threshold events
+    yield dict(name="robertson_radau3_events", problem="robertson",
+               params=perturbed_params("robertson", 8, 0.1, 0), method="Radau", rtol=1e-6, atol=1e-6,
+               t_eval=np.logspace(-5, 7, 13),
+               options=dict(events=[dict(component=0, value=0.9), dict(component=1, value=3e-5, direction=-1),
+                                    dict(component=2, value=0.5, terminal=True)]))
+    yield dict(name="robertson_bdf_events", problem="robertson",
+               params=perturbed_params("robertson", 8, 0.1, 0), method="BDF", rtol=1e-6, atol=1e-6,
+               options=dict(events=[dict(component=0, value=0.9), dict(component=1, value=3e-5, direction=-1),
+                                    dict(component=2, value=0.5, terminal=True)]))
+    # an event on y' (the Radau dense output reproduces y' at both step ends; with the reference's
+    # BDF interpolant the same event makes brentq raise "f(a) and f(b) must have different signs")
+    yield dict(name="robertson_radau3_events_yp", problem="robertson",
+               params=perturbed_params("robertson", 4, 0.1, 0), method="Radau", rtol=1e-6, atol=1e-6,
+               t_span=(0.0, 1e3),
+               options=dict(events=[dict(component=1, of="yp", value=0.0), dict(component=0, of="yp", value=-0.01, direction=1)]))
+    yield dict(name="transamp_radau3_events", problem="transamp",
+               params=perturbed_params("transamp", 4, 0.02, 1), method="Radau", rtol=1e-8, atol=1e-8,
+               options=dict(events=[dict(component=7, value=-1.0, direction=1),
+                                    dict(component=7, value=-1.0, direction=-1, terminal=5),
+                                    dict(component=4, value=3.0)]))
+    yield dict(name="akzo_bdf_events", problem="akzo_nobel",
+               params=perturbed_params("akzo_nobel", 8, 0.05, 0), method="BDF", rtol=1e-8, atol=1e-8,
+               options=dict(events=[dict(component=0, value=0.2, terminal=True), dict(component=2, value=0.1)]))
     # --- row N2 of SURVEY §8f: analytic Jacobian callables (base.py:299-331)
     yield dict(name="robertson_radau3_jac", problem="robertson",
                params=perturbed_params("robertson", 16, 0.1, 0), method="Radau",

@@ -107,8 +107,31 @@ def jacobian(name, t, y, yp, params):
     return Jy, Jyp
 
 
+MAX_EVENTS = 4
+
+
+class Events(ctypes.Structure):
+    _fields_ = [("n_events", ctypes.c_int32), ("of_yp", ctypes.c_int32 * MAX_EVENTS),
+                ("component", ctypes.c_int32 * MAX_EVENTS), ("value", ctypes.c_double * MAX_EVENTS),
+                ("direction", ctypes.c_int32 * MAX_EVENTS), ("max_events", ctypes.c_int32 * MAX_EVENTS)]
+
+
+def events_struct(events, cls=Events):
+    """events: list of dicts(component, value, of='y'|'yp', direction=0, terminal=False|True|int)."""
+    ev = cls()
+    ev.n_events = len(events)
+    for k, e in enumerate(events):
+        ev.of_yp[k] = 1 if e.get("of", "y") == "yp" else 0
+        ev.component[k] = int(e["component"])
+        ev.value[k] = float(e["value"])
+        ev.direction[k] = int(np.sign(e.get("direction", 0)))
+        term = e.get("terminal", False)
+        ev.max_events[k] = 0 if term in (False, None) else (1 if term is True else int(term))
+    return ev
+
+
 def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, atol=1e-6,
-                   t_eval=None, nthreads=1, max_steps=0, **options):
+                   t_eval=None, nthreads=1, max_steps=0, events=None, event_cap=16, **options):
     """N instances through the C oracle.  Arrays are AoS on the host: params[N,p], y0[N,n]."""
     pid, n, npar = problem_id(problem)
     params = np.ascontiguousarray(np.atleast_2d(params), dtype=float)
@@ -162,6 +185,16 @@ def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, 
     counters = np.zeros((N, 8), dtype=np.int64)
 
     lib().orc_set_analytic_jac(ctypes.c_int(1 if jac == "analytic" else 0))
+    ev = None
+    if events:
+        ev = events_struct(events)
+        ne = ev.n_events
+        t_events = np.full((N, ne, event_cap), np.nan)
+        y_events = np.full((N, ne, event_cap, n), np.nan)
+        yp_events = np.full((N, ne, event_cap, n), np.nan)
+        n_found = np.zeros((N, ne), dtype=np.int32)
+        lib().orc_set_events(ctypes.byref(ev), ctypes.c_int64(event_cap), _p(t_events), _p(y_events),
+                             _p(yp_events), _p(n_found, ctypes.c_int32))
     rc = lib().orc_solve_ensemble(
         ctypes.c_int(pid), ctypes.c_int(mcode), ctypes.c_int64(N),
         _p(params), _p(y0), _p(yp0), ctypes.c_double(t0), ctypes.c_double(t_bound), _p(atol_v),
@@ -172,6 +205,7 @@ def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, 
         _p(y_final), _p(yp_final), _p(t_final), _p(status, ctypes.c_int32),
         _p(counters, ctypes.c_int64), ctypes.c_int(nthreads))
     lib().orc_set_analytic_jac(ctypes.c_int(0))
+    lib().orc_set_events(None, ctypes.c_int64(0), None, None, None, None)
     if rc != 0:
         raise RuntimeError(f"orc_solve_ensemble returned {rc}")
     out = dict(status=status, t_final=t_final, y_final=y_final, yp_final=yp_final,
@@ -181,6 +215,8 @@ def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, 
     if t_eval is not None:
         out["y_eval"] = ye      # [N, m, n]
         out["yp_eval"] = ype
+    if ev is not None:
+        out.update(t_events=t_events, y_events=y_events, yp_events=yp_events, n_events_found=n_found)
     return out
 
 

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("B200DAE_LIB") or os.path.join(HERE, "libb200dae.so")
 NUM_COUNTERS = 8
 COUNTER_NAMES = ("nfev", "njev", "nlu", "nsolve", "n_accepted", "n_err_rejected",
                  "n_newton_fail", "n_newton_iter")
-ST_FINISHED, ST_TOO_SMALL_STEP, ST_NONFINITE, ST_MAX_STEPS, ST_RUNNING = 0, -1, -2, -3, 1
+ST_FINISHED, ST_TOO_SMALL_STEP, ST_NONFINITE, ST_MAX_STEPS, ST_RUNNING, ST_EVENT = 0, -1, -2, -3, 1, 2
 
 EXPORTS = ("b200dae_version", "b200dae_last_error", "b200dae_num_problems",
            "b200dae_problem_lookup", "b200dae_problem_name", "b200dae_residual",
@@ -62,7 +62,23 @@ class Outputs(ctypes.Structure):
                 ("m", ctypes.c_int64), ("y_eval", ctypes.c_void_p), ("yp_eval", ctypes.c_void_p),
                 ("n_eval_valid", ctypes.c_void_p), ("steps_cap", ctypes.c_int64),
                 ("t_steps", ctypes.c_void_p), ("y_steps", ctypes.c_void_p),
-                ("yp_steps", ctypes.c_void_p), ("n_steps", ctypes.c_void_p)]
+                ("yp_steps", ctypes.c_void_p), ("n_steps", ctypes.c_void_p),
+                ("events", ctypes.c_void_p)]
+
+
+MAX_EVENTS = 4
+
+
+class EventSpec(ctypes.Structure):
+    _fields_ = [("n_events", ctypes.c_int32), ("of_yp", ctypes.c_int32 * MAX_EVENTS),
+                ("component", ctypes.c_int32 * MAX_EVENTS), ("value", ctypes.c_double * MAX_EVENTS),
+                ("direction", ctypes.c_int32 * MAX_EVENTS), ("max_events", ctypes.c_int32 * MAX_EVENTS)]
+
+
+class Events(ctypes.Structure):
+    _fields_ = [("spec", EventSpec), ("cap", ctypes.c_int64), ("t_events", ctypes.c_void_p),
+                ("y_events", ctypes.c_void_p), ("yp_events", ctypes.c_void_p),
+                ("n_found", ctypes.c_void_p)]
 
 
 _lib = None
@@ -110,8 +126,8 @@ def load():
     L.b200dae_fp64_peak_kernel.argtypes = [ctypes.c_int, ctypes.c_int, i64, vp, vp]
     L.b200dae_selftest_fastmath.restype = ctypes.c_int
     L.b200dae_selftest_fastmath.argtypes = [i64, vp, vp, vp, vp]
-    if L.b200dae_version() != 101:
-        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 101")
+    if L.b200dae_version() != 102:
+        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 102")
     _lib = L
     return L
 

@@ -44,6 +44,43 @@ _BDF_KEYS = ("max_step", "first_step", "max_order", "NDF_strategy")
 _IGNORED_NONE_KEYS = ("jac_sparsity", "vectorized")
 
 
+@dataclass(frozen=True)
+class ThresholdEvent:
+    """A device event  g(t, y, y') = x[component] - value,  x = y (``of="y"``) or y' (``of="yp"``),
+    with the attributes of a ``solve_dae`` event function (dae.py:226-247): ``direction`` (> 0:
+    only - to +, < 0: only + to -, 0: both) and ``terminal`` (False, True = stop at the first
+    occurrence, or an int k = stop at the k-th)."""
+    component: int
+    value: float = 0.0
+    of: str = "y"
+    direction: float = 0.0
+    terminal: object = False
+
+
+def _events_struct(events, n):
+    ev = _lib.Events()
+    if len(events) > _lib.MAX_EVENTS:
+        raise ValueError(f"at most {_lib.MAX_EVENTS} device events are supported")
+    ev.spec.n_events = len(events)
+    for k, e in enumerate(events):
+        if isinstance(e, dict):
+            e = ThresholdEvent(**e)
+        if not isinstance(e, ThresholdEvent):
+            raise TypeError("device events are ThresholdEvent instances (or dicts with the same fields): "
+                            "a Python event callable cannot run inside the device step loop")
+        if e.of not in ("y", "yp"):
+            raise ValueError("ThresholdEvent.of must be 'y' or 'yp'")
+        if not 0 <= int(e.component) < n:
+            raise ValueError("ThresholdEvent.component out of range")
+        ev.spec.of_yp[k] = 1 if e.of == "yp" else 0
+        ev.spec.component[k] = int(e.component)
+        ev.spec.value[k] = float(e.value)
+        ev.spec.direction[k] = int(np.sign(e.direction))
+        term = e.terminal
+        ev.spec.max_events[k] = 0 if term in (False, None) else (1 if term is True else int(term))
+    return ev
+
+
 @dataclass
 class BatchedDaeResult:
     """Fields of the reference's DaeResult (dae.py:545-547) with a leading instance axis.
@@ -73,6 +110,10 @@ class BatchedDaeResult:
     y_steps: object = None
     yp_steps: object = None
     n_steps: object = None
+    t_events: object = None        # [N, n_events, cap] (NaN beyond n_events_found)
+    y_events: object = None        # [N, n_events, cap, n]
+    yp_events: object = None
+    n_events_found: object = None  # [N, n_events]
     method: str = ""
     problem: str = ""
     extra: dict = field(default_factory=dict)
@@ -155,7 +196,7 @@ def _warn_extraneous(extraneous):
 def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="Radau",
                       t_eval=None, rtol=1e-3, atol=1e-6, *, device=None, stream=None,
                       record_steps: int = 0, max_steps: int = 0, check_finite: bool = True,
-                      **options) -> BatchedDaeResult:
+                      events=None, event_cap: int = 16, **options) -> BatchedDaeResult:
     """Integrate ``N`` instances of a registered problem from ``t_span[0]`` to ``t_span[1]``.
 
     Parameters mirror ``solve_dae`` (dae.py:115-353); differences:
@@ -166,6 +207,9 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
     device  : torch device     default: current CUDA device
     record_steps : int         > 0: also return up to that many accepted steps per instance
     max_steps : int            > 0: stop every instance after that many accepted steps (status -3)
+    events : list of ThresholdEvent   located on the dense output with Brent's method as in the
+                               reference (dae.py:30-109, 466-490); a terminal event ends the instance
+                               with status 1; up to ``event_cap`` occurrences per event are stored
 
     Returns a ``BatchedDaeResult`` of device tensors (call ``.numpy()`` for host arrays).
     """
@@ -243,6 +287,19 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
             out.t_steps, out.y_steps, out.yp_steps = t_steps.data_ptr(), y_steps.data_ptr(), yp_steps.data_ptr()
             out.n_steps = n_steps.data_ptr()
 
+        ev_struct = t_events = y_events = yp_events = n_found = None
+        if events:
+            ev_struct = _events_struct(list(events), n)
+            ne, cap = ev_struct.spec.n_events, int(event_cap)
+            t_events = torch.full((ne, cap, ld), float("nan"), **f64)
+            y_events = torch.full((ne, cap, n, ld), float("nan"), **f64)
+            yp_events = torch.full((ne, cap, n, ld), float("nan"), **f64)
+            n_found = torch.zeros((ne, ld), **i32)
+            ev_struct.cap = cap
+            ev_struct.t_events, ev_struct.y_events = t_events.data_ptr(), y_events.data_ptr()
+            ev_struct.yp_events, ev_struct.n_found = yp_events.data_ptr(), n_found.data_ptr()
+            out.events = ctypes.addressof(ev_struct)
+
         # ---- options -----------------------------------------------------------------------
         opts = dict(options)
         jac = opts.pop("jac", None)
@@ -307,6 +364,8 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
                                      cu_stream)
         _lib.check(rc)
 
+    if ev_struct is not None:      # device code 2 -> solve_dae's status 1 ("A termination event occurred.")
+        status = torch.where(status == _lib.ST_EVENT, torch.ones_like(status), status)
     res = BatchedDaeResult(
         t_final=t_final, y_final=y_final.t(), yp_final=yp_final.t(), status=status,
         nfev=counters[0], njev=counters[1], nlu=counters[2], nsolve=counters[3],
@@ -322,6 +381,11 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
         res.y_steps = y_steps.permute(2, 1, 0)
         res.yp_steps = yp_steps.permute(2, 1, 0)
         res.n_steps = n_steps
+    if ev_struct is not None:
+        res.t_events = t_events.permute(2, 0, 1)            # [N, ne, cap]
+        res.y_events = y_events.permute(3, 0, 1, 2)         # [N, ne, cap, n]
+        res.yp_events = yp_events.permute(3, 0, 1, 2)
+        res.n_events_found = n_found.t()
     # keep the inputs alive until the caller synchronises
     res.extra["_keepalive"] = (y0_d, yp0_d, p_d)
     return res

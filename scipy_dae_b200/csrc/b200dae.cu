@@ -52,8 +52,29 @@ static int check_common(const ProblemEntry* e, int64_t N, int64_t ld, const doub
     return 0;
 }
 
+static int check_events(const ProblemEntry* e, const b200dae_outputs* out, EventLaunch* ev) {
+    memset(ev, 0, sizeof(*ev));
+    const b200dae_events* s = out->events;
+    if (!s || s->spec.n_events == 0) return 0;
+    if (s->spec.n_events < 0 || s->spec.n_events > B200DAE_MAX_EVENTS)
+        return fail(B200DAE_EINVAL, "need 0 <= n_events <= 4%s", "");
+    for (int k = 0; k < s->spec.n_events; ++k)
+        if (s->spec.component[k] < 0 || s->spec.component[k] >= e->n)
+            return fail(B200DAE_EINVAL, "event component out of range%s", "");
+    if (s->cap <= 0 || !s->t_events || !s->n_found)
+        return fail(B200DAE_EINVAL, "events need cap > 0, t_events and n_found%s", "");
+    ev->spec = s->spec;
+    ev->cap = s->cap;
+    ev->t_events = s->t_events;
+    ev->y_events = s->y_events;
+    ev->yp_events = s->yp_events;
+    ev->n_found = s->n_found;
+    return 0;
+}
+
 static b200dae_outputs normalise(const b200dae_outputs* out) {
     b200dae_outputs o = *out;
+    o.events = nullptr;
     if (o.m == 0) { o.t_eval = nullptr; o.y_eval = nullptr; o.yp_eval = nullptr; }
     if (o.steps_cap == 0) { o.t_steps = nullptr; o.y_steps = nullptr; o.yp_steps = nullptr; }
     return o;
@@ -188,6 +209,8 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
     L.yp0 = yp0;
     L.params = params;
     L.out = normalise(out);
+    rc = check_events(e, out, &L.ev);
+    if (rc) return rc;
     rc = e->radau[s](L, (cudaStream_t)stream);
     if (rc == kErrNoJac)
         return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s' (stages=%lld)", e->name, s);
@@ -240,6 +263,8 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
     L.yp0 = yp0;
     L.params = params;
     L.out = normalise(out);
+    rc = check_events(e, out, &L.ev);
+    if (rc) return rc;
     rc = e->bdf(L, (cudaStream_t)stream);
     if (rc == kErrNoJac)
         return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s'%s", e->name);

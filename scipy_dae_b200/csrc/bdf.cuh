@@ -11,6 +11,7 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/b200dae.h"
+#include "events.cuh"
 #include "fd_jacobian.cuh"
 #include "radau.cuh"   // finite_d, powi
 
@@ -33,6 +34,7 @@ struct BdfLaunch {
     int64_t N, ld;
     const double *y0, *yp0, *params;
     b200dae_outputs out;
+    EventLaunch ev;             // ev.spec.n_events == 0: no events
 };
 
 // change_D (bdf.py:24-29): D[:order+1] = (R @ U).T @ D[:order+1], evaluated as U.T @ (R.T @ D)
@@ -119,6 +121,13 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
         nst = 1;
     }
     if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; njev = 1; }
+    EventState evs;                  // g = event(t0, y0, yp0), dae.py:436
+    for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
+        evs.count[k] = evs.found[k] = 0;
+        evs.g[k] = (k < L.ev.spec.n_events)
+            ? (L.ev.spec.of_yp[k] ? pick<N>(yp, L.ev.spec.component[k]) : pick<N>(y, L.ev.spec.component[k])) - L.ev.spec.value[k]
+            : 0.0;
+    }
 
     double hl = 0.0, min_step = 0.0, h = 0.0, t_new = 0.0, c = 0.0;
 
@@ -270,6 +279,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
 
         // ---- phase C: accepted (bdf.py:359-415) ----------------------------------------------------
         ++n_equal_steps;
+        const double t_prev = t;
         t = t_new;
 #pragma unroll U
         for (int j = 0; j < N; ++j) { y[j] = y_new[j]; yp[j] = yp_new[j]; }
@@ -316,35 +326,69 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             lu_valid = false;
         }
 
-        // t_eval points passed by this step; BdfDenseOutput is built AFTER the rescale with
-        // h = h_abs*direction (bdf.py:417-419, 525-548)
+        // BdfDenseOutput is built AFTER the rescale with h = h_abs*direction and the NEW order
+        // (bdf.py:417-419, 525-548): value and derivative of the Newton interpolant at te
+        const double hh = h_abs * dir;
+        const double t_end = t;                  // the interpolant is anchored at the step end
+        auto dense_all = [&](double te, double* ya, double* ypa) {
+            for (int j = 0; j < N; ++j) { ya[j] = D[j]; ypa[j] = 0.0; }
+            double fact = 1.0, hj = 1.0;
+            for (int jj = 1; jj <= order; ++jj) {
+                fact *= jj;
+                hj *= hh;
+                double fac = 1.0, dfac = 0.0;
+                for (int mm = 0; mm < jj; ++mm) {
+                    fac *= te - (t_end - mm * hh);
+                    double dprod = 1.0;
+                    for (int i = 0; i < jj; ++i)
+                        if (i != mm) dprod *= te - (t_end - i * hh);
+                    dfac += dprod;
+                }
+                const double rden = 1.0 / (fact * hj);
+                for (int j = 0; j < N; ++j) {
+                    ya[j] = fma(D[jj * N + j], fac * rden, ya[j]);
+                    ypa[j] = fma(D[jj * N + j], dfac * rden, ypa[j]);
+                }
+            }
+        };
+        // events on this step's dense output (dae.py:466-490); a terminal one moves the step end
+        bool ev_stop = false;
+        if (L.ev.spec.n_events > 0) {
+            auto dense = [&](double te, int comp, bool of_yp) -> double {
+                double ya[N], ypa[N];
+                dense_all(te, ya, ypa);
+                return of_yp ? ypa[comp] : ya[comp];
+            };
+            auto record = [&](int k, int idx, double tr) {
+                double ya[N], ypa[N];
+                dense_all(tr, ya, ypa);
+                const int64_t row = (int64_t)k * L.ev.cap + idx;
+                L.ev.t_events[row * ld + inst] = tr;
+                for (int j = 0; j < N; ++j) {
+                    if (L.ev.y_events) L.ev.y_events[(row * N + j) * ld + inst] = ya[j];
+                    if (L.ev.yp_events) L.ev.yp_events[(row * N + j) * ld + inst] = ypa[j];
+                }
+            };
+            double gnew[B200DAE_MAX_EVENTS];
+            for (int k = 0; k < B200DAE_MAX_EVENTS; ++k)
+                gnew[k] = (L.ev.spec.of_yp[k] ? pick<N>(yp, L.ev.spec.component[k]) : pick<N>(y, L.ev.spec.component[k])) - L.ev.spec.value[k];
+            double ts = t;
+            if (handle_events(L.ev, evs, t_prev, t, dir, gnew, dense, record, ts)) {
+                ev_stop = true;
+                double ya[N], ypa[N];
+                dense_all(ts, ya, ypa);
+                t = ts;
+                for (int j = 0; j < N; ++j) { y[j] = ya[j]; yp[j] = ypa[j]; }
+            }
+        }
         if (L.out.t_eval != nullptr) {
-            const double hh = h_abs * dir;
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
                 if (!(dir > 0.0 ? te <= t : te >= t)) break;
                 double* ye = L.out.y_eval + ie * N * ld + inst;
                 double* ype = L.out.yp_eval ? L.out.yp_eval + ie * N * ld + inst : nullptr;
                 double ya[N], ypa[N];
-                for (int j = 0; j < N; ++j) { ya[j] = D[j]; ypa[j] = 0.0; }
-                double fact = 1.0, hj = 1.0;
-                for (int jj = 1; jj <= order; ++jj) {
-                    fact *= jj;
-                    hj *= hh;
-                    double fac = 1.0, dfac = 0.0;
-                    for (int mm = 0; mm < jj; ++mm) {
-                        fac *= te - (t - mm * hh);
-                        double dprod = 1.0;
-                        for (int i = 0; i < jj; ++i)
-                            if (i != mm) dprod *= te - (t - i * hh);
-                        dfac += dprod;
-                    }
-                    const double rden = 1.0 / (fact * hj);
-                    for (int j = 0; j < N; ++j) {
-                        ya[j] = fma(D[jj * N + j], fac * rden, ya[j]);
-                        ypa[j] = fma(D[jj * N + j], dfac * rden, ypa[j]);
-                    }
-                }
+                dense_all(te, ya, ypa);
                 for (int j = 0; j < N; ++j) {
                     ye[j * ld] = ya[j];
                     if (ype) ype[j * ld] = ypa[j];
@@ -361,7 +405,8 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             ++nst;
         }
         step_begin = true;
-        if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;
+        if (ev_stop) status = B200DAE_ST_EVENT;
+        else if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;
         else if (L.max_steps > 0 && nacc >= L.max_steps) status = B200DAE_ST_MAX_STEPS;
     }
 
@@ -374,6 +419,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
     L.out.status[inst] = status;
     if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
     if (L.out.n_steps) L.out.n_steps[inst] = nst;
+    for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
     if (L.out.counters) {
         int32_t* cn = L.out.counters + inst;
         cn[B200DAE_CNT_NFEV * ld] = nfev;

@@ -141,6 +141,12 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         nst = 1;
     }
     if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; njev = 1; }
+    EventState evs;                  // g = event(t0, y0, yp0), dae.py:436 (identical in every lane)
+    for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
+        evs.count[k] = evs.found[k] = 0;
+        evs.g[k] = (k < L.ev.spec.n_events)
+            ? g.bcast(L.ev.spec.of_yp[k] ? yp : y, L.ev.spec.component[k]) - L.ev.spec.value[k] : 0.0;
+    }
 
     double hl = 0.0, min_step = 0.0, h = 0.0, t_new = 0.0, c = 0.0;
     double y_predict = 0.0, psi = 0.0, inv_scale = 0.0, y_new = 0.0, yp_new = 0.0, d = 0.0;
@@ -291,6 +297,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
 
         // ---- phase C (bdf.py:359-415) ------------------------------------------------------------
         ++n_equal_steps;
+        const double t_prev = t;
         t = t_new;
         y = y_new;
         yp = yp_new;
@@ -349,33 +356,71 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             lu_valid = false;
         }
 
-        if (L.out.t_eval != nullptr) {                   // BdfDenseOutput, bdf.py:417-419, 525-548
-            const double hh = h_abs * dir;
+        // my component of BdfDenseOutput at te: built AFTER the rescale (bdf.py:417-419, 525-548)
+        const double hh = h_abs * dir;
+        const double t_end = t;
+        auto dense_lane = [&](double te, double& ya, double& ypa) {
+            ya = D[0];
+            ypa = 0.0;
+            double fact = 1.0, hj = 1.0;
+#pragma unroll
+            for (int jj = 1; jj < kBdfQ; ++jj) {
+                fact *= jj;
+                hj *= hh;
+                double fc = 1.0, dfac = 0.0;
+#pragma unroll
+                for (int mm = 0; mm < jj; ++mm) {
+                    fc *= te - (t_end - mm * hh);
+                    double dprod = 1.0;
+#pragma unroll
+                    for (int i = 0; i < jj; ++i)
+                        if (i != mm) dprod *= te - (t_end - i * hh);
+                    dfac += dprod;
+                }
+                const double rden = 1.0 / (fact * hj);
+                if (jj <= order) {
+                    ya = fma(D[jj], fc * rden, ya);
+                    ypa = fma(D[jj], dfac * rden, ypa);
+                }
+            }
+        };
+        // events on this step's dense output (dae.py:466-490); a terminal one moves the step end
+        bool ev_stop = false;
+        if (L.ev.spec.n_events > 0) {
+            auto dense = [&](double te, int comp, bool of_yp) -> double {
+                double av, bv;
+                dense_lane(te, av, bv);
+                return g.bcast(of_yp ? bv : av, comp);
+            };
+            auto record = [&](int k, int idx, double tr) {
+                double av, bv;
+                dense_lane(tr, av, bv);
+                const int64_t row = (int64_t)k * L.ev.cap + idx;
+                if (lane == 0) L.ev.t_events[row * ld + inst] = tr;
+                if (act) {
+                    if (L.ev.y_events) L.ev.y_events[(row * N + lane) * ld + inst] = av;
+                    if (L.ev.yp_events) L.ev.yp_events[(row * N + lane) * ld + inst] = bv;
+                }
+            };
+            double gnew[B200DAE_MAX_EVENTS];
+            for (int k = 0; k < B200DAE_MAX_EVENTS; ++k)
+                gnew[k] = g.bcast(L.ev.spec.of_yp[k] ? yp : y, L.ev.spec.component[k]) - L.ev.spec.value[k];
+            double ts = t;
+            if (handle_events(L.ev, evs, t_prev, t, dir, gnew, dense, record, ts)) {
+                ev_stop = true;
+                double av, bv;
+                dense_lane(ts, av, bv);
+                t = ts;
+                y = av;
+                yp = bv;
+            }
+        }
+        if (L.out.t_eval != nullptr) {
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
                 if (!(dir > 0.0 ? te <= t : te >= t)) break;
-                double ya = D[0], ypa = 0.0;
-                double fact = 1.0, hj = 1.0;
-#pragma unroll
-                for (int jj = 1; jj < kBdfQ; ++jj) {
-                    fact *= jj;
-                    hj *= hh;
-                    double fc = 1.0, dfac = 0.0;
-#pragma unroll
-                    for (int mm = 0; mm < jj; ++mm) {
-                        fc *= te - (t - mm * hh);
-                        double dprod = 1.0;
-#pragma unroll
-                        for (int i = 0; i < jj; ++i)
-                            if (i != mm) dprod *= te - (t - i * hh);
-                        dfac += dprod;
-                    }
-                    const double rden = 1.0 / (fact * hj);
-                    if (jj <= order) {
-                        ya = fma(D[jj], fc * rden, ya);
-                        ypa = fma(D[jj], dfac * rden, ypa);
-                    }
-                }
+                double ya, ypa;
+                dense_lane(te, ya, ypa);
                 if (act) {
                     L.out.y_eval[(ie * N + lane) * ld + inst] = ya;
                     if (L.out.yp_eval) L.out.yp_eval[(ie * N + lane) * ld + inst] = ypa;
@@ -392,7 +437,8 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             ++nst;
         }
         step_begin = true;
-        if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;
+        if (ev_stop) status = B200DAE_ST_EVENT;
+        else if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;
         else if (L.max_steps > 0 && nacc >= L.max_steps) status = B200DAE_ST_MAX_STEPS;
     }
 
@@ -405,6 +451,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         L.out.status[inst] = status;
         if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
         if (L.out.n_steps) L.out.n_steps[inst] = nst;
+        for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
         if (L.out.counters) {
             int32_t* cn = L.out.counters + inst;
             cn[B200DAE_CNT_NFEV * ld] = nfev;

@@ -119,7 +119,7 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
     constexpr int T = Tn::kThreads;
     const int64_t blocks = (L.N + T - 1) / T;
     const bool lean = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_eval == nullptr &&
-                      L.out.t_steps == nullptr;
+                      L.out.t_steps == nullptr && L.ev.spec.n_events == 0;
     bool done = false;
     if constexpr (kJacOk && Regime<P::N>::kReg) {
         if (L.analytic_jac) {

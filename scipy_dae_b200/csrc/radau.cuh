@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include "../../include/b200dae.h"
 #include "fastmath.cuh"
+#include "events.cuh"
 #include "fd_jacobian.cuh"
 
 namespace b200dae {
@@ -38,6 +39,7 @@ struct RadauLaunch {
     int64_t N, ld;
     const double *y0, *yp0, *params;
     b200dae_outputs out;
+    EventLaunch ev;             // ev.spec.n_events == 0: no events
 };
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
@@ -142,6 +144,16 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         nst = 1;
     }
     if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; need_jac = false; njev = 1; }  // base.py:376-381
+    EventState evs;                  // g = event(t0, y0, yp0), dae.py:436
+    if (!kLean) {
+#pragma unroll
+        for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
+            evs.count[k] = evs.found[k] = 0;
+            evs.g[k] = (k < L.ev.spec.n_events)
+                ? (L.ev.spec.of_yp[k] ? pick<N>(yp, L.ev.spec.component[k]) : pick<N>(y, L.ev.spec.component[k])) - L.ev.spec.value[k]
+                : 0.0;
+        }
+    }
 
     // per-step locals that survive across attempts of the same step
     double hl = 0.0, hl_old = 0.0, errl_old = 0.0, min_step = 0.0, factor = 0.0;
@@ -470,12 +482,61 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         h_old = h;
         have_sol = true;
 
+        // events on this step's dense output (dae.py:466-490); a terminal one moves the step end
+        double t_lim = t_new;
+        bool ev_stop = false;
+        double y_stop[N], yp_stop[N];
+        if (!kLean && L.ev.spec.n_events > 0) {
+            const double rho_e = fast_rcp(h);
+            auto dense_all = [&](double te, double* ya, double* ypa) {     // RadauDenseOutput, radau.py:681-699
+                const double x = (te - t) * rho_e;
+                double pw[S], dpw[S];
+                double xk = 1.0;
+#pragma unroll
+                for (int k = 0; k < S; ++k) { dpw[k] = (k + 1) * rho_e * xk; xk *= x; pw[k] = xk; }
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    double a = 0.0, b = 0.0;
+#pragma unroll
+                    for (int k = 0; k < S; ++k) { a = fma(ZP[j * S + k], pw[k], a); b = fma(ZP[j * S + k], dpw[k], b); }
+                    ya[j] = a + y[j];
+                    ypa[j] = b;
+                }
+            };
+            auto dense = [&](double te, int comp, bool of_yp) -> double {
+                double ya[N], ypa[N];
+                dense_all(te, ya, ypa);
+                return of_yp ? pick<N>(ypa, comp) : pick<N>(ya, comp);
+            };
+            auto record = [&](int k, int idx, double tr) {
+                double ya[N], ypa[N];
+                dense_all(tr, ya, ypa);
+                const int64_t row = (int64_t)k * L.ev.cap + idx;
+                L.ev.t_events[row * ld + inst] = tr;
+#pragma unroll U
+                for (int j = 0; j < N; ++j) {
+                    if (L.ev.y_events) L.ev.y_events[(row * N + j) * ld + inst] = ya[j];
+                    if (L.ev.yp_events) L.ev.yp_events[(row * N + j) * ld + inst] = ypa[j];
+                }
+            };
+            double gnew[B200DAE_MAX_EVENTS];
+#pragma unroll
+            for (int k = 0; k < B200DAE_MAX_EVENTS; ++k)
+                gnew[k] = (L.ev.spec.of_yp[k] ? pick<N>(Yp[S - 1], L.ev.spec.component[k])
+                                              : pick<N>(Y[S - 1], L.ev.spec.component[k])) - L.ev.spec.value[k];
+            double ts = t_new;
+            if (handle_events(L.ev, evs, t, t_new, dir, gnew, dense, record, ts)) {
+                ev_stop = true;
+                t_lim = ts;
+                dense_all(ts, y_stop, yp_stop);
+            }
+        }
         // t_eval points passed by this step (dae.py:496-515; RadauDenseOutput radau.py:681-699)
         if (!kLean && L.out.t_eval != nullptr) {
             const double rho = fast_rcp(h);
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
-                if (!(dir > 0.0 ? te <= t_new : te >= t_new)) break;
+                if (!(dir > 0.0 ? te <= t_lim : te >= t_lim)) break;
                 const double x = (te - t) * rho;
                 double pw[S], dpw[S];
                 double xk = 1.0;
@@ -495,9 +556,12 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
             }
         }
         // commit
-        t = t_new;
+        t = t_lim;
 #pragma unroll U
-        for (int j = 0; j < N; ++j) { y[j] = Y[S - 1][j]; yp[j] = Yp[S - 1][j]; }
+        for (int j = 0; j < N; ++j) {
+            y[j] = ev_stop ? y_stop[j] : Y[S - 1][j];
+            yp[j] = ev_stop ? yp_stop[j] : Yp[S - 1][j];
+        }
         ++nacc;
         if (!kLean && L.out.t_steps != nullptr && nst < L.out.steps_cap) {
             L.out.t_steps[(int64_t)nst * ld + inst] = t;
@@ -509,7 +573,8 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
             ++nst;
         }
         step_begin = true;
-        if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;            // base.py:389-390
+        if (ev_stop) status = B200DAE_ST_EVENT;                                    // dae.py:484-487
+        else if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;       // base.py:389-390
         else if (L.max_steps > 0 && nacc >= L.max_steps) status = B200DAE_ST_MAX_STEPS;
         // the reference still evaluates the Jacobian after its last step (radau.py:628-630)
         if (status != B200DAE_ST_RUNNING && need_jac) ++njev;
@@ -525,6 +590,9 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     L.out.status[inst] = status;
     if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
     if (L.out.n_steps) L.out.n_steps[inst] = nst;
+    if (!kLean) {
+        for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
+    }
     if (L.out.counters) {
         int32_t* c = L.out.counters + inst;
         c[B200DAE_CNT_NFEV * ld] = nfev;

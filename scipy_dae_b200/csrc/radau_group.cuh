@@ -246,6 +246,12 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         nst = 1;
     }
     if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; need_jac = false; njev = 1; }
+    EventState evs;                  // g = event(t0, y0, yp0), dae.py:436 (identical in every lane)
+    for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
+        evs.count[k] = evs.found[k] = 0;
+        evs.g[k] = (k < L.ev.spec.n_events)
+            ? g.bcast(L.ev.spec.of_yp[k] ? yp : y, L.ev.spec.component[k]) - L.ev.spec.value[k] : 0.0;
+    }
 
     double hl = 0.0, hl_old = 0.0, errl_old = 0.0, min_step = 0.0, factor = 0.0;
     double h = 0.0, t_new = 0.0;
@@ -529,29 +535,65 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         h_old = h;
         have_sol = true;
 
+        // my component of RadauDenseOutput at te (radau.py:681-699)
+        const double rho = fast_rcp(h);
+        auto dense_lane = [&](double te, double& av, double& bv) {
+            const double x = (te - t) * rho;
+            double xk = 1.0;
+            av = 0.0; bv = 0.0;
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                bv = fma(ZP[k], (k + 1) * rho * xk, bv);
+                xk *= x;
+                av = fma(ZP[k], xk, av);
+            }
+            av += y;
+        };
+        // events on this step's dense output (dae.py:466-490); a terminal one moves the step end
+        double t_lim = t_new, y_stop = 0.0, yp_stop = 0.0;
+        bool ev_stop = false;
+        if (L.ev.spec.n_events > 0) {
+            auto dense = [&](double te, int comp, bool of_yp) -> double {
+                double av, bv;
+                dense_lane(te, av, bv);
+                return g.bcast(of_yp ? bv : av, comp);
+            };
+            auto record = [&](int k, int idx, double tr) {
+                double av, bv;
+                dense_lane(tr, av, bv);
+                const int64_t row = (int64_t)k * L.ev.cap + idx;
+                if (lane == 0) L.ev.t_events[row * ld + inst] = tr;
+                if (act) {
+                    if (L.ev.y_events) L.ev.y_events[(row * N + lane) * ld + inst] = av;
+                    if (L.ev.yp_events) L.ev.yp_events[(row * N + lane) * ld + inst] = bv;
+                }
+            };
+            double gnew[B200DAE_MAX_EVENTS];
+            for (int k = 0; k < B200DAE_MAX_EVENTS; ++k)
+                gnew[k] = g.bcast(L.ev.spec.of_yp[k] ? Yp[S - 1] : Y[S - 1], L.ev.spec.component[k]) - L.ev.spec.value[k];
+            double ts = t_new;
+            if (handle_events(L.ev, evs, t, t_new, dir, gnew, dense, record, ts)) {
+                ev_stop = true;
+                t_lim = ts;
+                dense_lane(ts, y_stop, yp_stop);
+            }
+        }
         if (L.out.t_eval != nullptr) {
-            const double rho = fast_rcp(h);
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
-                if (!(dir > 0.0 ? te <= t_new : te >= t_new)) break;
-                const double x = (te - t) * rho;
-                double xk = 1.0, av = 0.0, bv = 0.0;
-#pragma unroll
-                for (int k = 0; k < S; ++k) {
-                    bv = fma(ZP[k], (k + 1) * rho * xk, bv);
-                    xk *= x;
-                    av = fma(ZP[k], xk, av);
-                }
+                if (!(dir > 0.0 ? te <= t_lim : te >= t_lim)) break;
+                double av, bv;
+                dense_lane(te, av, bv);
                 if (act) {
-                    L.out.y_eval[(ie * N + lane) * ld + inst] = av + y;
+                    L.out.y_eval[(ie * N + lane) * ld + inst] = av;
                     if (L.out.yp_eval) L.out.yp_eval[(ie * N + lane) * ld + inst] = bv;
                 }
                 ++ie;
             }
         }
-        t = t_new;
-        y = Y[S - 1];
-        yp = Yp[S - 1];
+        t = t_lim;
+        y = ev_stop ? y_stop : Y[S - 1];
+        yp = ev_stop ? yp_stop : Yp[S - 1];
         ++nacc;
         if (L.out.t_steps != nullptr && nst < L.out.steps_cap) {
             if (lane == 0) L.out.t_steps[(int64_t)nst * ld + inst] = t;
@@ -562,7 +604,8 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
             ++nst;
         }
         step_begin = true;
-        if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;
+        if (ev_stop) status = B200DAE_ST_EVENT;
+        else if (dir * (t - L.t_bound) >= 0.0) status = B200DAE_ST_FINISHED;
         else if (L.max_steps > 0 && nacc >= L.max_steps) status = B200DAE_ST_MAX_STEPS;
         if (status != B200DAE_ST_RUNNING && need_jac) ++njev;
     }
@@ -577,6 +620,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         L.out.status[inst] = status;
         if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
         if (L.out.n_steps) L.out.n_steps[inst] = nst;
+        for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
         if (L.out.counters) {
             int32_t* c = L.out.counters + inst;
             c[B200DAE_CNT_NFEV * ld] = nfev;

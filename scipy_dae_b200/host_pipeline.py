@@ -61,21 +61,64 @@ def _as_host(x, name):
     return t.contiguous()
 
 
+def _enqueue(prob, t_span, h_y0, h_yp0, h_p, method, rtol, atol, device, bounds, streams, out,
+             check_finite, options):
+    """Queue the whole pipeline (no host synchronisation): per chunk, on its stream, H2D ->
+    relayout -> integrator kernel -> relayout -> D2H.  Returns the device flag `inputs finite`
+    (or None) and the tensors that must outlive the queued work."""
+    main = torch.cuda.current_stream(device)
+    for s in streams:
+        s.wait_stream(main)
+    flags, keep = [], []
+    for c in range(len(bounds) - 1):
+        lo, hi = int(bounds[c]), int(bounds[c + 1])
+        if hi <= lo:
+            continue
+        s = streams[c % len(streams)]
+        with torch.cuda.stream(s):
+            r = solve_dae_batched(prob, t_span, h_y0[lo:hi], h_yp0[lo:hi], h_p[lo:hi], method=method,
+                                  rtol=rtol, atol=atol, device=device, stream=s, check_finite=False,
+                                  **options)
+            if check_finite:
+                yd, ypd, _ = r.extra["_keepalive"]
+                flags.append(torch.isfinite(yd).all() & torch.isfinite(ypd).all())
+            out.y_final[lo:hi].copy_(r.y_final.contiguous(), non_blocking=True)
+            out.yp_final[lo:hi].copy_(r.yp_final.contiguous(), non_blocking=True)
+            out.t_final[lo:hi].copy_(r.t_final, non_blocking=True)
+            out.status[lo:hi].copy_(r.status, non_blocking=True)
+            cnt = torch.stack([getattr(r, k) for k in _COUNTERS], dim=1)
+            out.counters[lo:hi].copy_(cnt, non_blocking=True)
+            keep.append(r)
+    for s in streams:
+        main.wait_stream(s)
+    ok = torch.stack(flags).all() if flags else None
+    return ok, keep
+
+
+_GRAPHS: dict = {}
+
+
 def solve_dae_batched_host(problem, t_span, y0, yp0, params, method="Radau", rtol=1e-3, atol=1e-6, *,
                            device=None, chunks: int = 8, n_streams: int = 3,
                            out: Optional[HostResultBuffers] = None, check_finite: bool = True,
-                           **options) -> BatchedDaeResult:
+                           use_graph: bool = False, **options) -> BatchedDaeResult:
     """Integrate ``N`` instances held in host memory; returns host (pinned) tensors.
 
     y0, yp0 : [N, n], params : [N, p]   NumPy arrays or CPU tensors (pinned memory makes the
                                         copies asynchronous)
     chunks, n_streams                   pipeline shape; ``chunks=1`` is the unpipelined call
     out                                 reusable result buffers (``alloc_host_result``)
+    use_graph                           capture the whole pipeline (copies, relayouts, kernels) in
+                                        ONE CUDA graph, cached for this set of pinned input /
+                                        output buffers and options; later calls with the same
+                                        buffers replay it with a single launch, so host-side
+                                        jitter cannot stall the queue between chunks.  Needs
+                                        pinned ``y0, yp0, params`` tensors and ``out``.
 
-    ``t_eval`` / ``record_steps`` are not offered here (their outputs are ``m`` times larger than
-    the inputs; use ``solve_dae_batched`` and copy what is needed).
+    ``t_eval`` / ``record_steps`` / ``events`` are not offered here (their outputs are much larger
+    than the inputs; use ``solve_dae_batched`` and copy what is needed).
     """
-    for k in ("t_eval", "record_steps"):
+    for k in ("t_eval", "record_steps", "events"):
         if options.get(k):
             raise NotImplementedError(f"`{k}` is not available on the host pipeline; use solve_dae_batched")
     if not torch.cuda.is_available():
@@ -89,43 +132,43 @@ def solve_dae_batched_host(problem, t_span, y0, yp0, params, method="Radau", rto
         raise ValueError("`y0` and `yp0` must be of same shape.")
     if h_y0.shape[1] != n or h_p.shape != (N, npar):
         raise ValueError(f"expected y0/yp0 of shape ({N}, {n}) and params of shape ({N}, {npar})")
+    if use_graph and (out is None or not all(t.is_pinned() for t in (h_p, h_y0, h_yp0))):
+        raise ValueError("use_graph=True needs pinned y0 / yp0 / params tensors and `out` buffers "
+                         "(a CUDA graph replays fixed addresses)")
     if out is None:
         out = alloc_host_result(N, n)
     chunks = max(1, min(int(chunks), N)) if N > 0 else 1
     bounds = np.linspace(0, N, chunks + 1).astype(np.int64)
+    nstr = max(1, min(n_streams, chunks))
     with torch.cuda.device(device):
         main = torch.cuda.current_stream(device)
-        streams = [torch.cuda.Stream(device=device) for _ in range(max(1, min(n_streams, chunks)))]
-        for s in streams:
-            s.wait_stream(main)
-        flags = []
-        for c in range(chunks):
-            lo, hi = int(bounds[c]), int(bounds[c + 1])
-            if hi <= lo:
-                continue
-            s = streams[c % len(streams)]
-            with torch.cuda.stream(s):
-                r = solve_dae_batched(prob, t_span, h_y0[lo:hi], h_yp0[lo:hi], h_p[lo:hi], method=method,
-                                      rtol=rtol, atol=atol, device=device, stream=s, check_finite=False,
-                                      **options)
-                if check_finite:
-                    yd, ypd, _ = r.extra["_keepalive"]
-                    flags.append(torch.isfinite(yd).all() & torch.isfinite(ypd).all())
-                out.y_final[lo:hi].copy_(r.y_final.contiguous(), non_blocking=True)
-                out.yp_final[lo:hi].copy_(r.yp_final.contiguous(), non_blocking=True)
-                out.t_final[lo:hi].copy_(r.t_final, non_blocking=True)
-                out.status[lo:hi].copy_(r.status, non_blocking=True)
-                cnt = torch.stack([getattr(r, k) for k in _COUNTERS], dim=1)
-                out.counters[lo:hi].copy_(cnt, non_blocking=True)
-        ok = None
-        if flags:
-            with torch.cuda.stream(streams[0]):
-                for s in streams[1:]:
-                    streams[0].wait_stream(s)
-                ok = torch.stack(flags).all()
-        for s in streams:
-            main.wait_stream(s)
-        main.synchronize()
+        if not use_graph:
+            streams = [torch.cuda.Stream(device=device) for _ in range(nstr)]
+            ok, keep = _enqueue(prob, t_span, h_y0, h_yp0, h_p, method, rtol, atol, device, bounds,
+                                streams, out, check_finite, options)
+            main.synchronize()
+        else:
+            key = (prob.name, tuple(map(float, t_span)), method, float(rtol), np.asarray(atol, dtype=float).tobytes(),
+                   str(device), chunks, nstr, check_finite, tuple(sorted((k, repr(v)) for k, v in options.items())),
+                   h_y0.data_ptr(), h_yp0.data_ptr(), h_p.data_ptr(), N,
+                   out.y_final.data_ptr(), out.yp_final.data_ptr(), out.t_final.data_ptr(),
+                   out.status.data_ptr(), out.counters.data_ptr())
+            entry = _GRAPHS.get(key)
+            if entry is None:
+                streams = [torch.cuda.Stream(device=device) for _ in range(nstr)]
+                # one eager pass first: warms the allocator and any per-kernel attribute set-up
+                _enqueue(prob, t_span, h_y0, h_yp0, h_p, method, rtol, atol, device, bounds, streams, out,
+                         check_finite, options)
+                main.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    ok, keep = _enqueue(prob, t_span, h_y0, h_yp0, h_p, method, rtol, atol, device, bounds,
+                                        streams, out, check_finite, options)
+                entry = (graph, ok, keep, streams, (h_y0, h_yp0, h_p, out))
+                _GRAPHS[key] = entry
+            graph, ok = entry[0], entry[1]
+            graph.replay()
+            torch.cuda.current_stream(device).synchronize()
         if ok is not None and not bool(ok):
             raise ValueError("All components of the initial state `y0` / `yp0` must be finite.")
     cn = out.counters
@@ -133,4 +176,4 @@ def solve_dae_batched_host(problem, t_span, y0, yp0, params, method="Radau", rto
         t_final=out.t_final, y_final=out.y_final, yp_final=out.yp_final, status=out.status,
         nfev=cn[:, 0], njev=cn[:, 1], nlu=cn[:, 2], nsolve=cn[:, 3], n_accepted=cn[:, 4],
         n_err_rejected=cn[:, 5], n_newton_fail=cn[:, 6], n_newton_iter=cn[:, 7],
-        method=method, problem=prob.name, extra={"chunks": chunks, "streams": len(streams)})
+        method=method, problem=prob.name, extra={"chunks": chunks, "streams": nstr, "graph": bool(use_graph)})

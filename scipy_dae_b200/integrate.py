@@ -41,9 +41,11 @@ def solve_dae(fun, t_span, y0=None, yp0=None, method="Radau", t_eval=None, dense
         raise TypeError("scipy_dae_b200.solve_dae integrates residuals that are registered as CUDA "
                         "device functors: pass a problem name or Problem (see scipy_dae_b200.problems); "
                         "a Python callable cannot run inside the device step loop.")
-    if dense_output or events is not None:
-        raise NotImplementedError("dense_output=True and events are not on the device path yet "
-                                  "(SURVEY.md §8f row N3); use t_eval.")
+    if dense_output:
+        raise NotImplementedError("dense_output=True (a DaeSolution of per-step interpolants) is not on the "
+                                  "device path; use t_eval.")
+    if events is not None and not isinstance(events, (list, tuple)):
+        events = [events]                                                           # dae.py:427 prepare_events
     prob = get_problem(fun)
     if args is not None:
         try:
@@ -64,7 +66,7 @@ def solve_dae(fun, t_span, y0=None, yp0=None, method="Radau", t_eval=None, dense
     cap = 0 if t_eval is not None else int(max_steps_recorded)
     while True:
         r = solve_dae_batched(prob, t_span, y0b, yp0b, params[None, :], method=method, t_eval=t_eval,
-                              device=device, record_steps=cap, **options).numpy()
+                              device=device, record_steps=cap, events=events, **options).numpy()
         if t_eval is not None or r.n_steps[0] < cap or r.n_accepted[0] + 1 <= cap:
             break
         cap *= 4       # the step trace overflowed: rerun with a larger trace
@@ -78,7 +80,13 @@ def solve_dae(fun, t_span, y0=None, yp0=None, method="Radau", t_eval=None, dense
         t, y, yp = r.t[:k], r.y[0, :, :k], r.yp[0, :, :k]
         if k == 0:
             t, y, yp = [], [], []                                                   # dae.py:523-535
-    return DaeResult(t=t, y=y, yp=yp, sol=None, t_events=None, y_events=None, yp_events=None,
+    t_ev = y_ev = yp_ev = None
+    if events:                       # lists per event, like dae.py:537-540
+        nf = np.minimum(r.n_events_found[0], r.t_events.shape[2])
+        t_ev = [r.t_events[0, k, :nf[k]] for k in range(len(events))]
+        y_ev = [r.y_events[0, k, :nf[k]] for k in range(len(events))]
+        yp_ev = [r.yp_events[0, k, :nf[k]] for k in range(len(events))]
+    return DaeResult(t=t, y=y, yp=yp, sol=None, t_events=t_ev, y_events=y_ev, yp_events=yp_ev,
                      nfev=int(r.nfev[0]), njev=int(r.njev[0]), nlu=int(r.nlu[0]),
                      status=-1 if status < 0 else status,
                      message=MESSAGES.get(status, ""), success=status >= 0,

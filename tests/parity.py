@@ -113,3 +113,22 @@ def compare(res, ref, meta, case, atol_vec, have_eval, eval_axes_ref="nm", eval_
         if not w <= slack:
             fails.append(f"y(t_eval) outside band: worst ratio {w:.3g} (allowed {slack})")
     return fails
+
+
+def check_events(t_events, y_events, n_found, t_final, g, meta, rel=1e-5):
+    """Event parity: the same occurrences per event as the reference, event times within `rel`
+    (they inherit the step-sequence drift; measured 1e-8 .. 7e-6), event states
+    within the state band, and a terminal event ends the integration at the same time."""
+    rtol = meta["rtol"]
+    atol = np.asarray(meta["atol"], dtype=float)
+    assert np.array_equal(np.asarray(n_found), g["n_events_found"]), (n_found, g["n_events_found"])
+    ok = np.isfinite(g["t_events"])
+    assert np.array_equal(np.isfinite(t_events), ok)
+    if ok.any():
+        a, b = np.asarray(t_events)[ok], g["t_events"][ok]
+        assert (np.abs(a - b) <= rel * np.abs(b) + 1e-300).all(), np.abs(a - b).max()
+        ya, yb = np.asarray(y_events)[ok], g["y_events"][ok]
+        # the event component itself is pinned to the threshold; the others move with |dy/dt| * dt
+        band = np.maximum(10 * rtol * np.abs(yb), atol) + rel * np.abs(yb) * 10
+        assert (np.abs(ya - yb) <= 4 * band).all(), (np.abs(ya - yb) / band).max()
+    assert (np.abs(np.asarray(t_final) - g["t_final"]) <= rel * np.abs(g["t_final"])).all()

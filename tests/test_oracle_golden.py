@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import golden_cases, load_golden
-from parity import compare
+from parity import check_events, compare
 
 
 @pytest.mark.parametrize("case", golden_cases())
@@ -20,6 +20,8 @@ def test_oracle_matches_reference_golden(case, oracle):
     assert not fails, "; ".join(fails)
     if te is not None:
         assert np.array_equal(res["n_eval_valid"], g["n_eval_valid"])
+    if "events" in meta["options"]:
+        check_events(res["t_events"], res["y_events"], res["n_events_found"], res["t_final"], g, meta)
 
 
 def test_exact_counters_on_headline_config(oracle):
