@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--jac", default="fd", choices=["fd", "analytic"],
                     help="fd = finite-difference Jacobian (the headline, jac=None in the reference); "
                          "analytic = the functor's analytic Jacobians (a `jac` callable in the reference)")
+    ap.add_argument("--t-eval-points", type=int, default=64,
+                    help="also time the ensemble with dense output at this many t_eval points (0 = skip)")
     ap.add_argument("--e2e-no-graph", action="store_true",
                     help="queue the host pipeline eagerly instead of replaying its CUDA graph")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline chunks of the host-facing call")
@@ -390,6 +392,42 @@ def main():
     torch.cuda.synchronize(dev)
     fp64_peak_tflops = 148 * 8 * 256 * iters * 16 / (a.elapsed_time(b) * 1e-3) / 1e12
 
+    # ---- secondary: the same ensemble WITH t_eval output (the HBM-heavier mode) --------
+    te_mode = None
+    if args.t_eval_points > 0 and rank == 0:
+        m = int(args.t_eval_points)
+        te = torch.from_numpy(np.logspace(-6, 7, m)).to(dev)
+        y_eval = torch.empty((m, n, Nper), **f64)
+        yp_eval = torch.empty((m, n, Nper), **f64)
+        nev = torch.empty((Nper,), dtype=torch.int32, device=dev)
+        out2 = _lib.Outputs()
+        out2.y_final, out2.yp_final, out2.t_final = y_final.data_ptr(), yp_final.data_ptr(), t_final.data_ptr()
+        out2.status, out2.counters = status.data_ptr(), counters.data_ptr()
+        out2.t_eval, out2.m = te.data_ptr(), m
+        out2.y_eval, out2.yp_eval, out2.n_eval_valid = y_eval.data_ptr(), yp_eval.data_ptr(), nev.data_ptr()
+
+        def launch_te():
+            _lib.check(L.b200dae_solve_radau(pid, Nper, Nper, d_y0.data_ptr(), d_yp0.data_ptr(), d_p.data_ptr(),
+                                             WORKLOAD["t_span"][0], WORKLOAD["t_span"][1], atol, ctypes.byref(ro),
+                                             ctypes.byref(tb), ctypes.byref(out2), ctypes.c_void_p(stream.cuda_stream)))
+        launch_te()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(2):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); launch_te(); b.record(stream)
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        assert bool((nev == m).all())
+        ms = float(np.mean(ts))
+        nbytes = Nper * (compulsory_bytes(n, npar) + 16 * n * m)
+        te_mode = {"t_eval_points": m, "ms_per_launch": ms, "solves_per_s": Nper / (ms * 1e-3),
+                   "hbm_bytes_per_launch": nbytes, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
+                   "note": "same ensemble with dense output at m log-spaced points written to HBM "
+                           "(y and yp, [m][n][N] SoA); full-options kernel variant"}
+        del y_eval, yp_eval
+
     # ---- max over ranks ----------------------------------------------------------------------------------
     t_all = torch.tensor([total_ms, e2e_total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -417,6 +455,8 @@ def main():
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        if te_mode is not None:
+            te_mode["hbm_frac"] = te_mode["hbm_gbs"] / hbm_peak
         ach_tflops = flops_per_launch / kernel_s / 1e12
         ach_gbs = bytes_per_launch / kernel_s / 1e9
         line = {
@@ -447,6 +487,7 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             },
             "work_per_solve": {k: float(v) / Nper for k, v in cnt.items()},
+            "t_eval_mode": te_mode,
             "gather_ms": gather_ms,
         }
         if not args.no_cpu_baseline and world == 1:
