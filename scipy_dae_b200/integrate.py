@@ -14,6 +14,40 @@ from .batched import MESSAGES, METHODS, solve_dae_batched
 from .problems import Problem, get_problem
 
 
+class ReplayDaeSolution:
+    """Continuous solution ``sol(t) -> (y, yp)`` with the call signature of the reference's
+    ``DaeSolution`` (common.py:9-126).
+
+    The reference keeps one interpolant object per step.  The device step loop is deterministic,
+    so the same piecewise interpolant is obtained by replaying the integration with the requested
+    times as ``t_eval`` (dae.py:496-515 evaluates exactly the per-step dense output there; a time
+    equal to a step end belongs to the earlier step, as in ``DaeSolution``).  Each call costs one
+    launch; times outside ``[t_min, t_max]`` are rejected instead of extrapolated.
+    """
+
+    def __init__(self, solve, t_span, t_reached, n):
+        self._solve, self.n = solve, n
+        t0, t1 = float(t_span[0]), float(t_reached)
+        self.ascending = t1 >= t0
+        self.t_min, self.t_max = (t0, t1) if self.ascending else (t1, t0)
+
+    def __call__(self, t):
+        t = np.asarray(t, dtype=float)
+        if t.ndim > 1:
+            raise ValueError("`t` must be a float or a 1-D array.")
+        ts = np.atleast_1d(t)
+        if np.any(ts < self.t_min) or np.any(ts > self.t_max):
+            raise ValueError(f"`t` must lie in [{self.t_min}, {self.t_max}] (no extrapolation on the device path)")
+        uniq, inv = np.unique(ts, return_inverse=True)
+        order = uniq if self.ascending else uniq[::-1]
+        r = self._solve(order)
+        y, yp = r.y[0], r.yp[0]                                  # [n, m] in integration order
+        if not self.ascending:
+            y, yp = y[:, ::-1], yp[:, ::-1]
+        y, yp = y[:, inv], yp[:, inv]
+        return (y[:, 0], yp[:, 0]) if t.ndim == 0 else (y, yp)
+
+
 class DaeResult(dict):
     """Same fields as the reference's DaeResult (an OptimizeResult, dae.py:26-27,545-547)."""
     __getattr__ = dict.get
@@ -41,9 +75,6 @@ def solve_dae(fun, t_span, y0=None, yp0=None, method="Radau", t_eval=None, dense
         raise TypeError("scipy_dae_b200.solve_dae integrates residuals that are registered as CUDA "
                         "device functors: pass a problem name or Problem (see scipy_dae_b200.problems); "
                         "a Python callable cannot run inside the device step loop.")
-    if dense_output:
-        raise NotImplementedError("dense_output=True (a DaeSolution of per-step interpolants) is not on the "
-                                  "device path; use t_eval.")
     if events is not None and not isinstance(events, (list, tuple)):
         events = [events]                                                           # dae.py:427 prepare_events
     prob = get_problem(fun)
@@ -86,7 +117,13 @@ def solve_dae(fun, t_span, y0=None, yp0=None, method="Radau", t_eval=None, dense
         t_ev = [r.t_events[0, k, :nf[k]] for k in range(len(events))]
         y_ev = [r.y_events[0, k, :nf[k]] for k in range(len(events))]
         yp_ev = [r.yp_events[0, k, :nf[k]] for k in range(len(events))]
-    return DaeResult(t=t, y=y, yp=yp, sol=None, t_events=t_ev, y_events=y_ev, yp_events=yp_ev,
+    sol = None
+    if dense_output:
+        def _replay(times, _o=dict(options)):
+            return solve_dae_batched(prob, t_span, y0b, yp0b, params[None, :], method=method, t_eval=times,
+                                     device=device, events=events, **_o).numpy()
+        sol = ReplayDaeSolution(_replay, t_span, r.t_final[0], prob.n)
+    return DaeResult(t=t, y=y, yp=yp, sol=sol, t_events=t_ev, y_events=y_ev, yp_events=yp_ev,
                      nfev=int(r.nfev[0]), njev=int(r.njev[0]), nlu=int(r.nlu[0]),
                      status=-1 if status < 0 else status,
                      message=MESSAGES.get(status, ""), success=status >= 0,

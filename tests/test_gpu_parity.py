@@ -248,3 +248,25 @@ def test_group_and_thread_regimes_agree():
     ya, yb = np.array(a["y"]), np.array(b["y"])
     assert (np.abs(ya - yb) <= 4.0 * np.maximum(10 * 1e-10 * np.abs(yb), 1e-6)).all()
     assert (np.abs(np.array(a["acc"]) - np.array(b["acc"])) <= 0.05 * np.array(b["acc"]) + 2).all()
+
+
+def test_single_system_surface_events_and_dense_output():
+    """scipy_dae_b200.integrate.solve_dae: the reference's single-system signature with events
+    (ThresholdEvent) and dense_output=True (sol(t) by deterministic replay)."""
+    from scipy_dae_b200 import ThresholdEvent
+    from scipy_dae_b200.integrate import solve_dae
+    ev = [ThresholdEvent(component=0, value=0.9), ThresholdEvent(component=2, value=0.5, terminal=True)]
+    r = solve_dae("robertson", (0.0, 1e7), method="Radau", rtol=1e-6, atol=1e-6, events=ev, dense_output=True)
+    assert r.status == 1 and r.message == "A termination event occurred."
+    assert len(r.t_events[0]) == 1 and len(r.t_events[1]) == 1
+    assert abs(r.y_events[0][0][0] - 0.9) < 1e-9 and abs(r.y_events[1][0][2] - 0.5) < 1e-9
+    assert r.t[-1] == r.t_events[1][0]                       # the last point is the terminal event
+    # sol(t) reproduces the step ends and interpolates in between
+    y, yp = r.sol(r.t[5])
+    assert np.allclose(y, r.y[:, 5], rtol=1e-12, atol=1e-15)
+    tt = np.array([r.t[3], 0.5 * (r.t[3] + r.t[4]), r.t[4]])
+    Y, Yp = r.sol(tt[[2, 0, 1]])                             # any order, repeated times allowed
+    assert Y.shape == (3, 3) and np.allclose(Y[:, 1], r.y[:, 3], rtol=1e-12, atol=1e-15)
+    assert (np.abs(Y.sum(axis=0) - 1.0) < 1e-6).all()
+    with pytest.raises(ValueError):
+        r.sol(2 * r.t[-1])
