@@ -66,7 +66,7 @@ __device__ __forceinline__ void change_D_call(double (&D)[kBdfRows], int order, 
     for (int i = 0; i < kBdfRows; ++i) D[i] = tmp[i];
 }
 
-template <class P, int G, int kThreads, int kMinBlocks, bool kJac = false>
+template <class P, int G, int kThreads, int kMinBlocks, bool kJac = false, bool kEv = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     constexpr int N = P::N, NP = P::NP;
@@ -142,7 +142,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     }
     if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; njev = 1; }
     EventState evs;                  // g = event(t0, y0, yp0), dae.py:436 (identical in every lane)
-    for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
+    if (kEv) for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
         evs.count[k] = evs.found[k] = 0;
         evs.g[k] = (k < L.ev.spec.n_events)
             ? g.bcast(L.ev.spec.of_yp[k] ? yp : y, L.ev.spec.component[k]) - L.ev.spec.value[k] : 0.0;
@@ -386,7 +386,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         };
         // events on this step's dense output (dae.py:466-490); a terminal one moves the step end
         bool ev_stop = false;
-        if (L.ev.spec.n_events > 0) {
+        if (kEv && L.ev.spec.n_events > 0) {
             auto dense = [&](double te, int comp, bool of_yp) -> double {
                 double av, bv;
                 dense_lane(te, av, bv);
@@ -451,7 +451,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         L.out.status[inst] = status;
         if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
         if (L.out.n_steps) L.out.n_steps[inst] = nst;
-        for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
+        if (kEv) for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
         if (L.out.counters) {
             int32_t* cn = L.out.counters + inst;
             cn[B200DAE_CNT_NFEV * ld] = nfev;

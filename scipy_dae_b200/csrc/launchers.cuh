@@ -136,7 +136,7 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-template <class P, bool J = false>
+template <class P, bool J = false, bool E = false>
 static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
     constexpr int G = GroupSize<P::N>::value;
     constexpr int T = (G == 32) ? 32 : 64;
@@ -144,7 +144,7 @@ static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
     constexpr size_t smem = (size_t)(T / G) * Lay::doubles(P::NP) * sizeof(double);
     static_assert(smem <= 227 * 1024, "per-block shared memory");
     constexpr int MB = B200DAE_GROUP_MINBLOCKS(G);
-    auto kern = bdf_group_kernel<P, G, T, MB, J>;
+    auto kern = bdf_group_kernel<P, G, T, MB, J, E>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -162,10 +162,11 @@ static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
     if (L.analytic_jac && !P::kHasJac) return kErrNoJac;
     if constexpr (!Regime<P::N>::kReg) {
         if (!force_thread_regime()) {
+            const bool ev = L.ev.spec.n_events > 0;      // the event code is compiled out otherwise
             if constexpr (P::kHasJac) {
-                if (L.analytic_jac) return launch_bdf_group<P, true>(L, st);
+                if (L.analytic_jac) return ev ? launch_bdf_group<P, true, true>(L, st) : launch_bdf_group<P, true, false>(L, st);
             }
-            return launch_bdf_group<P, false>(L, st);
+            return ev ? launch_bdf_group<P, false, true>(L, st) : launch_bdf_group<P, false, false>(L, st);
         }
         if (L.analytic_jac) return kErrNoJac;
     }
