@@ -79,7 +79,7 @@ static bool force_thread_regime() {
 
 constexpr int kErrNoJac = -77;    // analytic Jacobian requested but not compiled for (problem, stages)
 
-template <class P, int S, bool J = false>
+template <class P, int S, bool J = false, bool LEAN = false>
 static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
     constexpr int G = GroupSize<P::N>::value;
     constexpr int T = (G == 32) ? 32 : 64;
@@ -88,7 +88,7 @@ static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
     static_assert(smem <= 227 * 1024, "per-block shared memory");
     // sub-warp groups: cap the registers at 168 so that six 64-thread blocks (12 warps) share an SM
     constexpr int MB = B200DAE_GROUP_MINBLOCKS(G);
-    auto kern = radau_group_kernel<P, S, G, T, MB, J>;
+    auto kern = radau_group_kernel<P, S, G, T, MB, J, LEAN>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -108,10 +108,12 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
     if (L.analytic_jac && !kJacOk) return kErrNoJac;
     if constexpr (!Regime<P::N>::kReg) {
         if (!force_thread_regime()) {
+            const bool glean = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_eval == nullptr &&
+                               L.out.t_steps == nullptr && L.ev.spec.n_events == 0;
             if constexpr (kJacOk) {
-                if (L.analytic_jac) return launch_radau_group<P, S, true>(L, st);
+                if (L.analytic_jac) return launch_radau_group<P, S, true, false>(L, st);
             }
-            return launch_radau_group<P, S, false>(L, st);
+            return glean ? launch_radau_group<P, S, false, true>(L, st) : launch_radau_group<P, S, false, false>(L, st);
         }
         if (L.analytic_jac) return kErrNoJac;
     }

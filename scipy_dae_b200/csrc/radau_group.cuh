@@ -161,7 +161,9 @@ __device__ __forceinline__ void analytic_jacobian_group(const Grp& g, double t, 
     g.sync();
 }
 
-template <class P, int S, int G, int kThreads, int kMinBlocks, bool kJac = false>
+// kLean: default error estimator, no t_eval / step trace / events (compiled out: these kernels
+// are bound by instruction fetch, every KB of cold code costs throughput).
+template <class P, int S, int G, int kThreads, int kMinBlocks, bool kJac = false, bool kLean = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
@@ -237,7 +239,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     int32_t nst = 0;
     const int newton_max_iter = L.newton_max_iter;
 
-    if (L.out.t_steps != nullptr && L.out.steps_cap > 0) {
+    if (!kLean && L.out.t_steps != nullptr && L.out.steps_cap > 0) {
         if (lane == 0) L.out.t_steps[inst] = t;
         if (act) {
             if (L.out.y_steps) L.out.y_steps[lane * ld + inst] = y;
@@ -247,7 +249,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     }
     if (L.t0 == L.t_bound) { status = B200DAE_ST_FINISHED; need_jac = false; njev = 1; }
     EventState evs;                  // g = event(t0, y0, yp0), dae.py:436 (identical in every lane)
-    for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
+    if (!kLean) for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
         evs.count[k] = evs.found[k] = 0;
         evs.g[k] = (k < L.ev.spec.n_events)
             ? g.bcast(L.ev.spec.of_yp[k] ? yp : y, L.ev.spec.component[k]) - L.ev.spec.value[k] : 0.0;
@@ -440,7 +442,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         // ---- phase E (radau.py:560-596) -------------------------------------------------------
         double err;
         {
-            const int emb = L.newton_iter_embedded;
+            const int emb = kLean ? 1 : L.newton_iter_embedded;
             if (emb == 0) {
                 double acc = 0.0;
 #pragma unroll
@@ -483,7 +485,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         }
         double error_norm;
         {
-            const double w = L.cew;
+            const double w = kLean ? 0.0 : L.cew;
             double e = (1.0 - w) * fabs(err);
             if (w != 0.0) {
                 double acc = 0.0;
@@ -552,7 +554,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         // events on this step's dense output (dae.py:466-490); a terminal one moves the step end
         double t_lim = t_new, y_stop = 0.0, yp_stop = 0.0;
         bool ev_stop = false;
-        if (L.ev.spec.n_events > 0) {
+        if (!kLean && L.ev.spec.n_events > 0) {
             auto dense = [&](double te, int comp, bool of_yp) -> double {
                 double av, bv;
                 dense_lane(te, av, bv);
@@ -578,7 +580,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                 dense_lane(ts, y_stop, yp_stop);
             }
         }
-        if (L.out.t_eval != nullptr) {
+        if (!kLean && L.out.t_eval != nullptr) {
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
                 if (!(dir > 0.0 ? te <= t_lim : te >= t_lim)) break;
@@ -595,7 +597,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         y = ev_stop ? y_stop : Y[S - 1];
         yp = ev_stop ? yp_stop : Yp[S - 1];
         ++nacc;
-        if (L.out.t_steps != nullptr && nst < L.out.steps_cap) {
+        if (!kLean && L.out.t_steps != nullptr && nst < L.out.steps_cap) {
             if (lane == 0) L.out.t_steps[(int64_t)nst * ld + inst] = t;
             if (act) {
                 if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + lane) * ld + inst] = y;
@@ -620,7 +622,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         L.out.status[inst] = status;
         if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
         if (L.out.n_steps) L.out.n_steps[inst] = nst;
-        for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
+        if (!kLean) for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
         if (L.out.counters) {
             int32_t* c = L.out.counters + inst;
             c[B200DAE_CNT_NFEV * ld] = nfev;
