@@ -233,7 +233,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
                 yp_new = fma(c, d, psi);
                 if (act) { sY[lane] = y_new; sYp[lane] = yp_new; }
                 g.sync();
-                if (lane == 0) eval_shared<P>(t_new, sY, sYp, p, sF);
+                eval_shared<P>(t_new, sY, sYp, p, sF);           // every lane, identical writes
                 g.sync();
                 double f = act ? sF[lane] : 0.0;
                 ++nfev;

@@ -47,12 +47,16 @@ struct RadauGroupLayout {   // offsets in doubles inside one group's shared-memo
     __host__ __device__ static constexpr int doubles(int np) { return oPar + np + ((oPar + np) & 1); }   // keep groups 16 B aligned
 };
 
-// Residual call of the cooperative kernels (all pointers point into shared memory).  Small
-// functors are inlined at the four call sites; a large one (Andrews) declares itself
-// __noinline__ and then exists once per kernel.  A __noinline__ wrapper for every functor was
-// tried (it shrinks the transistor-amplifier kernel from 94 to 70 KB) and is kept behind
-// -DB200DAE_NOINLINE_EVAL, but with it the amplifier ensembles fail after t = 7e-4 on sm_100a
-// (nvcc 12.9) while the inlined build of the same source is correct, so it is off.
+// Residual call of the cooperative kernels (all pointers point into shared memory).  Every call
+// is made by ALL lanes of a group (lanes without a stage / column of their own repeat another
+// lane's evaluation and write identical values): free in SIMT, and it removes the divergent
+// regions around the calls (+5..9 % on the amplifier).  Small functors are inlined at the four
+// call sites; a large one (Andrews) declares itself __noinline__ and then exists once per kernel.
+// A __noinline__ wrapper for every functor (-DB200DAE_NOINLINE_EVAL, 10 KB less code) is NOT
+// usable: with it the amplifier ensembles fail deterministically after t = 7e-4 on sm_100a
+// (nvcc 12.9; same step counts with divergent and with convergent call sites, so not a race),
+// while the inlined build of the same source matches the reference; Akzo Nobel is correct
+// either way and not faster.
 #ifdef B200DAE_NOINLINE_EVAL
 #define B200DAE_EVAL_ATTR __noinline__
 #else
@@ -78,36 +82,40 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
     const bool act = c < N;
     if (act) { sy[c] = yj; syp[c] = ypj; }
     g.sync();
-    if (c == 0) eval_shared<P>(t, sy, syp, p, sf);
+    // Every residual call below is made by ALL lanes of the group (idle lanes repeat lane work
+    // and discard it): in SIMT that costs nothing extra, and the call sites stay convergent.
+    eval_shared<P>(t, sy, syp, p, sf);                       // identical writes from every lane
     g.sync();
+    const int cc = act ? c : 0;                              // idle lanes shadow column 0
     double* xc = scratch + c * (3 * LD);
     double* fbuf0 = xc + LD;
     double* fbuf1 = fbuf0 + LD;
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
-        if (act) {
-            const bool wrt_yp = (which == 1);
-            const double* xs = wrt_yp ? syp : sy;
-            const double xi = wrt_yp ? ypj : yj;
-            const double f_sign = (sf[c] >= 0.0) ? 1.0 : -1.0;
-            const double y_scale = f_sign * fmax(thr_j, fabs(xi));
-            double fac = wrt_yp ? fac_yp : fac_y;
-            double xp = fma(fac, y_scale, xi);
-            double h = xp - xi;
-            while (h == 0.0) {
-                fac *= 10.0;
-                xp = fma(fac, y_scale, xi);
-                h = xp - xi;
-            }
-            for (int r = 0; r < N; ++r) xc[r] = xs[r];
-            double max_diff = 0.0, scale = 0.0;
-            double fac_try = fac, xp_try = xp, h_try = h;
-            const double* fsel = fbuf0;
+        const bool wrt_yp = (which == 1);
+        const double* xs = wrt_yp ? syp : sy;
+        const double xi = act ? (wrt_yp ? ypj : yj) : xs[0];
+        const double f_sign = (sf[cc] >= 0.0) ? 1.0 : -1.0;
+        const double y_scale = f_sign * fmax(thr_j, fabs(xi));
+        double fac = wrt_yp ? fac_yp : fac_y;
+        double xp = fma(fac, y_scale, xi);
+        double h = xp - xi;
+        while (h == 0.0) {
+            fac *= 10.0;
+            xp = fma(fac, y_scale, xi);
+            h = xp - xi;
+        }
+        for (int r = 0; r < N; ++r) xc[r] = xs[r];
+        double max_diff = 0.0, scale = 0.0;
+        double fac_try = fac, xp_try = xp, h_try = h;
+        const double* fsel = fbuf0;
+        bool want = true;                                    // this lane takes part in the attempt
 #pragma unroll 1
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                double* fnew = attempt ? fbuf1 : fbuf0;
-                xc[c] = xp_try;
-                eval_shared<P>(t, wrt_yp ? sy : xc, wrt_yp ? xc : syp, p, fnew);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            double* fnew = attempt ? fbuf1 : fbuf0;
+            xc[cc] = xp_try;
+            eval_shared<P>(t, wrt_yp ? sy : xc, wrt_yp ? xc : syp, p, fnew);
+            if (want) {
                 double best = -1.0, f_at = 0.0, fn_at = 0.0, d_at = 0.0;
                 for (int r = 0; r < N; ++r) {
                     const double fr = sf[r], fn = fnew[r];
@@ -125,11 +133,18 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
                     scale = sc2;
                     max_diff = md2;
                 }
-                if (attempt == 1 || !(max_diff < kNjDiffReject * scale)) break;
+            }
+            // second attempt only for the lanes whose difference drowned in round-off
+            // (SP/common.py:350-371); the others re-evaluate their first point and ignore it
+            want = want && attempt == 0 && (max_diff < kNjDiffReject * scale);
+            if (attempt == 1 || !g.any(act && want)) break;
+            if (want) {
                 fac_try = 10.0 * fac;
                 xp_try = fma(fac_try, y_scale, xi);
                 h_try = xp_try - xi;
             }
+        }
+        if (act) {
             const double rh = fast_rcp(h);
             double* J = wrt_yp ? sJyp : sJy;
             for (int r = 0; r < N; ++r) J[r * LD + c] = (fsel[r] - sf[r]) * rh;
@@ -362,7 +377,10 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                     for (int i = 0; i < S; ++i) { sY[i * LD + lane] = Y[i]; sYp[i * LD + lane] = Yp[i]; }
                 }
                 g.sync();
-                if (lane < S) eval_shared<P>(fma(h, tb.C[lane], t), sY + lane * LD, sYp + lane * LD, p, sF + lane * LD);
+                {
+                    const int st = lane % S;             // lanes >= S repeat a stage (identical writes)
+                    eval_shared<P>(fma(h, tb.C[st], t), sY + st * LD, sYp + st * LD, p, sF + st * LD);
+                }
                 g.sync();
                 bool fin = true;
 #pragma unroll
@@ -470,7 +488,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                     const double yph = (emb == 1) ? yph0 : fma(yh, rhm, yph0);
                     if (act) { sY[lane] = yh; sYp[lane] = yph; }
                     g.sync();
-                    if (lane == 0) eval_shared<P>(t_new, sY, sYp, p, sF);
+                    eval_shared<P>(t_new, sY, sYp, p, sF);       // every lane, identical writes
                     g.sync();
                     e = act ? sF[lane] : 0.0;
                     ++nfev;
