@@ -30,6 +30,12 @@ STATE_SLACK = {
 # bands.  The t_eval band of that case is widened accordingly; its final-state band is not.
 EVAL_SLACK = {
     "transamp_radau3_ens": 40.0,
+    # Akzo Nobel with BDF at rtol = atol = 1e-8: the band (1e-7 relative) is at the level of the
+    # method's own sensitivity to rounding.  Measured: the CPU oracle built WITH FMA contraction
+    # (gcc -ffp-contract=fast -mfma, otherwise identical) moves y(t_eval) by 0.78 bands against the
+    # reference; two CUDA builds of the same source (different inlining contexts of the residual)
+    # gave < 1 and 2.76 bands.  The final state stays inside the unwidened band (0.39).
+    "akzo_bdf_ens": 4.0,
 }
 
 # Andrews' squeezer: the reference's step sequence is itself chaotic at these tolerances.

