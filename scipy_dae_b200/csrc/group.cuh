@@ -27,6 +27,12 @@
 #include <cuda_runtime.h>
 #include "dense_lu.cuh"
 
+// Unroll factor of the substitution loops.  Swept on B200 (solves/s, amplifier Radau s=3 / Andrews
+// Radau s=5): 1 -> 60.8 k / 91.6 k, 2 -> 63.4 k / 93.7 k, 4 (Andrews) -> 90.8 k, full for n <= 8 -> 56.7 k.
+#ifndef B200DAE_SOLVE_UNROLL
+#define B200DAE_SOLVE_UNROLL(N) 2
+#endif
+
 namespace b200dae {
 
 template <int G>
@@ -221,7 +227,8 @@ __device__ __forceinline__ void group_lu_solve(const Grp& g, const double* __res
         bi[c] = g.bcast(bi[c], cperm[c]);
     }
     // forward substitution with the unit lower factor
-#pragma unroll 2
+    constexpr int kSolveUnroll = B200DAE_SOLVE_UNROLL(N);
+#pragma unroll kSolveUnroll
     for (int k = 0; k < N - 1; ++k) {
         const bool below = lane > k && lane < N;
         if (kReal) {
@@ -239,7 +246,7 @@ __device__ __forceinline__ void group_lu_solve(const Grp& g, const double* __res
         }
     }
     // back substitution with U (reciprocal pivots on the diagonal)
-#pragma unroll 2
+#pragma unroll kSolveUnroll
     for (int k = N - 1; k >= 0; --k) {
         const bool above = lane < k;
         if (kReal) {
