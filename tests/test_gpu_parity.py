@@ -173,9 +173,11 @@ def test_edge_cases():
         solve_dae_batched("robertson", (0.0, 1.0), [[np.inf, 0, 0]], [[0.0, 0, 0]], rtol=1e-6, atol=1e-6)
 
 
-def test_full_size_properties():
-    """Size-independent properties at the bench size (2^20 Robertson instances):
-    mass conservation of the algebraic constraint, monotone dependence, all finished."""
+def test_full_size_properties(oracle):
+    """The bench ensemble itself (config 2: 2^20 Robertson instances, seed 0): size-independent
+    properties (mass conservation of the algebraic constraint, all finished, placement
+    independence) and the SURVEY.md §8d parity sample (the first 4 096 instances and 4 096 random
+    ones against the oracle)."""
     from scipy_dae_b200 import solve_dae_batched, perturbed_params, initial_conditions
     N = 1 << 20
     params = perturbed_params("robertson", N, 0.1, seed=0)
@@ -183,6 +185,14 @@ def test_full_size_properties():
     r = solve_dae_batched("robertson", (0.0, 1e7), y0, yp0, params, rtol=1e-6, atol=1e-6)
     torch.cuda.synchronize()
     assert bool((r.status == 0).all())
+    idx = np.concatenate([np.arange(4096), np.random.default_rng(123).choice(N, 4096, replace=False)])
+    ref = oracle.solve_ensemble("robertson", params[idx], y0[idx], yp0[idx], (0.0, 1e7), method="Radau",
+                                rtol=1e-6, atol=1e-6, nthreads=8)
+    yg = r.y_final[torch.from_numpy(idx).to(r.y_final.device)].cpu().numpy()
+    ratio = np.abs(yg - ref["y_final"]) / np.maximum(1e-5 * np.abs(ref["y_final"]), 1e-6)
+    assert (ref["status"] == 0).all() and ratio.max() <= 1.0, ratio.max()
+    acc_g = r.n_accepted[torch.from_numpy(idx).to(r.n_accepted.device)].cpu().numpy()
+    assert (np.abs(acc_g - ref["n_accepted"]) <= 0.05 * ref["n_accepted"] + 2).all()
     y = r.y_final
     assert float((y.sum(dim=1) - 1.0).abs().max()) < 1e-5          # y1 + y2 + y3 = 1 (algebraic row)
     assert float(y.min()) > -1e-6
