@@ -249,3 +249,60 @@ def consistent_initial_conditions(problem, t0, y0, yp0, params, jac=None, fixed_
     if rc != 0:
         raise RuntimeError(f"orc_consistent_ic_ensemble returned {rc}")
     return dict(y0=y0, yp0=yp0, f=f, status=status, n_iter=n_iter)
+
+
+def solve_trace(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, atol=1e-6, cap=1 << 14, **options):
+    """ONE instance with its accepted-step trace (what solve_dae returns as t / y when t_eval is
+    None, dae.py:492-495): dict(t_steps[k], y_steps[n, k], yp_steps[n, k], status, nfev, njev, nlu,
+    n_accepted).  yp at the step ends comes from a second pass with t_eval = step ends."""
+    pid, n, npar = problem_id(problem)
+    L = lib()
+    fn = ctypes.c_void_p(ctypes.cast(L.orc_problem_residual, ctypes.c_void_p).value)
+    L.orc_problem_residual.restype = ctypes.c_void_p
+    fnp = L.orc_problem_residual(ctypes.c_int(pid))
+    p = np.ascontiguousarray(params, dtype=float).reshape(npar)
+    y0 = np.ascontiguousarray(y0, dtype=float).reshape(n)
+    yp0 = np.ascontiguousarray(yp0, dtype=float).reshape(n)
+    atol_v = np.ascontiguousarray(np.broadcast_to(np.asarray(atol, dtype=float), (n,)))
+    t0, t1 = map(float, t_span)
+    t_steps = np.empty(cap); y_steps = np.empty((cap, n)); nsteps = ctypes.c_int64(0)
+    y_final = np.empty(n); yp_final = np.empty(n); t_final = ctypes.c_double(0.0)
+    counters = np.zeros(8, dtype=np.int64); nev = ctypes.c_int64(0)
+    if method == "Radau":
+        s = int(options.pop("stages", 3))
+        tb = radau_tables_c(s)
+        db = options.pop("controller_deadband", (1.0, 1.2))
+        ro = RadauOpts(rtol=rtol, max_step=float(options.pop("max_step", np.inf)),
+                       first_step=float(options.pop("first_step", None) or 0.0),
+                       continuous_error_weight=float(options.pop("continuous_error_weight", 0.0)),
+                       jac_recompute_rate=float(options.pop("jac_recompute_rate", 1e-3)),
+                       deadband_lo=db[0], deadband_hi=db[1], newton_max_iter=int(options.pop("newton_max_iter", None) or 0),
+                       newton_iter_embedded=int(options.pop("newton_iter_embedded", 1)), max_steps=0)
+        L.orc_solve_radau.restype = ctypes.c_int
+        st = L.orc_solve_radau(ctypes.c_void_p(fnp), ctypes.c_int(n), _p(p), ctypes.c_double(t0), ctypes.c_double(t1),
+                               _p(y0), _p(yp0), _p(atol_v), ctypes.byref(ro), ctypes.byref(tb),
+                               None, ctypes.c_int64(0), None, None, ctypes.byref(nev),
+                               _p(y_final), _p(yp_final), ctypes.byref(t_final), _p(counters, ctypes.c_int64),
+                               _p(t_steps), _p(y_steps), ctypes.c_int64(cap), ctypes.byref(nsteps))
+        opts2 = dict(stages=s)
+    else:
+        bo = BdfOpts(rtol=rtol, max_step=float(options.pop("max_step", np.inf)),
+                     first_step=float(options.pop("first_step", None) or 0.0), max_order=int(options.pop("max_order", 5)),
+                     ndf_strategy=NDF_STRATEGIES[options.pop("NDF_strategy", "stability")], max_steps=0)
+        L.orc_solve_bdf.restype = ctypes.c_int
+        st = L.orc_solve_bdf(ctypes.c_void_p(fnp), ctypes.c_int(n), _p(p), ctypes.c_double(t0), ctypes.c_double(t1),
+                             _p(y0), _p(yp0), _p(atol_v), ctypes.byref(bo),
+                             None, ctypes.c_int64(0), None, None, ctypes.byref(nev),
+                             _p(y_final), _p(yp_final), ctypes.byref(t_final), _p(counters, ctypes.c_int64),
+                             _p(t_steps), _p(y_steps), ctypes.c_int64(cap), ctypes.byref(nsteps))
+        opts2 = {}
+    k = int(nsteps.value)
+    ts = t_steps[:k].copy()
+    yps = np.empty((n, k)); yps[:, 0] = yp0
+    if k > 1:
+        r2 = solve_ensemble(problem, p[None, :], y0[None, :], yp0[None, :], t_span, method=method, rtol=rtol,
+                            atol=atol, t_eval=ts[1:], **opts2)
+        nv = int(r2["n_eval_valid"][0])
+        yps[:, 1:1 + nv] = r2["yp_eval"][0, :nv].T
+    return dict(t_steps=ts, y_steps=y_steps[:k].T.copy(), yp_steps=yps, status=int(st), nfev=int(counters[0]),
+                njev=int(counters[1]), nlu=int(counters[2]), n_accepted=int(counters[4]))
