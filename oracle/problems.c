@@ -170,6 +170,49 @@ static void andrews(double t, const double *y, const double *yp, const double *p
     }
 }
 
+/* ---- the reference's own known-answer test problems (twins of problems.py) ---- */
+static void rational(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    (void)p;
+    out[0] = yp[0] - y[1] / t;
+    out[1] = yp[1] - y[1] * (y[0] + 2 * y[1] - 1) / (t * (y[0] - 1));
+}
+static void rational_jac(double t, const double *y, const double *yp, const double *p, double *Jy, double *Jyp)
+{
+    (void)yp; (void)p;
+    Jy[0] = -0.0; Jy[1] = -(1 / t);
+    Jy[2] = -(-2 * y[1] * y[1] / (t * (y[0] - 1) * (y[0] - 1)));
+    Jy[3] = -((y[0] + 4 * y[1] - 1) / (t * (y[0] - 1)));
+    Jyp[0] = 1; Jyp[1] = 0; Jyp[2] = 0; Jyp[3] = 1;
+}
+static void linear(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    (void)t; (void)p;
+    out[0] = yp[0] - (-y[0] - 5 * y[1]);
+    out[1] = yp[1] - (y[0] + y[1]);
+}
+static void linear_jac(double t, const double *y, const double *yp, const double *p, double *Jy, double *Jyp)
+{
+    (void)t; (void)y; (void)yp; (void)p;
+    Jy[0] = 1; Jy[1] = 5; Jy[2] = -1; Jy[3] = -1;
+    Jyp[0] = 1; Jyp[1] = 0; Jyp[2] = 0; Jyp[3] = 1;
+}
+static void cosine(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    (void)y;
+    out[0] = yp[0] - p[0] * cos(t);
+}
+static void weissinger(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    double u = y[0] / p[0], up = yp[0] / p[0];
+    out[0] = t * (u * u) * (up * up * up) - (u * u * u) * (up * up) + t * (t * t + 1) * up - (t * t) * u;
+}
+static void brenan(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    out[0] = yp[0] - t * yp[1] + y[0] - (1 + t) * y[1];
+    out[1] = y[1] - p[0] * sin(t);
+}
+
 /* ---- analytic Jacobians (the reference's `jac=` callable, base.py:299-331), row-major n*n;
  * twins of problems.py: robertson_jacobian, akzo_jacobian, transamp_jacobian ---- */
 static void robertson_jac(double t, const double *y, const double *yp, const double *p,
@@ -254,6 +297,11 @@ static const struct {
     {"akzo_nobel", 6, 7, akzo_nobel, akzo_nobel_jac},
     {"transamp", 8, 3, transamp, transamp_jac},
     {"andrews", 26, 2, andrews, 0},
+    {"rational", 2, 0, rational, rational_jac},
+    {"linear", 2, 0, linear, linear_jac},
+    {"cosine", 1, 1, cosine, 0},
+    {"weissinger", 1, 1, weissinger, 0},
+    {"brenan", 2, 1, brenan, 0},
 };
 #define N_PROBLEMS ((int)(sizeof(REGISTRY) / sizeof(REGISTRY[0])))
 

@@ -163,7 +163,7 @@ def _validate_t_eval(t_eval, t0, t_bound):
     d = np.diff(t_eval)
     if t_bound > t0 and np.any(d <= 0) or t_bound < t0 and np.any(d >= 0):
         raise ValueError("Values in `t_eval` are not properly sorted.")
-    return np.ascontiguousarray(t_eval)
+    return np.array(t_eval, dtype=float, copy=True)     # owns its data (reversed views have negative strides)
 
 
 def _as_device_soa(x, N, width, name, device, check_finite=True):

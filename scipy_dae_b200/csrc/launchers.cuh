@@ -46,6 +46,11 @@ ProblemEntry entry_robertson();
 ProblemEntry entry_akzo_nobel();
 ProblemEntry entry_transamp();
 ProblemEntry entry_andrews();
+ProblemEntry entry_rational();
+ProblemEntry entry_linear();
+ProblemEntry entry_cosine();
+ProblemEntry entry_weissinger();
+ProblemEntry entry_brenan();
 
 // threads per block: register-regime kernels keep ~255 registers per thread live, so 128
 // threads x 2 blocks fill an SM's register file; the local-memory regime prefers fewer

@@ -150,6 +150,92 @@ struct Transamp {
     }
 };
 
+// ---- the reference's own known-answer test problems ---------------------------
+
+// 2-D rational ODE of tests/test_integration_rational.py (scipy test_ivp.fun_rational) as
+// F = y' - f(t, y); exact solution (t / (t + 10), 10 t / (t + 10)^2).
+struct Rational {
+    static constexpr int N = 2, NP = 0;
+    static constexpr const char* name() { return "rational"; }
+    static constexpr int kFlops = 12;
+    __device__ __forceinline__ static void eval(double t, const double* y, const double* yp, const double*,
+                                                double* out) {
+        out[0] = yp[0] - y[1] / t;
+        out[1] = yp[1] - y[1] * (y[0] + 2.0 * y[1] - 1.0) / (t * (y[0] - 1.0));
+    }
+    static constexpr bool kHasJac = true;      // J_rational, tests/test_integration_rational.py:20-23
+    template <class M>
+    __device__ __forceinline__ static void jac(double t, const double* y, const double*, const double*,
+                                               M Jy, M Jyp) {
+        const double d = y[0] - 1.0;
+        Jy(0, 1) = -1.0 / t;
+        Jy(1, 0) = 2.0 * y[1] * y[1] / (t * d * d);
+        Jy(1, 1) = -(y[0] + 4.0 * y[1] - 1.0) / (t * d);
+        Jyp(0, 0) = 1.0; Jyp(1, 1) = 1.0;
+    }
+};
+
+// linear 2-D ODE of tests/test_integration_linear.py (scipy test_ivp.fun_linear):
+// exact solution (-5 sin 2t, 2 cos 2t + sin 2t).
+struct Linear {
+    static constexpr int N = 2, NP = 0;
+    static constexpr const char* name() { return "linear"; }
+    static constexpr int kFlops = 6;
+    __device__ __forceinline__ static void eval(double, const double* y, const double* yp, const double*,
+                                                double* out) {
+        out[0] = yp[0] - (-y[0] - 5.0 * y[1]);
+        out[1] = yp[1] - (y[0] + y[1]);
+    }
+    static constexpr bool kHasJac = true;      // J_linear (a constant tuple in the reference's test)
+    template <class M>
+    __device__ __forceinline__ static void jac(double, const double*, const double*, const double*, M Jy, M Jyp) {
+        Jy(0, 0) = 1.0; Jy(0, 1) = 5.0; Jy(1, 0) = -1.0; Jy(1, 1) = -1.0;
+        Jyp(0, 0) = 1.0; Jyp(1, 1) = 1.0;
+    }
+};
+
+// y' - a cos t = 0 (tests/test_events.py:8-9 with a = 1): y = a sin t, the event test problem.
+struct Cosine {
+    static constexpr int N = 1, NP = 1;
+    static constexpr const char* name() { return "cosine"; }
+    static constexpr int kFlops = 3;
+    __device__ __forceinline__ static void eval(double t, const double*, const double* yp, const double* p,
+                                                double* out) {
+        out[0] = yp[0] - p[0] * cos(t);
+    }
+    static constexpr bool kHasJac = false;
+};
+
+// Weissinger's fully implicit equation (benchmarks/weissinger/weissinger.py:11-17,
+// tests/test_consistent_initial_conditions.py) for z = a y:  F(t, z / a, z' / a) = 0,
+// exact solution z = a sqrt(t^2 + 1/2).
+struct Weissinger {
+    static constexpr int N = 1, NP = 1;
+    static constexpr const char* name() { return "weissinger"; }
+    static constexpr int kFlops = 16;
+    __device__ __forceinline__ static void eval(double t, const double* y, const double* yp, const double* p,
+                                                double* out) {
+        const double ra = 1.0 / p[0];
+        const double u = y[0] * ra, up = yp[0] * ra;
+        out[0] = t * (u * u) * (up * up * up) - (u * u * u) * (up * up) + t * (t * t + 1.0) * up - (t * t) * u;
+    }
+    static constexpr bool kHasJac = false;
+};
+
+// Brenan's index-1 problem (benchmarks/brenan/brenan.py:11-19) with amplitude A:
+// y1' - t y2' + y1 - (1 + t) y2 = 0,  y2 - A sin t = 0;  y1 = C exp(-t) + A t sin t, y2 = A sin t.
+struct Brenan {
+    static constexpr int N = 2, NP = 1;
+    static constexpr const char* name() { return "brenan"; }
+    static constexpr int kFlops = 10;
+    __device__ __forceinline__ static void eval(double t, const double* y, const double* yp, const double* p,
+                                                double* out) {
+        out[0] = yp[0] - t * yp[1] + y[0] - (1.0 + t) * y[1];
+        out[1] = y[1] - p[0] * sin(t);
+    }
+    static constexpr bool kHasJac = false;
+};
+
 // Andrews' squeezer, stabilised index-1 form, n = 26: y = (q[7], u[7], la[6], mu[6]),
 // yp = (q'[7], u'[7], lambda[6], mu-multipliers[6]); p = (mom, c0).
 struct Andrews {

@@ -44,6 +44,8 @@ class Problem:
     param_names: tuple = field(default_factory=tuple)
     initial_batch: Callable = None   # optional vectorised initial(params[N, p]) -> (y0[N, n], yp0[N, n])
     jacobian: Callable = None        # optional analytic jac(t, y, yp, *params) -> (Jy[n, n], Jyp[n, n])
+    solution: Callable = None        # optional exact solution(t, *params) -> (y[n, ...], yp[n, ...])
+    t0_default: float = None         # start of t_span (for problems whose ICs depend on it)
 
     def __call__(self, t, y, yp, *params):
         if not params:
@@ -335,6 +337,82 @@ def andrews_initial(params):
 # --------------------------------------------------------------------------- #
 # registry
 # --------------------------------------------------------------------------- #
+# --------------------------------------------------------------------------- #
+# The reference's own known-answer test problems
+# --------------------------------------------------------------------------- #
+def rational_residual(t, y, yp):
+    """tests/test_integration_rational.py:12-13 with scipy's test_ivp.fun_rational."""
+    return np.array([yp[0] - y[1] / t,
+                     yp[1] - y[1] * (y[0] + 2 * y[1] - 1) / (t * (y[0] - 1))])
+
+
+def rational_jacobian(t, y, yp):
+    Jy = -np.array([[0, 1 / t],
+                    [-2 * y[1] ** 2 / (t * (y[0] - 1) ** 2), (y[0] + 4 * y[1] - 1) / (t * (y[0] - 1))]])
+    return Jy, np.eye(2)
+
+
+def rational_solution(t):
+    t = np.asarray(t, dtype=float)
+    return (np.array([t / (t + 10), 10 * t / (t + 10) ** 2]),
+            np.array([10 / (t + 10) ** 2, 10 * (10 - t) / (t + 10) ** 3]))
+
+
+def linear_residual(t, y, yp):
+    """tests/test_integration_linear.py:9-10 with scipy's test_ivp.fun_linear."""
+    return np.array([yp[0] - (-y[0] - 5 * y[1]), yp[1] - (y[0] + y[1])])
+
+
+def linear_jacobian(t, y, yp):
+    return np.array([[1.0, 5.0], [-1.0, -1.0]]), np.eye(2)
+
+
+def linear_solution(t):
+    t = np.asarray(t, dtype=float)
+    return (np.array([-5 * np.sin(2 * t), 2 * np.cos(2 * t) + np.sin(2 * t)]),
+            np.array([-10 * np.cos(2 * t), -4 * np.sin(2 * t) + 2 * np.cos(2 * t)]))
+
+
+def cosine_residual(t, y, yp, a):
+    """tests/test_events.py:8-9 (a = 1)."""
+    return np.array([yp[0] - a * np.cos(t)])
+
+
+def cosine_solution(t, a=1.0):
+    t = np.asarray(t, dtype=float)
+    return np.array([a * np.sin(t)]), np.array([a * np.cos(t)])
+
+
+def weissinger_residual(t, y, yp, a):
+    """benchmarks/weissinger/weissinger.py:11-17 for z = a*y."""
+    u, up = y[0] / a, yp[0] / a
+    return np.array([t * u ** 2 * up ** 3 - u ** 3 * up ** 2 + t * (t ** 2 + 1) * up - t ** 2 * u])
+
+
+def weissinger_solution(t, a=1.0):
+    t = np.asarray(t, dtype=float)
+    r = np.sqrt(t ** 2 + 0.5)
+    return np.array([a * r]), np.array([a * t / r])
+
+
+def brenan_residual(t, y, yp, A):
+    """benchmarks/brenan/brenan.py:11-19 with amplitude A."""
+    return np.array([yp[0] - t * yp[1] + y[0] - (1 + t) * y[1], y[1] - A * np.sin(t)])
+
+
+def brenan_solution(t, A=1.0, C=1.0):
+    t = np.asarray(t, dtype=float)
+    return (np.array([C * np.exp(-t) + A * t * np.sin(t), A * np.sin(t)]),
+            np.array([-C * np.exp(-t) + A * (np.sin(t) + t * np.cos(t)), A * np.cos(t)]))
+
+
+def _ic_from_solution(sol, t0):
+    def initial(params):
+        y, yp = sol(t0, *params)
+        return np.asarray(y, dtype=float).reshape(-1), np.asarray(yp, dtype=float).reshape(-1)
+    return initial
+
+
 PROBLEMS: dict[str, Problem] = {}
 
 
@@ -370,6 +448,37 @@ ANDREWS = _register(Problem(
     param_names=("mom", "c0"),
     doc="Andrews' squeezer mechanism, stabilised index-1 formulation (n = 26)"))
 
+RATIONAL = _register(Problem(
+    name="rational", n=2, n_params=0, residual=rational_residual, default_params=(),
+    initial=_ic_from_solution(rational_solution, 5.0), t_span=(5.0, 9.0), jacobian=rational_jacobian,
+    solution=rational_solution, t0_default=5.0,
+    doc="2-D rational ODE of the reference's test_integration_rational.py"))
+
+LINEAR = _register(Problem(
+    name="linear", n=2, n_params=0, residual=linear_residual, default_params=(),
+    initial=_ic_from_solution(linear_solution, 0.0), t_span=(0.0, 2.0), jacobian=linear_jacobian,
+    solution=linear_solution, t0_default=0.0,
+    doc="linear 2-D ODE of the reference's test_integration_linear.py"))
+
+COSINE = _register(Problem(
+    name="cosine", n=1, n_params=1, residual=cosine_residual, default_params=(1.0,),
+    initial=_ic_from_solution(cosine_solution, -0.1), t_span=(-0.1, -0.1 + 2 * np.pi),
+    solution=cosine_solution, t0_default=-0.1, param_names=("a",),
+    doc="y' = a cos t, the problem of the reference's test_events.py"))
+
+WEISSINGER = _register(Problem(
+    name="weissinger", n=1, n_params=1, residual=weissinger_residual, default_params=(1.0,),
+    initial=_ic_from_solution(weissinger_solution, np.sqrt(0.5)), t_span=(np.sqrt(0.5), 10.0),
+    solution=weissinger_solution, t0_default=np.sqrt(0.5), param_names=("a",),
+    doc="Weissinger's fully implicit differential equation (scaled by a)"))
+
+BRENAN = _register(Problem(
+    name="brenan", n=2, n_params=1, residual=brenan_residual, default_params=(1.0,),
+    initial=_ic_from_solution(brenan_solution, 0.0), t_span=(0.0, 10.0),
+    solution=brenan_solution, t0_default=0.0, param_names=("A",),
+    doc="Brenan's index-1 DAE with a time-dependent leading matrix (amplitude A)"))
+
+
 def get_problem(name_or_problem) -> Problem:
     if isinstance(name_or_problem, Problem):
         return name_or_problem
@@ -390,13 +499,14 @@ def perturbed_params(problem, N: int, sigma: float, seed: int = 0) -> np.ndarray
     problem = get_problem(problem)
     rng = np.random.default_rng(seed)
     u = rng.uniform(-1.0, 1.0, size=(N, problem.n_params))
-    return np.asarray(problem.default_params)[None, :] * np.exp(sigma * u)
+    return np.asarray(problem.default_params, dtype=float).reshape(1, problem.n_params) * np.exp(sigma * u)
 
 
 def initial_conditions(problem, params: np.ndarray):
     """Consistent ``(y0[N,n], yp0[N,n])`` for an ``(N, n_params)`` parameter array."""
     problem = get_problem(problem)
-    params = np.atleast_2d(np.asarray(params, dtype=float))
+    params = np.asarray(params, dtype=float)
+    params = params.reshape(-1, problem.n_params) if params.ndim != 2 else params
     if problem.initial_batch is not None:
         return problem.initial_batch(params)
     y0 = np.empty((params.shape[0], problem.n))
