@@ -234,6 +234,20 @@ def cases():
     yield dict(name="andrews_radau3_ens", problem="andrews",
                params=perturbed_params("andrews", 4, 0.05, 2), method="Radau",
                rtol=1e-6, atol=1e-6, options=dict(stages=3))
+    # --- option matrix and stage counts on the group-per-system kernels (n > 4)
+    yield dict(name="akzo_radau3_emb0", problem="akzo_nobel", params=perturbed_params("akzo_nobel", 4, 0.05, 3),
+               method="Radau", rtol=1e-6, atol=1e-8, options=dict(newton_iter_embedded=0))
+    yield dict(name="akzo_radau3_emb2", problem="akzo_nobel", params=perturbed_params("akzo_nobel", 4, 0.05, 3),
+               method="Radau", rtol=1e-6, atol=1e-8, options=dict(newton_iter_embedded=2))
+    yield dict(name="akzo_radau3_cew05", problem="akzo_nobel", params=perturbed_params("akzo_nobel", 4, 0.05, 3),
+               method="Radau", rtol=1e-6, atol=1e-8, options=dict(continuous_error_weight=0.5),
+               t_eval=np.linspace(0, 180, 7))
+    yield dict(name="akzo_radau5_ens", problem="akzo_nobel", params=perturbed_params("akzo_nobel", 4, 0.05, 3),
+               method="Radau", rtol=1e-8, atol=1e-8, options=dict(stages=5))
+    yield dict(name="akzo_bdf_variants", problem="akzo_nobel", params=perturbed_params("akzo_nobel", 4, 0.05, 3),
+               method="BDF", rtol=1e-6, atol=1e-8, options=dict(NDF_strategy="efficiency", max_order=3, max_step=5.0))
+    yield dict(name="andrews_bdf_ens", problem="andrews", params=perturbed_params("andrews", 3, 0.05, 2),
+               method="BDF", rtol=1e-5, atol=1e-5, t_eval=np.linspace(0, 0.03, 4))
     # --- row N3 of SURVEY §8f: events (dae.py:30-109, 426-490) as threshold events
     yield dict(name="robertson_radau3_events", problem="robertson",
                params=perturbed_params("robertson", 8, 0.1, 0), method="Radau", rtol=1e-6, atol=1e-6,

@@ -52,6 +52,12 @@ STEP_BAND_CASE = {
 # 67.4 -- the same spread the reference shows against itself.
 STATE_SLACK.update({"andrews_radau5_ens": 10.0, "andrews_radau3_ens": 4.0})
 EVAL_SLACK.update({"andrews_radau5_ens": 10.0})
+# Andrews with BDF at rtol = atol = 1e-5: the UNMODIFIED reference run twice with a 1e-15 relative
+# parameter perturbation ends 47.8 bands apart and changes its accepted steps 360 -> 342 / 368 and
+# 378 -> 355 (measured, oracle/gen_golden.py case andrews_bdf_ens); the bands are set to that.
+STATE_SLACK.update({"andrews_bdf_ens": 100.0})
+EVAL_SLACK.update({"andrews_bdf_ens": 100.0})
+STEP_BAND_CASE.update({"andrews_bdf_ens": 0.10})
 
 
 def state_band(y_ref, rtol, atol):
