@@ -101,7 +101,9 @@ __device__ __forceinline__ bool pivot_search(const Grp& g, bool cand, double v, 
 // (Tried, B200 round 1: splitting the step loop into four ranges with narrower unrolled bodies,
 // which cuts the FMA count from N^2 to 0.63 N^2.  The extra code cost more than the FMAs saved:
 // Andrews 91 -> 85 k solves/s, amplifier 57 -> 44 k solves/s.  These kernels are bound by
-// instruction fetch and latency, not by the FP64 pipe, so the single rolled loop stays.)
+// instruction fetch and latency, not by the FP64 pipe, so the single rolled loop stays.  A two-range
+// split for n >= 16 only (-25 % FMAs, +50 % code in the elimination body) was neutral for Andrews:
+// 93.8 k vs 94.3 k solves/s.)
 //
 // Real LU.  a[0..N-1] = row `lane` of the matrix (lanes >= N: ignored).  On return
 // mat[k * LD + j] holds the factors in getrf layout with the reciprocal pivots on the diagonal and
