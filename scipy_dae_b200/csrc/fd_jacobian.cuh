@@ -83,6 +83,146 @@ __device__ __forceinline__ void analytic_jacobian(double t, const double* __rest
     P::jac(t, y, yp, p, MatRef<V, LD>{Jy}, MatRef<V, LD>{Jyp});
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched form for the register regime (n <= 4), B200DAE_FD_BATCH = 1 (the y columns, then the y'
+// columns) or 2 (all 2n columns at once).
+//
+// The column-at-a-time form below is a chain of ~25 dependent FP64 operations per column
+// (perturb -> residual -> argmax -> scale test -> reciprocal -> quotient), seven times per
+// Jacobian, with nothing else for the warp to issue: 29 % of the Robertson solve time for 15 % of
+// its instructions.  Here the FIRST attempts of all columns of a batch form one basic block (n or
+// 2n independent chains), the second attempts (a column of Jyp that belongs to an algebraic
+// variable always takes one: about one column per Robertson Jacobian) follow as predicated
+// blocks, and the reciprocals / quotients / factor updates of all columns close the batch.
+// Same arithmetic per column as the reference's vectorised num_jac, which also evaluates all
+// first attempts before any second one (SP/common.py:330-371).
+//
+// Reduction of a column: only max_diff and scale leave it, so the running argmax carries
+// (|diff|, max(|f|, |f_new|)) instead of (f, f_new, diff) at the maximal row.  np.argmax returns
+// the first NaN if there is one (max_diff = NaN: no second attempt, no factor update); that case
+// is restored by max_diff = best + 0 * (sum of the differences), NaN exactly when a difference
+// is non-finite (then J is non-finite and the solve ends with B200DAE_ST_NONFINITE either way).
+template <class P>
+__device__ __forceinline__ void fd_probe(double t, const double* __restrict__ y, const double* __restrict__ yp,
+                                         const double* __restrict__ p, const double* __restrict__ f,
+                                         int col, double xp,
+                                         double* __restrict__ diff, double& max_diff, double& scale) {
+    constexpr int N = P::N;
+    double yy[N], yyp[N], fnew[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        yy[j] = (col == j) ? xp : y[j];
+        yyp[j] = (col == N + j) ? xp : yp[j];
+    }
+    P::eval(t, yy, yyp, p, fnew);
+    double best = 0.0, s_at = 0.0, sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        const double dr = fnew[r] - f[r];
+        diff[r] = dr;
+        sum += dr;
+        const double a = fabs(dr);
+        const double s = fmax(fabs(f[r]), fabs(fnew[r]));
+        if (r == 0 || a > best) { best = a; s_at = s; }
+    }
+    max_diff = fma(0.0, sum, best);
+    scale = s_at;
+}
+
+#ifndef B200DAE_FD_STAGE
+#define B200DAE_FD_STAGE 0
+#endif
+// B200DAE_FD_STAGE = 1: the differences of a column wait in their slots of Jy / Jyp (shared
+// memory in the register regime) instead of in registers until the quotients are formed.
+template <class P, class V, int C0, int C1>
+__device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y, const double* __restrict__ yp,
+                                         const double* __restrict__ p, const double* __restrict__ thr,
+                                         const double* __restrict__ f,
+                                         V factor_y, V factor_yp, V Jy, V Jyp) {
+    constexpr int N = P::N, NC = C1 - C0;
+    constexpr bool kStage = (B200DAE_FD_STAGE != 0);
+    double fac[NC], ysc[NC], h[NC], xp[NC], diff[kStage ? 1 : NC][N], md[NC], sc[NC];
+    auto stash = [&](int c, const double* d) {
+        const int col = C0 + c, i = col % N;
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            if (!kStage) diff[kStage ? 0 : c][r] = d[r];
+            else if (col >= N) Jyp[r * N + i] = d[r];
+            else Jy[r * N + i] = d[r];
+        }
+    };
+    bool any_zero = false;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int col = C0 + c, i = col % N;
+        const double xi = (col >= N) ? yp[i] : y[i];
+        const double f_sign = (f[i] >= 0.0) ? 1.0 : -1.0;
+        ysc[c] = f_sign * fmax(thr[i], fabs(xi));
+        fac[c] = (col >= N) ? factor_yp[i] : factor_y[i];
+        xp[c] = fma(fac[c], ysc[c], xi);
+        h[c] = xp[c] - xi;
+        any_zero = any_zero || (h[c] == 0.0);
+    }
+    if (any_zero) {                                   // rare: the step vanished in round-off
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int col = C0 + c, i = col % N;
+            const double xi = (col >= N) ? yp[i] : y[i];
+            while (h[c] == 0.0) {
+                fac[c] *= 10.0;
+                xp[c] = fma(fac[c], ysc[c], xi);
+                h[c] = xp[c] - xi;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        double d1[N];
+        fd_probe<P>(t, y, yp, p, f, C0 + c, xp[c], d1, md[c], sc[c]);
+        stash(c, d1);
+    }
+    // second attempt with 10 * factor where the difference drowns in round-off (SP/common.py:350-371)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (md[c] < kNjDiffReject * sc[c]) {
+            const int col = C0 + c, i = col % N;
+            const double xi = (col >= N) ? yp[i] : y[i];
+            const double fac2 = 10.0 * fac[c];
+            const double xp2 = fma(fac2, ysc[c], xi);
+            const double h2 = xp2 - xi;
+            double d2[N], md2, sc2;
+            fd_probe<P>(t, y, yp, p, f, col, xp2, d2, md2, sc2);
+            if (md[c] * sc2 < md2 * sc[c]) {
+                fac[c] = fac2;
+                h[c] = h2;
+                stash(c, d2);
+                sc[c] = sc2;
+                md[c] = md2;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int col = C0 + c, i = col % N;
+        const double rh = fast_rcp(h[c]);     // h = inf (a factor that grew for 300+ refreshes on an algebraic column) -> 0
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            if (col >= N) Jyp[r * N + i] = (kStage ? Jyp[r * N + i] : diff[kStage ? 0 : c][r]) * rh;
+            else Jy[r * N + i] = (kStage ? Jy[r * N + i] : diff[kStage ? 0 : c][r]) * rh;
+        }
+        double fc = fac[c];
+        if (md[c] < kNjDiffSmall * sc[c]) fc *= 10.0;
+        if (md[c] > kNjDiffBig * sc[c]) fc *= 0.1;
+        fc = fmax(fc, kNjMinFactor);
+        if (col >= N) factor_yp[i] = fc;
+        else factor_y[i] = fc;
+    }
+}
+
+#ifndef B200DAE_FD_BATCH
+#define B200DAE_FD_BATCH 1
+#endif
+
 // Jy and Jyp (row-major N*N) at (t, y, yp).  thr[i] = atol[i] / rtol.
 //
 // Tried and rejected (round 1, B200): a branch-free form for n <= 4 that evaluates both attempts
@@ -103,6 +243,14 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
     constexpr int U = Regime<N>::kUnroll;
     double f[N];
     P::eval(t, y, yp, p, f);
+    if constexpr (Regime<N>::kReg && B200DAE_FD_BATCH == 2) {
+        fd_batch<P, V, 0, 2 * N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
+        return;
+    } else if constexpr (Regime<N>::kReg && B200DAE_FD_BATCH == 1) {
+        fd_batch<P, V, 0, N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
+        fd_batch<P, V, N, 2 * N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
+        return;
+    }
 #pragma unroll U
     for (int which = 0; which < 2; ++which) {
         const bool wrt_yp = (which == 1);

@@ -19,6 +19,9 @@
 #ifndef B200DAE_REG_MINBLOCKS
 #define B200DAE_REG_MINBLOCKS 6
 #endif
+#ifndef B200DAE_REG_THREADS
+#define B200DAE_REG_THREADS 64
+#endif
 #ifndef B200DAE_GROUP_MINBLOCKS
 #define B200DAE_GROUP_MINBLOCKS(G) ((G) == 32 ? 1 : 6)
 #endif
@@ -67,7 +70,7 @@ template <class P, int S>
 struct RadauTune {
     static constexpr int N = P::N, NCS = S / 2;
     static constexpr bool kReg = Regime<N>::kReg;
-    static constexpr int kThreads = 64;
+    static constexpr int kThreads = kReg ? B200DAE_REG_THREADS : 64;
     static constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
     static constexpr bool kSharedCold = kReg && (kCold * kThreads * 8 <= 48 * 1024);
     static constexpr int kMinBlocks = (kSharedCold && S <= 3) ? B200DAE_REG_MINBLOCKS : 1;

@@ -44,7 +44,27 @@ struct RadauLaunch {
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-__device__ __forceinline__ double powi(double x, int k) { return powi32(x, k); }   // 0 <= k < 32
+__device__ __forceinline__ double powi(double x, int k) {                          // 0 <= k < 32
+#if B200DAE_OPT2 & 2
+    // k = newton_max_iter - iteration is the same for every lane still iterating, and < 8 for the
+    // default newton_max_iter = 7 of s = 3: a uniform branch picks the short form
+    if (k < 8) return powi8(x, k);
+#endif
+    return powi32(x, k);
+}
+
+// nextafter(t, dir * inf) for finite t (radau.py:489) on the integer pipe: one step of the bit
+// pattern away from zero when t and dir have the same sign, towards zero otherwise.
+__device__ __forceinline__ double next_toward(double t, double dir) {
+#if B200DAE_FASTMATH_LITE
+    const long long b = __double_as_longlong(t);
+    const bool away = (t > 0.0) == (dir > 0.0);
+    const double nt = __longlong_as_double(b + (away ? 1LL : -1LL));
+    return (t == 0.0) ? copysign(4.9406564584124654e-324, dir) : nt;
+#else
+    return nextafter(t, dir * INFINITY);
+#endif
+}
 
 // predict_factor, radau.py:198-240 (KAPPA = 1).  inv_sp1 = 1 / (s + 1).
 template <int S>
@@ -65,12 +85,41 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
     return 1.0 + atan(factor - 1.0);
 }
 
+#ifndef B200DAE_PF_ROOTS
+#define B200DAE_PF_ROOTS 1
+#endif
+// B200DAE_PF_ROOTS = 1 (s = 3): err ** (1/4) and err ** (-1/4) from one sqrt and one coupled
+// sqrt / rsqrt, and (err_old / err) ** (1/4) as err_old ** (1/4) * err ** (-1/4) with the first
+// factor carried over from the step that produced err_old: 2 root evaluations per attempt
+// instead of 4 and no reciprocal.  `q` returns err ** (1/4) for the caller to keep.
+template <int S>
+__device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old, double err,
+                                                 double err_old, bool have_old, double q_old, double& q) {
+    double mult = 1.0;
+    if constexpr (S == 3 && B200DAE_PF_ROOTS) {
+        double rq;                                   // err ** (-1/4); err == 0 -> inf -> 1 + pi/2
+        q = fast_sqrt_rsqrt(fast_sqrt(err), rq);
+        if (have_old && err != 0.0) mult = h_abs * fast_rcp(h_abs_old) * (q_old * rq);
+        const double factor = fmin(1.0, mult) * rq;
+        return 1.0 + atan(factor - 1.0);
+    }
+    q = 0.0;
+    return predict_factor<S>(h_abs, h_abs_old, err, err_old, have_old);
+}
+
 // kLean: the launch uses the default error estimator (newton_iter_embedded = 1,
 // continuous_error_weight = 0) and asks for neither t_eval output nor a step trace.  Those options
 // are then compiled out, which shrinks the hot kernel (instruction-cache misses were 11 % of the
 // warp stalls of the all-options kernel).
+// B200DAE_REG_MAXNREG (experiments): an explicit register cap instead of the one ptxas derives
+// from the launch bounds (which rounds 7 blocks x 64 threads down to 128 registers).
+#ifdef B200DAE_REG_MAXNREG
+#define B200DAE_RADAU_BOUNDS(T, MB) __maxnreg__(B200DAE_REG_MAXNREG)
+#else
+#define B200DAE_RADAU_BOUNDS(T, MB) __launch_bounds__(T, MB)
+#endif
 template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold, bool kLean, bool kJac = false>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
+__global__ void B200DAE_RADAU_BOUNDS(kThreads, kMinBlocks)
 radau_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
     constexpr int U = Regime<N>::kUnroll;
@@ -123,7 +172,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         if (h_abs * rh > 1.0) h_abs = fast_rcp(rh);
         h_abs = fmax(h_abs, 16.0 * kEps * fabs(L.t0));
     }
-    double h_abs_old = 0.0, err_old = 0.0;
+    double h_abs_old = 0.0, err_old = 0.0, q_old = 0.0;   // q_old = err_old ** (1/4) (B200DAE_PF_ROOTS)
     bool have_old = false, have_sol = false;
     bool need_jac = true;            // first Jacobian in the constructor, base.py:297
     bool current_jac = true;         // radau.py:460 (quirk 7)
@@ -156,7 +205,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     }
 
     // per-step locals that survive across attempts of the same step
-    double hl = 0.0, hl_old = 0.0, errl_old = 0.0, min_step = 0.0, factor = 0.0;
+    double hl = 0.0, hl_old = 0.0, errl_old = 0.0, ql_old = 0.0, min_step = 0.0, factor = 0.0;
     double h = 0.0, t_new = 0.0;
     bool havel_old = false, have_factor = false;
 
@@ -170,11 +219,11 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         }
         // ---- phase B: a new step begins (radau.py:489-512) --------------------------------
         if (step_begin) {
-            min_step = 10.0 * fabs(nextafter(t, dir * INFINITY) - t);
+            min_step = 10.0 * fabs(next_toward(t, dir) - t);
             if (h_abs > L.max_step) { hl = L.max_step; havel_old = false; }
             else if (h_abs < min_step) { hl = min_step; havel_old = false; }
             else { hl = h_abs; havel_old = have_old; }
-            hl_old = h_abs_old; errl_old = err_old;
+            hl_old = h_abs_old; errl_old = err_old; ql_old = q_old;
             have_factor = false;
             step_begin = false;
         }
@@ -194,7 +243,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     for (int j = 0; j < N; ++j) Yp[i][j] = yp[j];
             } else {
                 // extrapolate the previous collocation polynomial's derivative (radau.py:531,693)
-                const double rho = fast_rcp(h_old);
+                const double rho = fast_rcp_nz(h_old);
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
                     const double x = (fma(h, tb.C[i], t) - t_old) * rho;
@@ -441,11 +490,12 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
             }
             error_norm = fast_sqrt(ss * (1.0 / N));
         }
-        const double safety = 0.9 * (2 * newton_max_iter + 1) * fast_rcp((double)(2 * newton_max_iter + n_iter));
+        const double safety = 0.9 * (2 * newton_max_iter + 1) * fast_rcp_nz((double)(2 * newton_max_iter + n_iter));
 
         // one code site for predict_factor: the reject path always needs it, the accept path
         // unless a factor is left over from a rejected attempt of this step (quirk 3)
-        const double pf = predict_factor<S>(hl, hl_old, error_norm, errl_old, havel_old);
+        double q_err;
+        const double pf = predict_factor<S>(hl, hl_old, error_norm, errl_old, havel_old, ql_old, q_err);
         if (error_norm > 1.0) {                    // reject (radau.py:598-603); quirk 8: J is kept
             factor = pf;
             have_factor = true;
@@ -465,6 +515,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         current_jac = recompute_jac;
         h_abs_old = h_abs;                         // quirk 4: the PRE-step proposal
         err_old = error_norm;
+        q_old = q_err;
         have_old = true;
         h_abs = hl * factor;
 
@@ -491,7 +542,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         bool ev_stop = false;
         double y_stop[N], yp_stop[N];
         if (!kLean && L.ev.spec.n_events > 0) {
-            const double rho_e = fast_rcp(h);
+            const double rho_e = fast_rcp_nz(h);
             auto dense_all = [&](double te, double* ya, double* ypa) {     // RadauDenseOutput, radau.py:681-699
                 const double x = (te - t) * rho_e;
                 double pw[S], dpw[S];
@@ -537,7 +588,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         }
         // t_eval points passed by this step (dae.py:496-515; RadauDenseOutput radau.py:681-699)
         if (!kLean && L.out.t_eval != nullptr) {
-            const double rho = fast_rcp(h);
+            const double rho = fast_rcp_nz(h);
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
                 if (!(dir > 0.0 ? te <= t_lim : te >= t_lim)) break;
