@@ -75,3 +75,6 @@ for f, n in ft.most_common():
 print("\n== hottest source lines (by stall samples) ==")
 for (f, l), (n, sm, text) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
     print(f"{f}:{l:<4d} {n / nw:8.0f} {100 * n / tot:5.1f}% smp {100 * sm / max(tots, 1):5.1f}%  {text}")
+print("\n== source lines by instructions executed ==")
+for (f, l), (n, sm, text) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:60]:
+    print(f"{f}:{l:<4d} {n / nw:8.0f} {100 * n / tot:5.1f}% smp {100 * sm / max(tots, 1):5.1f}%  {text}")

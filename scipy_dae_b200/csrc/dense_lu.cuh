@@ -128,19 +128,8 @@ __device__ __forceinline__ void crecip(double pr, double pi, double& rr, double&
     // 1 / (pr + i pi) = conj / |.|^2 with one reciprocal.  When |.|^2 would leave [1e-280, 1e280]
     // (pivots beyond 1e+-140: rare branch) the operands are first rescaled by a power of two,
     // which is what Smith's formula guards against in LAPACK's zladiv.
-#if B200DAE_OPT2 & 4
-    // the guard on the integer pipe: biased exponents of both parts inside [1023 - 465, 1023 + 465]
-    // (1e-140 .. 1e140) take the straight path; everything else (incl. 0, inf, NaN, denormals:
-    // never in a converging solve) the rescaling branch
-    const unsigned er = ((unsigned)__double2hiint(pr) >> 20) & 0x7ffu, ei = ((unsigned)__double2hiint(pi) >> 20) & 0x7ffu;
-    if (__builtin_expect(max(er, ei) - 558u <= 930u, 1)) {
-        const double r = fast_rcp(fma(pr, pr, pi * pi));
-        rr = pr * r; ri = -pi * r;
-        return;
-    }
-#endif
     double sc = 1.0;
-    const double m = fmax(fabs(pr), fabs(pi));
+    const double m = amax_sel(pr, pi);
     if (!(m >= 1e-140 && m <= 1e140)) sc = (m > 1.0) ? 0x1p-600 : ((m > 0.0) ? 0x1p+600 : 1.0);
     const double a = pr * sc, b = pi * sc;
     const double r = fast_rcp(fma(a, a, b * b)) * sc;

@@ -14,6 +14,32 @@
 
 namespace b200dae {
 
+// max / min as one compare and one select.  fmax / fmin compile to an 8-instruction IEEE-754
+// maxNum sequence on sm_100a (DSETP.MAX, moves, FSEL, NaN quieting), and the integrator calls
+// them ~3000 times per Robertson solve (num_jac scales, error scales): 8 % of its instructions.
+// NaN: the SECOND argument is returned when the comparison is unordered, so a NaN there
+// propagates (like np.maximum) and a NaN in the first is dropped; call sites order their
+// arguments accordingly.
+__device__ __forceinline__ double max_sel(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double min_sel(double a, double b) { return (a < b) ? a : b; }
+// max(|a|, |b|)
+__device__ __forceinline__ double amax_sel(double a, double b) {
+    // the select works on the raw words and the sign is cleared on the selected high word, so no
+    // fabs() is materialised on the FP64 pipe (|.| on the compare operands is free)
+    const bool gt = fabs(a) > fabs(b);
+    const int hi = (gt ? __double2hiint(a) : __double2hiint(b)) & 0x7fffffff;
+    const int lo = gt ? __double2loint(a) : __double2loint(b);
+    return __hiloint2double(hi, lo);
+}
+
+// max(|a|, |b|) with the sign of num_jac's f_sign = 2 (f >= 0) - 1 (negative for NaN, positive for -0)
+__device__ __forceinline__ double amax_signed(double a, double b, double f) {
+    const bool gt = fabs(a) > fabs(b);
+    const int hi = ((gt ? __double2hiint(a) : __double2hiint(b)) & 0x7fffffff) | ((f >= 0.0) ? 0 : (int)0x80000000);
+    const int lo = gt ? __double2loint(a) : __double2loint(b);
+    return __hiloint2double(hi, lo);
+}
+
 __device__ __forceinline__ double rcp_seed(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -63,23 +89,16 @@ __device__ __forceinline__ double fast_rcp_nz(double x) {
 
 __device__ __forceinline__ double fast_div(double a, double b) { return a * fast_rcp(b); }
 
-#ifndef B200DAE_OPT2
-#define B200DAE_OPT2 0
-#endif
-
 // sqrt(x), correct for 0, inf, NaN, negative and denormal arguments.
-// Arguments below 1e-200 (denormals would flush in the seed) are rescaled first: by selects in
-// the baseline, by a never-taken branch with B200DAE_OPT2 (6 instructions less per call; the
-// integrator's arguments are error norms, which are either 0 or far above 1e-200).
+// Arguments below 1e-200 (denormals would flush in the seed) are rescaled first, by selects.
+// (Tried on B200: a never-taken branch for that case instead of the selects, 6 instructions
+// less per call: 13.83 ms instead of 13.61 ms per 2^20 Robertson solves.  The same happened with
+// a uniform branch to a 3-bit powi for newton_max_iter - k < 8 (13.71 ms) and with an integer
+// exponent guard + branch in crecip (13.76 ms): every extra basic-block boundary costs the
+// scheduler more than the instructions it saves, so the straight-line forms stay.)
 __device__ __forceinline__ double fast_sqrt(double x) {
-#if B200DAE_OPT2 & 1
-    if (__builtin_expect(x < 1e-200 && x > 0.0, 0)) return sqrt(x);
-    const double xs = x;
-    constexpr bool tiny = false;
-#else
     const bool tiny = x < 1e-200;
     const double xs = tiny ? x * 0x1p+600 : x;              // also normalises denormals
-#endif
     const double r0 = rsqrt_seed(xs);
     double g = xs * r0, h = 0.5 * r0;
     double e = fma(-h, g, 0.5);
@@ -99,14 +118,8 @@ __device__ __forceinline__ double fast_sqrt(double x) {
 // sqrt(x) and 1/sqrt(x) from one refinement (the coupled iteration carries h ~ 1/(2 sqrt x)).
 // For x = 0 returns (0, inf); for x = inf (inf, 0); NaN / negative -> NaN.
 __device__ __forceinline__ double fast_sqrt_rsqrt(double x, double& rsq) {
-#if B200DAE_OPT2 & 1
-    if (__builtin_expect(x < 1e-200 && x > 0.0, 0)) { const double g0 = sqrt(x); rsq = 1.0 / g0; return g0; }
-    const double xs = x;
-    constexpr bool tiny = false;
-#else
     const bool tiny = x < 1e-200;
     const double xs = tiny ? x * 0x1p+600 : x;
-#endif
     const double r0 = rsqrt_seed(xs);
     double g = xs * r0, h = 0.5 * r0;
     double e = fma(-h, g, 0.5);
@@ -133,15 +146,6 @@ __device__ __forceinline__ double powi32(double x, int k) {
     r *= (k & 4) ? x4 : 1.0;
     r *= (k & 8) ? x8 : 1.0;
     r *= (k & 16) ? x16 : 1.0;
-    return r;
-}
-
-// x ** k for 0 <= k < 8
-__device__ __forceinline__ double powi8(double x, int k) {
-    const double x2 = x * x, x4 = x2 * x2;
-    double r = (k & 1) ? x : 1.0;
-    r *= (k & 2) ? x2 : 1.0;
-    r *= (k & 4) ? x4 : 1.0;
     return r;
 }
 

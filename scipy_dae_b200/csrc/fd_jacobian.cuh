@@ -57,7 +57,7 @@ __device__ __forceinline__ void fd_column(double t, double* __restrict__ y, doub
         if (a > best || (a != a && best == best)) { best = a; f_at = f[r]; fn_at = fnew[r]; d_at = dr; }
     }
     max_diff = fabs(d_at);
-    scale = fmax(fabs(f_at), fabs(fn_at));
+    scale = amax_sel(f_at, fn_at);
     if (f_at != f_at || fn_at != fn_at) scale = nan("");
 }
 
@@ -97,11 +97,10 @@ __device__ __forceinline__ void analytic_jacobian(double t, const double* __rest
 // Same arithmetic per column as the reference's vectorised num_jac, which also evaluates all
 // first attempts before any second one (SP/common.py:330-371).
 //
-// Reduction of a column: only max_diff and scale leave it, so the running argmax carries
-// (|diff|, max(|f|, |f_new|)) instead of (f, f_new, diff) at the maximal row.  np.argmax returns
-// the first NaN if there is one (max_diff = NaN: no second attempt, no factor update); that case
-// is restored by max_diff = best + 0 * (sum of the differences), NaN exactly when a difference
-// is non-finite (then J is non-finite and the solve ends with B200DAE_ST_NONFINITE either way).
+// Reduction of a column: only max_diff and scale leave it.  np.argmax returns the first NaN if
+// there is one (max_diff = NaN: no second attempt, no factor update); that case is restored by
+// max_diff = |best| + 0 * (sum of the other differences), NaN exactly when a difference is
+// non-finite (then J is non-finite and the solve ends with B200DAE_ST_NONFINITE either way).
 template <class P>
 __device__ __forceinline__ void fd_probe(double t, const double* __restrict__ y, const double* __restrict__ yp,
                                          const double* __restrict__ p, const double* __restrict__ f,
@@ -115,49 +114,36 @@ __device__ __forceinline__ void fd_probe(double t, const double* __restrict__ y,
         yyp[j] = (col == N + j) ? xp : yp[j];
     }
     P::eval(t, yy, yyp, p, fnew);
-    double best = 0.0, s_at = 0.0, sum = 0.0;
+    // running argmax on the raw differences (|.| is a free operand modifier of the compare; a
+    // materialised fabs() is one more FP64 instruction per row), carrying f and f_new of that row
+    double bd = 0.0, f_at = 0.0, fn_at = 0.0, sum = 0.0;
 #pragma unroll
     for (int r = 0; r < N; ++r) {
         const double dr = fnew[r] - f[r];
         diff[r] = dr;
-        sum += dr;
-        const double a = fabs(dr);
-        const double s = fmax(fabs(f[r]), fabs(fnew[r]));
-        if (r == 0 || a > best) { best = a; s_at = s; }
+        if (r == 0) { bd = dr; f_at = f[r]; fn_at = fnew[r]; }
+        else {
+            sum += dr;                       // a NaN in row 0 already sticks to bd
+            if (fabs(dr) > fabs(bd)) { bd = dr; f_at = f[r]; fn_at = fnew[r]; }
+        }
     }
-    max_diff = fma(0.0, sum, best);
-    scale = s_at;
+    max_diff = fma(0.0, sum, fabs(bd));
+    scale = amax_sel(f_at, fn_at);
 }
 
-#ifndef B200DAE_FD_STAGE
-#define B200DAE_FD_STAGE 0
-#endif
-// B200DAE_FD_STAGE = 1: the differences of a column wait in their slots of Jy / Jyp (shared
-// memory in the register regime) instead of in registers until the quotients are formed.
 template <class P, class V, int C0, int C1>
 __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y, const double* __restrict__ yp,
                                          const double* __restrict__ p, const double* __restrict__ thr,
                                          const double* __restrict__ f,
                                          V factor_y, V factor_yp, V Jy, V Jyp) {
     constexpr int N = P::N, NC = C1 - C0;
-    constexpr bool kStage = (B200DAE_FD_STAGE != 0);
-    double fac[NC], ysc[NC], h[NC], xp[NC], diff[kStage ? 1 : NC][N], md[NC], sc[NC];
-    auto stash = [&](int c, const double* d) {
-        const int col = C0 + c, i = col % N;
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-            if (!kStage) diff[kStage ? 0 : c][r] = d[r];
-            else if (col >= N) Jyp[r * N + i] = d[r];
-            else Jy[r * N + i] = d[r];
-        }
-    };
+    double fac[NC], ysc[NC], h[NC], xp[NC], diff[NC][N], md[NC], sc[NC];
     bool any_zero = false;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const int col = C0 + c, i = col % N;
         const double xi = (col >= N) ? yp[i] : y[i];
-        const double f_sign = (f[i] >= 0.0) ? 1.0 : -1.0;
-        ysc[c] = f_sign * fmax(thr[i], fabs(xi));
+        ysc[c] = amax_signed(thr[i], xi, f[i]);            // f_sign * max(thr, |x|), thr > 0
         fac[c] = (col >= N) ? factor_yp[i] : factor_y[i];
         xp[c] = fma(fac[c], ysc[c], xi);
         h[c] = xp[c] - xi;
@@ -176,11 +162,7 @@ __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y,
         }
     }
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        double d1[N];
-        fd_probe<P>(t, y, yp, p, f, C0 + c, xp[c], d1, md[c], sc[c]);
-        stash(c, d1);
-    }
+    for (int c = 0; c < NC; ++c) fd_probe<P>(t, y, yp, p, f, C0 + c, xp[c], diff[c], md[c], sc[c]);
     // second attempt with 10 * factor where the difference drowns in round-off (SP/common.py:350-371)
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -195,7 +177,8 @@ __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y,
             if (md[c] * sc2 < md2 * sc[c]) {
                 fac[c] = fac2;
                 h[c] = h2;
-                stash(c, d2);
+#pragma unroll
+                for (int r = 0; r < N; ++r) diff[c][r] = d2[r];
                 sc[c] = sc2;
                 md[c] = md2;
             }
@@ -207,13 +190,13 @@ __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y,
         const double rh = fast_rcp(h[c]);     // h = inf (a factor that grew for 300+ refreshes on an algebraic column) -> 0
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-            if (col >= N) Jyp[r * N + i] = (kStage ? Jyp[r * N + i] : diff[kStage ? 0 : c][r]) * rh;
-            else Jy[r * N + i] = (kStage ? Jy[r * N + i] : diff[kStage ? 0 : c][r]) * rh;
+            if (col >= N) Jyp[r * N + i] = diff[c][r] * rh;
+            else Jy[r * N + i] = diff[c][r] * rh;
         }
         double fc = fac[c];
         if (md[c] < kNjDiffSmall * sc[c]) fc *= 10.0;
         if (md[c] > kNjDiffBig * sc[c]) fc *= 0.1;
-        fc = fmax(fc, kNjMinFactor);
+        fc = max_sel(kNjMinFactor, fc);
         if (col >= N) factor_yp[i] = fc;
         else factor_y[i] = fc;
     }
@@ -261,7 +244,7 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
         for (int i = 0; i < N; ++i) {
             const double xi = x[i];
             const double f_sign = (f[i] >= 0.0) ? 1.0 : -1.0;
-            const double y_scale = f_sign * fmax(thr[i], fabs(xi));
+            const double y_scale = f_sign * amax_sel(thr[i], xi);   // thr > 0
             double fac = factor[i];
             double xp = fma(fac, y_scale, xi);
             double h = xp - xi;
@@ -297,7 +280,7 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
             for (int r = 0; r < N; ++r) J[r * N + i] = diff[r] * rh;
             if (max_diff < kNjDiffSmall * scale) fac *= 10.0;
             if (max_diff > kNjDiffBig * scale) fac *= 0.1;
-            factor[i] = fmax(fac, kNjMinFactor);
+            factor[i] = max_sel(kNjMinFactor, fac);
         }
     }
 }

@@ -44,14 +44,7 @@ struct RadauLaunch {
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-__device__ __forceinline__ double powi(double x, int k) {                          // 0 <= k < 32
-#if B200DAE_OPT2 & 2
-    // k = newton_max_iter - iteration is the same for every lane still iterating, and < 8 for the
-    // default newton_max_iter = 7 of s = 3: a uniform branch picks the short form
-    if (k < 8) return powi8(x, k);
-#endif
-    return powi32(x, k);
-}
+__device__ __forceinline__ double powi(double x, int k) { return powi32(x, k); }   // 0 <= k < 32
 
 // nextafter(t, dir * inf) for finite t (radau.py:489) on the integer pipe: one step of the bit
 // pattern away from zero when t and dir have the same sign, towards zero otherwise.
@@ -81,7 +74,7 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
     // err_old / err and h_abs / h_abs_old share one reciprocal each; err == 0 -> factor = inf -> 1 + pi/2
     const double r_err = fast_rcp(err);
     if (have_old && err != 0.0) mult = h_abs * fast_rcp(h_abs_old) * root_sp1<S>(err_old * r_err);
-    const double factor = fmin(1.0, mult) * root_sp1<S>(r_err);
+    const double factor = min_sel(mult, 1.0) * root_sp1<S>(r_err);     // min(1, nan) = 1 like Python's min
     return 1.0 + atan(factor - 1.0);
 }
 
@@ -100,7 +93,7 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
         double rq;                                   // err ** (-1/4); err == 0 -> inf -> 1 + pi/2
         q = fast_sqrt_rsqrt(fast_sqrt(err), rq);
         if (have_old && err != 0.0) mult = h_abs * fast_rcp(h_abs_old) * (q_old * rq);
-        const double factor = fmin(1.0, mult) * rq;
+        const double factor = min_sel(mult, 1.0) * rq;
         return 1.0 + atan(factor - 1.0);
     }
     q = 0.0;
@@ -378,7 +371,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     // c = dY_norm / (1 - rate).  quirk 2: the rate test breaks AFTER the update.
                     rate = dY_norm * inv_norm_old;
                     have_rate = true;
-                    const double c = dY_norm * fast_rcp(1.0 - rate);
+                    const double c = dY_norm * fast_rcp_nz(1.0 - rate);   // only used when rate < 1
                     if (rate >= 1.0 || powi(rate, newton_max_iter - k) * c > L.newton_tol) break;
                     if (dY_norm == 0.0 || rate * c < L.newton_tol) { converged = true; break; }
                 } else if (dY_norm == 0.0) {
@@ -484,7 +477,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     for (int l = 0; l < S; ++l) acc = fma(tb.P2row0[l], Y[l][j], acc);
                     e = fma(w, pow(fabs(y[j] - acc), (S + 1.0) / S), e);
                 }
-                const double sc = fma(fmax(fabs(y[j]), fabs(Y[S - 1][j])), rtol, L.atol[j]);
+                const double sc = fma(amax_sel(y[j], Y[S - 1][j]), rtol, L.atol[j]);
                 const double q = e * fast_rcp(sc);
                 ss = fma(q, q, ss);
             }

@@ -96,7 +96,7 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
         const double* xs = wrt_yp ? syp : sy;
         const double xi = act ? (wrt_yp ? ypj : yj) : xs[0];
         const double f_sign = (sf[cc] >= 0.0) ? 1.0 : -1.0;
-        const double y_scale = f_sign * fmax(thr_j, fabs(xi));
+        const double y_scale = f_sign * amax_sel(thr_j, xi);
         double fac = wrt_yp ? fac_yp : fac_y;
         double xp = fma(fac, y_scale, xi);
         double h = xp - xi;
@@ -124,7 +124,7 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
                     if (a > best || (a != a && best == best)) { best = a; f_at = fr; fn_at = fn; d_at = dr; }
                 }
                 const double md2 = fabs(d_at);
-                double sc2 = fmax(fabs(f_at), fabs(fn_at));
+                double sc2 = amax_sel(f_at, fn_at);
                 if (f_at != f_at || fn_at != fn_at) sc2 = nan("");
                 if (attempt == 0 || max_diff * sc2 < md2 * scale) {
                     fac = fac_try;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
             for (int r = 0; r < N; ++r) J[r * LD + c] = (fsel[r] - sf[r]) * rh;
             if (max_diff < kNjDiffSmall * scale) fac *= 10.0;
             if (max_diff > kNjDiffBig * scale) fac *= 0.1;
-            fac = fmax(fac, kNjMinFactor);
+            fac = max_sel(kNjMinFactor, fac);
             if (wrt_yp) fac_yp = fac; else fac_y = fac;
         }
     }
@@ -511,7 +511,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                 for (int l = 0; l < S; ++l) acc = fma(tb.P2row0[l], Y[l], acc);
                 e = fma(w, pow(fabs(y - acc), (S + 1.0) / S), e);
             }
-            const double sc = fma(fmax(fabs(y), fabs(Y[S - 1])), rtol, atol_j);
+            const double sc = fma(amax_sel(y, Y[S - 1]), rtol, atol_j);
             const double q = e * fast_rcp(sc);
             const double ss = g.sum(act ? q * q : 0.0);
             error_norm = fast_sqrt(ss * (1.0 / N));
