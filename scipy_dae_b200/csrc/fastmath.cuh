@@ -96,8 +96,20 @@ __device__ __forceinline__ double fast_div(double a, double b) { return a * fast
 // a uniform branch to a 3-bit powi for newton_max_iter - k < 8 (13.71 ms) and with an integer
 // exponent guard + branch in crecip (13.76 ms): every extra basic-block boundary costs the
 // scheduler more than the instructions it saves, so the straight-line forms stay.)
+//
+// kTiny = false drops the rescaling: arguments in (0, 1e-200) may then come back as 0 (and 1/sqrt
+// as inf).  For callers to which "below 1e-100" and "zero" mean the same (an error norm that only
+// feeds predict_factor, where both saturate at 1 + pi/2).
+//
+// positive, normal and finite <=> biased exponent in [1, 0x7fe] with a clear sign bit: one
+// subtraction and one unsigned compare on the high word.
+__device__ __forceinline__ bool pos_normal(double xs) {
+    return (unsigned)(__double2hiint(xs) - 0x00100000) < 0x7fe00000u;
+}
+
+template <bool kTiny = true>
 __device__ __forceinline__ double fast_sqrt(double x) {
-    const bool tiny = x < 1e-200;
+    const bool tiny = kTiny && x < 1e-200;
     const double xs = tiny ? x * 0x1p+600 : x;              // also normalises denormals
     const double r0 = rsqrt_seed(xs);
     double g = xs * r0, h = 0.5 * r0;
@@ -112,13 +124,15 @@ __device__ __forceinline__ double fast_sqrt(double x) {
     const double d = fma(-g, g, xs);
     g = fma(d, h, g);
     g = tiny ? g * 0x1p-300 : g;
-    return (xs > 0.0 && xs < INFINITY) ? g : ((x < 0.0) ? nan("") : x);
+    if (!kTiny) return pos_normal(xs) ? g : ((x < 0.0) ? nan("") : ((x < 1.0) ? 0.0 : x));
+    return pos_normal(xs) ? g : ((x < 0.0) ? nan("") : x);
 }
 
 // sqrt(x) and 1/sqrt(x) from one refinement (the coupled iteration carries h ~ 1/(2 sqrt x)).
 // For x = 0 returns (0, inf); for x = inf (inf, 0); NaN / negative -> NaN.
+template <bool kTiny = true>
 __device__ __forceinline__ double fast_sqrt_rsqrt(double x, double& rsq) {
-    const bool tiny = x < 1e-200;
+    const bool tiny = kTiny && x < 1e-200;
     const double xs = tiny ? x * 0x1p+600 : x;
     const double r0 = rsqrt_seed(xs);
     double g = xs * r0, h = 0.5 * r0;
@@ -132,7 +146,12 @@ __device__ __forceinline__ double fast_sqrt_rsqrt(double x, double& rsq) {
     g = fma(d, h, g);
     e = fma(-h, g, 0.5);
     h = fma(h, e, h);
-    const bool ok = (xs > 0.0 && xs < INFINITY);
+    const bool ok = pos_normal(xs);
+    if (!kTiny) {
+        // denormal x: the seed flushed it to zero and returned inf, which is the x = 0 answer
+        rsq = ok ? 2.0 * h : ((x < 0.0) ? nan("") : r0);
+        return ok ? g : ((x < 0.0) ? nan("") : ((x < 1.0) ? 0.0 : x));
+    }
     rsq = ok ? (tiny ? 2.0 * h * 0x1p+300 : 2.0 * h) : ((x < 0.0) ? nan("") : r0);
     g = tiny ? g * 0x1p-300 : g;
     return ok ? g : ((x < 0.0) ? nan("") : x);

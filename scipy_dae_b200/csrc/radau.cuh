@@ -91,7 +91,7 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
     double mult = 1.0;
     if constexpr (S == 3 && B200DAE_PF_ROOTS) {
         double rq;                                   // err ** (-1/4); err == 0 -> inf -> 1 + pi/2
-        q = fast_sqrt_rsqrt(fast_sqrt(err), rq);
+        q = fast_sqrt_rsqrt<false>(fast_sqrt<false>(err), rq);   // err < 1e-200 acts like err = 0: same limit
         if (have_old && err != 0.0) mult = h_abs * fast_rcp(h_abs_old) * (q_old * rq);
         const double factor = min_sel(mult, 1.0) * rq;
         return 1.0 + atan(factor - 1.0);
@@ -274,13 +274,13 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
 #pragma unroll U
                 for (int k = 0; k < N * N; ++k) {
                     const double vr = fma(mr, Jy[k], Jyp[k]), vi = mi * Jy[k];
-                    fin.add(vr);
-                    fin.add(vi);
                     (LUcr0 + c * N * N)[k] = vr;
                     (LUci0 + c * N * N)[k] = vi;
                 }
             }
-            if (!fin.all_finite()) { status = B200DAE_ST_NONFINITE; break; }   // lu_factor(check_finite=True) raises
+            // lu_factor(check_finite=True) raises.  Checked on the real matrix only: a non-finite
+            // entry of Jy or Jyp shows up there (or as inf - inf = NaN), and |mu_complex| < mu_real
+            if (!fin.all_finite()) { status = B200DAE_ST_NONFINITE; break; }
             lu_factor<N>(LUr, pivr);
 #pragma unroll
             for (int c = 0; c < NCS; ++c) zlu_factor<N>(LUcr0 + c * N * N, LUci0 + c * N * N, pivc[c]);
@@ -481,7 +481,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 const double q = e * fast_rcp(sc);
                 ss = fma(q, q, ss);
             }
-            error_norm = fast_sqrt(ss * (1.0 / N));
+            error_norm = fast_sqrt<false>(ss * (1.0 / N));   // only compared with 1 and fed to predict_factor
         }
         const double safety = 0.9 * (2 * newton_max_iter + 1) * fast_rcp_nz((double)(2 * newton_max_iter + n_iter));
 
