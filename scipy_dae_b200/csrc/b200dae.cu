@@ -180,6 +180,13 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
     if (!(opts->deadband_lo > 0 && opts->deadband_lo <= opts->deadband_hi))
         return fail(B200DAE_EINVAL, "need 0 < controller_deadband[0] <= controller_deadband[1]%s", "");
     if (opts->newton_iter_embedded < 0) return fail(B200DAE_EINVAL, "need newton_iter_embedded >= 0%s", "");
+    // The thread-per-system kernel relies on the normalisation of the reference's eigen-transformation
+    // (radau.py:72-84): eigenvectors scaled to a unit last row, so T[s-1] = (1, 0, 1, 0, ..., 1), and
+    // on a dense first row of TI (a non-finite stage residual then shows in TI[0] @ F).
+    for (int l = 0; l < s; ++l) {
+        if (tb->T[(s - 1) * s + l] != ((l % 2 == 0) ? 1.0 : 0.0) || tb->TI[l] == 0.0)
+            return fail(B200DAE_EINVAL, "Radau tables are not in the reference's normalisation (radau.py:72-84)%s", "");
+    }
     if (N == 0) return 0;
 
     RadauLaunch L;
@@ -199,6 +206,7 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
         const double expmns = (s + 1.0) / (2.0 * s);                           // radau.py:422-433
         L.newton_tol = fmax(10 * kEps / L.rtol, fmin(0.03, pow(L.rtol, 1.0 / expmns - 1)));
     }
+    L.inv_mu_real = 1.0 / tb->mu_real;
     for (int j = 0; j < e->n; ++j) { L.atol[j] = atol[j]; L.thr[j] = atol[j] / L.rtol; }
     L.newton_max_iter = opts->newton_max_iter > 0 ? opts->newton_max_iter
                                                   : 7 + (int)((s - 3) * 2.5);  // radau.py:440-441

@@ -131,11 +131,11 @@ __device__ __forceinline__ void fd_probe(double t, const double* __restrict__ y,
     scale = amax_sel(f_at, fn_at);
 }
 
-template <class P, class V, int C0, int C1>
+template <class P, class V, class VJ, int C0, int C1>
 __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y, const double* __restrict__ yp,
                                          const double* __restrict__ p, const double* __restrict__ thr,
                                          const double* __restrict__ f,
-                                         V factor_y, V factor_yp, V Jy, V Jyp) {
+                                         V factor_y, V factor_yp, VJ Jy, VJ Jyp) {
     constexpr int N = P::N, NC = C1 - C0;
     double fac[NC], ysc[NC], h[NC], xp[NC], diff[NC][N], md[NC], sc[NC];
     bool any_zero = false;
@@ -218,20 +218,20 @@ __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y,
 // Jacobian the same launch takes 10.9 ms); the second attempt is not rare either: a column of
 // Jyp that belongs to an algebraic variable has diff = 0 and always takes it (16.4 % of the
 // Robertson columns, counted with the CPU oracle).
-template <class P, class V>
+template <class P, class V, class VJ = V>
 __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, double* __restrict__ yp,
                                             const double* __restrict__ p, const double* __restrict__ thr,
-                                            V factor_y, V factor_yp, V Jy, V Jyp) {
+                                            V factor_y, V factor_yp, VJ Jy, VJ Jyp) {
     constexpr int N = P::N;
     constexpr int U = Regime<N>::kUnroll;
     double f[N];
     P::eval(t, y, yp, p, f);
     if constexpr (Regime<N>::kReg && B200DAE_FD_BATCH == 2) {
-        fd_batch<P, V, 0, 2 * N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
+        fd_batch<P, V, VJ, 0, 2 * N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
         return;
     } else if constexpr (Regime<N>::kReg && B200DAE_FD_BATCH == 1) {
-        fd_batch<P, V, 0, N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
-        fd_batch<P, V, N, 2 * N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
+        fd_batch<P, V, VJ, 0, N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
+        fd_batch<P, V, VJ, N, 2 * N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
         return;
     }
 #pragma unroll U
@@ -239,7 +239,7 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
         const bool wrt_yp = (which == 1);
         const double* x = wrt_yp ? yp : y;
         V factor = wrt_yp ? factor_yp : factor_y;
-        V J = wrt_yp ? Jyp : Jy;
+        VJ J = wrt_yp ? Jyp : Jy;
 #pragma unroll U
         for (int i = 0; i < N; ++i) {
             const double xi = x[i];

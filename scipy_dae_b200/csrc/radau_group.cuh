@@ -475,7 +475,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                     double acc = 0.0;
 #pragma unroll
                     for (int l = 0; l < S; ++l) acc = fma(tb.v_implicit[l], Yp[l], acc);
-                    yph0 = (acc - tb.b_hat1_implicit * yp) * fast_rcp(tb.mu_real);
+                    yph0 = (acc - tb.b_hat1_implicit * yp) * L.inv_mu_real;
                 } else {
                     double acc = 0.0;
 #pragma unroll
