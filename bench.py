@@ -58,7 +58,9 @@ def parse_args():
                     help="also time the ensemble with dense output at this many t_eval points (0 = skip)")
     ap.add_argument("--e2e-no-graph", action="store_true",
                     help="queue the host pipeline eagerly instead of replaying its CUDA graph")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline chunks of the host-facing call")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="pipeline chunks of the host-facing call")
+    ap.add_argument("--e2e-no-taper", action="store_true", help="equal chunk sizes in the host pipeline")
+    ap.add_argument("--e2e-streams", type=int, default=3, help="compute streams of the host pipeline")
     return ap.parse_args()
 
 
@@ -354,7 +356,8 @@ def main():
     def e2e_step():
         return solve_dae_batched_host("robertson", WORKLOAD["t_span"], h_y0, h_yp0, h_params, method="Radau",
                                       rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], device=dev,
-                                      chunks=args.e2e_chunks, out=host_out, use_graph=e2e_graph,
+                                      chunks=args.e2e_chunks, n_streams=args.e2e_streams,
+                                      taper=not args.e2e_no_taper, out=host_out, use_graph=e2e_graph,
                                       jac="analytic" if args.jac == "analytic" else None)
 
     try:
@@ -478,7 +481,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
                     "timer": "host perf_counter bracketed by cuda synchronize",
-                    "api": f"solve_dae_batched_host(chunks={args.e2e_chunks}, use_graph={e2e_graph}), "
+                    "api": f"solve_dae_batched_host(chunks={args.e2e_chunks}, n_streams={args.e2e_streams}, "
+                           f"taper={not args.e2e_no_taper}, use_graph={e2e_graph}), "
                            "pinned host inputs and outputs",
                     "ms_each": [round(x, 3) for x in e2e_ms], "cpu_affinity": affinity},
             "gpu_launches": int(gpu_launches),

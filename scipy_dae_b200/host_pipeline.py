@@ -61,52 +61,107 @@ def _as_host(x, name):
     return t.contiguous()
 
 
+class _Streams:
+    """Streams of one pipeline: `feed` (host->device copies + AoS->SoA relayout of every chunk) and
+    `drain` (SoA->AoS relayout + device->host copies) have HIGH priority, the `compute` streams
+    that carry the integrator kernels the default one.
+
+    Why priorities (measured with scripts/e2e_timeline.py): the small relayout kernels that follow
+    the integrator kernel of chunk c used to queue behind every pending block of the integrator
+    kernels of chunks c+1, c+2 (the block scheduler serves kernels in launch order), so the
+    device->host copy of chunk 0 only started after 4 ms, the stream's next host->device copy
+    waited behind it, and the SMs idled 0.3 ms between chunks.  On a high-priority stream those
+    kernels are dispatched as soon as any block slot frees up."""
+
+    def __init__(self, device, n_compute: int):
+        lo, hi = 0, -1                                    # CUDA: lower number = higher priority
+        self.feed = torch.cuda.Stream(device=device, priority=hi)
+        self.drain = torch.cuda.Stream(device=device, priority=hi)
+        self.compute = [torch.cuda.Stream(device=device, priority=lo) for _ in range(n_compute)]
+
+    def all(self):
+        return [self.feed, self.drain, *self.compute]
+
+
 def _enqueue(prob, t_span, h_y0, h_yp0, h_p, method, rtol, atol, device, bounds, streams, out,
              check_finite, options):
-    """Queue the whole pipeline (no host synchronisation): per chunk, on its stream, H2D ->
-    relayout -> integrator kernel -> relayout -> D2H.  Returns the device flag `inputs finite`
-    (or None) and the tensors that must outlive the queued work."""
+    """Queue the whole pipeline (no host synchronisation).  feed: every chunk's H2D + relayout, in
+    chunk order, not waiting for anything; compute[c % k]: the integrator kernel of chunk c once its
+    inputs are there; drain: relayout + D2H of chunk c once its kernel is done.  Returns the
+    device flag `inputs finite` (or None) and the tensors that must outlive the queued work."""
     main = torch.cuda.current_stream(device)
-    for s in streams:
+    for s in streams.all():
         s.wait_stream(main)
-    flags, keep = [], []
-    for c in range(len(bounds) - 1):
-        lo, hi = int(bounds[c]), int(bounds[c + 1])
-        if hi <= lo:
-            continue
-        s = streams[c % len(streams)]
+    flags, keep, staged = [], [], []
+    with torch.cuda.stream(streams.feed):
+        for c in range(len(bounds) - 1):
+            lo, hi = int(bounds[c]), int(bounds[c + 1])
+            if hi <= lo:
+                continue
+            soa = [h[lo:hi].to(device, non_blocking=True).t().contiguous() for h in (h_y0, h_yp0, h_p)]
+            if check_finite:
+                flags.append(torch.isfinite(soa[0]).all() & torch.isfinite(soa[1]).all())
+            ev = torch.cuda.Event()
+            ev.record(streams.feed)
+            staged.append((lo, hi, soa, ev))
+    keep.append(staged)
+    for c, (lo, hi, soa, ev) in enumerate(staged):
+        s = streams.compute[c % len(streams.compute)]
+        s.wait_event(ev)
         with torch.cuda.stream(s):
-            r = solve_dae_batched(prob, t_span, h_y0[lo:hi], h_yp0[lo:hi], h_p[lo:hi], method=method,
+            # [N, width] views of the SoA tensors: solve_dae_batched's own relayout is then a no-op
+            r = solve_dae_batched(prob, t_span, soa[0].t(), soa[1].t(), soa[2].t(), method=method,
                                   rtol=rtol, atol=atol, device=device, stream=s, check_finite=False,
                                   **options)
-            if check_finite:
-                yd, ypd, _ = r.extra["_keepalive"]
-                flags.append(torch.isfinite(yd).all() & torch.isfinite(ypd).all())
+            done = torch.cuda.Event()
+            done.record(s)
+        streams.drain.wait_event(done)
+        with torch.cuda.stream(streams.drain):
             out.y_final[lo:hi].copy_(r.y_final.contiguous(), non_blocking=True)
             out.yp_final[lo:hi].copy_(r.yp_final.contiguous(), non_blocking=True)
             out.t_final[lo:hi].copy_(r.t_final, non_blocking=True)
             out.status[lo:hi].copy_(r.status, non_blocking=True)
             cnt = torch.stack([getattr(r, k) for k in _COUNTERS], dim=1)
             out.counters[lo:hi].copy_(cnt, non_blocking=True)
-            keep.append(r)
-    for s in streams:
+        keep.append((r, cnt, done))
+    for s in streams.all():
         main.wait_stream(s)
     ok = torch.stack(flags).all() if flags else None
+    if ok is not None:
+        keep.append(flags)
     return ok, keep
+
+
+def _chunk_bounds(N: int, chunks: int, taper: bool) -> np.ndarray:
+    """Chunk boundaries on the instance axis.  With `taper` the first and the last chunk are a
+    quarter (and their neighbours three quarters) of the interior ones: the host->device copy
+    of the first chunk and the device->host copy of the last one are the only transfers no kernel
+    hides, so they are kept short."""
+    if not taper or chunks < 5:
+        return np.linspace(0, N, chunks + 1).astype(np.int64)
+    w = np.ones(chunks)
+    w[0] = w[-1] = 0.25
+    w[1] = w[-2] = 0.75
+    edges = np.concatenate([[0.0], np.cumsum(w) / w.sum()])
+    b = np.round(edges * N).astype(np.int64)
+    b[-1] = N
+    return b
 
 
 _GRAPHS: dict = {}
 
 
 def solve_dae_batched_host(problem, t_span, y0, yp0, params, method="Radau", rtol=1e-3, atol=1e-6, *,
-                           device=None, chunks: int = 8, n_streams: int = 3,
+                           device=None, chunks: int = 16, n_streams: int = 3,
                            out: Optional[HostResultBuffers] = None, check_finite: bool = True,
-                           use_graph: bool = False, **options) -> BatchedDaeResult:
+                           use_graph: bool = False, taper: bool = True, **options) -> BatchedDaeResult:
     """Integrate ``N`` instances held in host memory; returns host (pinned) tensors.
 
     y0, yp0 : [N, n], params : [N, p]   NumPy arrays or CPU tensors (pinned memory makes the
                                         copies asynchronous)
-    chunks, n_streams                   pipeline shape; ``chunks=1`` is the unpipelined call
+    chunks, n_streams                   pipeline shape (``n_streams`` compute streams besides the
+                                        feed and drain streams); ``chunks=1`` is the unpipelined call
+    taper                               short first / last chunks (see ``_chunk_bounds``)
     out                                 reusable result buffers (``alloc_host_result``)
     use_graph                           capture the whole pipeline (copies, relayouts, kernels) in
                                         ONE CUDA graph, cached for this set of pinned input /
@@ -138,24 +193,24 @@ def solve_dae_batched_host(problem, t_span, y0, yp0, params, method="Radau", rto
     if out is None:
         out = alloc_host_result(N, n)
     chunks = max(1, min(int(chunks), N)) if N > 0 else 1
-    bounds = np.linspace(0, N, chunks + 1).astype(np.int64)
+    bounds = _chunk_bounds(N, chunks, taper)
     nstr = max(1, min(n_streams, chunks))
     with torch.cuda.device(device):
         main = torch.cuda.current_stream(device)
         if not use_graph:
-            streams = [torch.cuda.Stream(device=device) for _ in range(nstr)]
+            streams = _Streams(device, nstr)
             ok, keep = _enqueue(prob, t_span, h_y0, h_yp0, h_p, method, rtol, atol, device, bounds,
                                 streams, out, check_finite, options)
             main.synchronize()
         else:
             key = (prob.name, tuple(map(float, t_span)), method, float(rtol), np.asarray(atol, dtype=float).tobytes(),
-                   str(device), chunks, nstr, check_finite, tuple(sorted((k, repr(v)) for k, v in options.items())),
+                   str(device), chunks, nstr, bool(taper), check_finite, tuple(sorted((k, repr(v)) for k, v in options.items())),
                    h_y0.data_ptr(), h_yp0.data_ptr(), h_p.data_ptr(), N,
                    out.y_final.data_ptr(), out.yp_final.data_ptr(), out.t_final.data_ptr(),
                    out.status.data_ptr(), out.counters.data_ptr())
             entry = _GRAPHS.get(key)
             if entry is None:
-                streams = [torch.cuda.Stream(device=device) for _ in range(nstr)]
+                streams = _Streams(device, nstr)
                 # one eager pass first: warms the allocator and any per-kernel attribute set-up
                 _enqueue(prob, t_span, h_y0, h_yp0, h_p, method, rtol, atol, device, bounds, streams, out,
                          check_finite, options)
