@@ -469,9 +469,16 @@ def main():
     total_ms, e2e_total_ms = float(t_all[0]), float(t_all[1])
 
     # one gather of the results (rank 0 receives every rank's final states), timed separately
-    gather_ms = None
+    gather_ms = gather_first_ms = None
     if world > 1:
         parts = [torch.empty_like(y_final) for _ in range(world)] if rank == 0 else None
+        # the first NCCL gather also sets up the peer-to-peer channels of every (rank, 0) pair
+        # (0.16 / 0.48 / 1.8 s at 2 / 4 / 8 GPUs, once per process): reported apart from the steady one
+        barrier()
+        t0 = time.perf_counter()
+        dist.gather(y_final, parts, dst=0)
+        torch.cuda.synchronize(dev)
+        gather_first_ms = 1e3 * (time.perf_counter() - t0)
         barrier()
         t0 = time.perf_counter()
         dist.gather(y_final, parts, dst=0)
@@ -523,7 +530,7 @@ def main():
             },
             "work_per_solve": {k: float(v) / Nper for k, v in cnt.items()},
             "t_eval_mode": te_mode,
-            "gather_ms": gather_ms,
+            "gather_ms": gather_ms, "gather_first_ms": gather_first_ms,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample, os.cpu_count() or 1)
