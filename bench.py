@@ -459,7 +459,7 @@ def main():
         te_mode = {"t_eval_points": m, "ms_per_launch": ms, "solves_per_s": Nper / (ms * 1e-3),
                    "hbm_bytes_per_launch": nbytes, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
                    "note": "same ensemble with dense output at m log-spaced points written to HBM "
-                           "(y and yp, [m][n][N] SoA); full-options kernel variant"}
+                           "(y and yp, [m][n][N] SoA); lean kernel twin with t_eval output"}
         del y_eval, yp_eval
 
     # ---- max over ranks ----------------------------------------------------------------------------------

@@ -131,13 +131,22 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
     using Tn = RadauTune<P, S>;
     constexpr int T = Tn::kThreads;
     const int64_t blocks = (L.N + T - 1) / T;
-    const bool lean = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_eval == nullptr &&
-                      L.out.t_steps == nullptr && L.ev.spec.n_events == 0;
+    // lean: default options, no step trace, no events; with or without t_eval output (FD Jacobian,
+    // register regime, s = 3: the headline kernel and its dense-output twin)
+    const bool lean_opts = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_steps == nullptr &&
+                           L.ev.spec.n_events == 0;
+    const bool lean = lean_opts && L.out.t_eval == nullptr;
     bool done = false;
     if constexpr (kJacOk && Regime<P::N>::kReg) {
         if (L.analytic_jac) {
             if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, true><<<(unsigned)blocks, T, 0, st>>>(L);
             else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false, true><<<(unsigned)blocks, T, 0, st>>>(L);
+            done = true;
+        }
+    }
+    if constexpr (Regime<P::N>::kReg && S == 3) {
+        if (!done && lean_opts && !lean) {
+            radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, true><<<(unsigned)blocks, T, 0, st>>>(L);
             done = true;
         }
     }

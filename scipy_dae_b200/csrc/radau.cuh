@@ -112,7 +112,10 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
 #else
 #define B200DAE_RADAU_BOUNDS(T, MB) __launch_bounds__(T, MB)
 #endif
-template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold, bool kLean, bool kJac = false>
+// kEval: t_eval output compiled in (always in the full-options kernel; the lean kernel comes with
+// and without it, so that dense output at t_eval does not pull in the other option paths).
+template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold, bool kLean, bool kJac = false,
+          bool kEval = !kLean>
 __global__ void B200DAE_RADAU_BOUNDS(kThreads, kMinBlocks)
 radau_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
@@ -597,7 +600,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
             }
         }
         // t_eval points passed by this step (dae.py:496-515; RadauDenseOutput radau.py:681-699)
-        if (!kLean && L.out.t_eval != nullptr) {
+        if (kEval && L.out.t_eval != nullptr) {
             const double rho = fast_rcp_nz(h);
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
