@@ -25,3 +25,15 @@ def test_tapered_ends_are_short():
     assert abs(sizes[1] - 3 * interior[0] / 4) <= 2 and abs(sizes[-2] - 3 * interior[0] / 4) <= 2
     # fewer than five chunks: nothing to taper
     assert (np.diff(_chunk_bounds(N, 4, True)) == N // 4).all()
+
+
+def test_radau_tables_have_the_normalisation_the_kernel_relies_on():
+    """The thread-per-system Radau kernel assumes T[s-1] = (1, 0, 1, 0, ..., 1) and a dense first
+    row of TI (csrc/radau.cuh; the launcher rejects other tables).  Both follow from the
+    reference's eigenvector scaling (radau.py:72-84); pinned here for every stage count."""
+    from scipy_dae_b200.constants import radau_tables
+    for s in (1, 3, 5, 7):
+        tb = radau_tables(s)
+        T, TI = np.asarray(tb.T).reshape(s, s), np.asarray(tb.TI).reshape(s, s)
+        assert np.array_equal(T[-1], np.array([1.0 if l % 2 == 0 else 0.0 for l in range(s)]))
+        assert (TI[0] != 0.0).all()
