@@ -36,27 +36,35 @@ static __device__ __noinline__ double pow_neg_recip(double x, int k) { return po
 // change_D (bdf.py:24-29) for one component: D[:order+1] <- (R U)^T D[:order+1], evaluated as
 // U^T (R^T D) with R generated column by column (bdf.py:14-21).
 // Not inlined: six call sites; the array travels through the local stack (9 loads + 9 stores).
+// The outer loops are ROLLED (the inner ones unrolled over registers): fully unrolled the body was
+// 690 of the kernel's 4600 instructions, and this kernel is instruction-fetch bound.  Same
+// operations in the same order as the unrolled form.
 static __device__ __noinline__ void change_D_lane(double* __restrict__ D, int order, double factor,
                                            const double* __restrict__ Umat) {
     const int q = order + 1;
-    double E[kBdfQ];
+    double Dl[kBdfQ], E[kBdfQ];
 #pragma unroll
+    for (int l = 0; l < kBdfQ; ++l) Dl[l] = D[l];
+#pragma unroll 1
     for (int j = 0; j < kBdfQ; ++j) {
-        double acc = D[0];
+        double acc = Dl[0];
         double r = 1.0;
 #pragma unroll
         for (int l = 1; l < kBdfQ; ++l) {
             r *= (j == 0) ? 0.0 : ((l - 1) - factor * j) * (1.0 / l);
-            if (l < q) acc = fma(r, D[l], acc);
+            if (l < q) acc = fma(r, Dl[l], acc);
         }
         E[j] = acc;
     }
+    double El[kBdfQ];
 #pragma unroll
+    for (int l = 0; l < kBdfQ; ++l) El[l] = E[l];
+#pragma unroll 1
     for (int i = 0; i < kBdfQ; ++i) {
         double acc = 0.0;
 #pragma unroll
         for (int l = 0; l < kBdfQ; ++l)
-            if (l < q) acc = fma(Umat[l * kBdfQ + i], E[l], acc);
+            if (l < q) acc = fma(Umat[l * kBdfQ + i], El[l], acc);
         if (i < q) D[i] = acc;
     }
 }
