@@ -17,6 +17,8 @@ sys.path.insert(0, REPO)
 
 CASES = [
     # name, problem, method, N_gpu, N_cpu, sigma, rtol, atol, opts
+    # the headline ensemble with the other method (thread-per-system BDF kernel, n <= 4)
+    ("C2 robertson BDF", "robertson", "BDF", 1 << 20, 16384, 0.1, 1e-6, 1e-6, {}),
     ("C3 akzo BDF", "akzo_nobel", "BDF", 1 << 17, 4096, 0.05, 1e-8, 1e-8, {}),
     ("C3 akzo Radau3", "akzo_nobel", "Radau", 1 << 17, 4096, 0.05, 1e-8, 1e-8, {}),
     ("C4 andrews Radau5", "andrews", "Radau", 1 << 13, 256, 0.05, 1e-4, 1e-4, {"stages": 5}),
