@@ -39,27 +39,52 @@ struct BdfLaunch {
 
 // change_D (bdf.py:24-29): D[:order+1] = (R @ U).T @ D[:order+1], evaluated as U.T @ (R.T @ D)
 // with R = cumprod_i (i - 1 - factor*j) / i generated column by column (bdf.py:14-21).
+//
+// Cost matters more than it looks: with one system per lane, SOME lane of a warp needs a rescale in
+// nearly every trip of the flattened step loop, so the warp runs this function almost every trip
+// (ncu, Robertson ensemble: 60 % of all instructions, 10 of 32 lanes active).  The inner loops are
+// therefore unrolled over compile-time l (masked by l < q) and the division by l is a
+// multiplication by the constant 1 / l as in the group kernel (<= 1 ulp from the reference's true
+// division for l = 3, 5; exact for l = 1, 2, 4): the rolled form with q^2 IEEE divisions cost ~4x
+// as many instructions.
 template <int N>
 __device__ __noinline__ void change_D(double* __restrict__ D, int order, double factor,
                                       const double* __restrict__ Umat) {
     double E[kBdfQ * N];
     const int q = order + 1;
+#pragma unroll 1
     for (int j = 0; j < q; ++j) {
         double acc[N];
+#pragma unroll
         for (int c = 0; c < N; ++c) acc[c] = D[c];          // R[0][j] = 1
         double r = 1.0;
-        for (int l = 1; l < q; ++l) {
-            r *= (j == 0) ? 0.0 : ((l - 1) - factor * j) / l;
-            for (int c = 0; c < N; ++c) acc[c] = fma(r, D[l * N + c], acc[c]);
+#pragma unroll
+        for (int l = 1; l < kBdfQ; ++l) {
+            r *= (j == 0) ? 0.0 : ((l - 1) - factor * j) * (1.0 / l);
+            if (l < q) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) acc[c] = fma(r, D[l * N + c], acc[c]);
+            }
         }
+#pragma unroll
         for (int c = 0; c < N; ++c) E[j * N + c] = acc[c];
     }
-    for (int i = 0; i < q; ++i)
-        for (int c = 0; c < N; ++c) {
-            double acc = 0.0;
-            for (int l = 0; l < q; ++l) acc = fma(Umat[l * kBdfQ + i], E[l * N + c], acc);
-            D[i * N + c] = acc;
+#pragma unroll 1
+    for (int i = 0; i < q; ++i) {
+        double acc[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) acc[c] = 0.0;
+#pragma unroll
+        for (int l = 0; l < kBdfQ; ++l) {
+            if (l < q) {
+                const double u = Umat[l * kBdfQ + i];
+#pragma unroll
+                for (int c = 0; c < N; ++c) acc[c] = fma(u, E[l * N + c], acc[c]);
+            }
         }
+#pragma unroll
+        for (int c = 0; c < N; ++c) D[i * N + c] = acc[c];
+    }
 }
 
 template <class P, int kThreads, bool kJac = false>
