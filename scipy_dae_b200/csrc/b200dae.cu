@@ -264,6 +264,7 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
         }
     }
     fill_U(L.U);
+    for (int k = 1; k < kBdfQ + 2; ++k) L.neg_inv[k] = -1.0 / k;
     L.max_order = opts->max_order;
     L.max_steps = opts->max_steps;
     L.analytic_jac = opts->analytic_jac;

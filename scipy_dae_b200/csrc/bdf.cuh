@@ -28,6 +28,7 @@ struct BdfLaunch {
     double thr[B200DAE_MAX_N];
     double gamma[kBdfQ], alpha[kBdfQ], error_const[kBdfQ + 1];
     double U[kBdfQ * kBdfQ];   // compute_R(6, 1): its leading blocks are compute_R(order, 1)
+    double neg_inv[kBdfQ + 2]; // neg_inv[k] = -1.0 / k, k = 1 .. max_order + 2 (exponents of the controller), from the host
     int32_t max_order;
     int64_t max_steps;
     int32_t analytic_jac;       // host-side dispatch only (kJac template parameter)
@@ -36,6 +37,15 @@ struct BdfLaunch {
     b200dae_outputs out;
     EventLaunch ev;             // ev.spec.n_events == 0: no events
 };
+
+// norm ** (-1 / k) of the step-size / order controller (bdf.py:353,398-404), one shared copy of
+// libdevice's pow for all call sites (these kernels are instruction-fetch bound).  The exponent
+// comes from a host-built table, and an infinite norm (order at its bound) short-cuts to the
+// limit 0 that pow would return through its special-case path.
+static __device__ __noinline__ double pow_ctrl(double x, double e) { return pow(x, e); }
+__device__ __forceinline__ double norm_root(double norm, double e) {
+    return (norm == INFINITY) ? 0.0 : pow_ctrl(norm, e);
+}
 
 // change_D (bdf.py:24-29): D[:order+1] = (R @ U).T @ D[:order+1], evaluated as U.T @ (R.T @ D)
 // with R = cumprod_i (i - 1 - factor*j) / i generated column by column (bdf.py:14-21).
@@ -294,7 +304,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             error_norm = fast_sqrt(ss * (1.0 / N));
         }
         if (error_norm > 1.0) {
-            const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (order + 1)));
+            const double factor = fmax(0.2, safety * norm_root(error_norm, L.neg_inv[order + 1]));
             hl *= factor;
             change_D<N>(D, order, factor, L.U);
             n_equal_steps = 0;                     // LU is kept (bdf.py:353-354)
@@ -340,7 +350,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             int arg = 0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const double fc = pow(norms[i], -1.0 / (order + i));
+                const double fc = norm_root(norms[i], L.neg_inv[order + i]);
                 if (i == 0 || (best == best && (fc > best || fc != fc))) { best = fc; arg = i; }
             }
             order += arg - 1;

@@ -28,11 +28,6 @@ struct BdfGroupLayout {
     __host__ __device__ static constexpr int doubles(int np) { return oPar + np + ((oPar + np) & 1); }
 };
 
-// x ** (-1 / k) of the step-size / order controller (bdf.py:353,398-404).  Not inlined: the four
-// call sites would each carry a copy of libdevice's pow (~90 instructions), and this kernel is
-// instruction-fetch bound (ncu: stall_no_inst 34 % at 4600 instructions).
-static __device__ __noinline__ double pow_neg_recip(double x, int k) { return pow(x, -1.0 / k); }
-
 // change_D (bdf.py:24-29) for one component: D[:order+1] <- (R U)^T D[:order+1], evaluated as
 // U^T (R^T D) with R generated column by column (bdf.py:14-21).
 // Not inlined: six call sites; the array travels through the local stack (9 loads + 9 stores).
@@ -302,7 +297,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             error_norm = fast_sqrt(ss * (1.0 / N));
         }
         if (error_norm > 1.0) {
-            const double factor = fmax(0.2, safety * pow_neg_recip(error_norm, order + 1));
+            const double factor = fmax(0.2, safety * norm_root(error_norm, L.neg_inv[order + 1]));
             hl *= factor;
             change_D_call(D, order, factor, L.U);
             n_equal_steps = 0;
@@ -360,7 +355,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             int arg = 0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const double fc = pow_neg_recip(norms[i], order + i);
+                const double fc = norm_root(norms[i], L.neg_inv[order + i]);
                 if (i == 0 || (best == best && (fc > best || fc != fc))) { best = fc; arg = i; }
             }
             order += arg - 1;
