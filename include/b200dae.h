@@ -71,7 +71,9 @@ enum {
 
 /* Radau IIA method tables = the return value of radau_constants(s) (radau.py:51-134), computed
  * on the host in float64 with the same NumPy/SciPy primitives (scipy_dae_b200/constants.py).
- * Matrices are row-major with stride s. */
+ * Matrices are row-major with stride s.  The kernels rely on the normalisation of the reference's
+ * eigen-transformation (radau.py:72-84): T[s-1] = (1, 0, 1, 0, ..., 1) and no zero in TI[0];
+ * b200dae_solve_radau returns B200DAE_EINVAL for tables that do not have it. */
 typedef struct b200dae_radau_tables {
     int32_t s;
     int32_t order;
