@@ -194,9 +194,13 @@ static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
     }
     constexpr int T = BlockSize<P>::value;
     const int64_t blocks = (L.N + T - 1) / T;
+    const bool lean = L.out.t_eval == nullptr && L.out.t_steps == nullptr && L.ev.spec.n_events == 0;
     bool done = false;
     if constexpr (P::kHasJac && Regime<P::N>::kReg) {
         if (L.analytic_jac) { bdf_kernel<P, T, true><<<(unsigned)blocks, T, 0, st>>>(L); done = true; }
+    }
+    if constexpr (Regime<P::N>::kReg) {
+        if (!done && lean) { bdf_kernel<P, T, false, true><<<(unsigned)blocks, T, 0, st>>>(L); done = true; }
     }
     if (!done) bdf_kernel<P, T><<<(unsigned)blocks, T, 0, st>>>(L);
     g_launches.fetch_add(1);
