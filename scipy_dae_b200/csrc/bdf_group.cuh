@@ -76,7 +76,8 @@ __device__ __forceinline__ void change_D_call(double (&D)[kBdfRows], int order, 
     for (int i = 0; i < kBdfRows; ++i) D[i] = tmp[i];
 }
 
-template <class P, int G, int kThreads, int kMinBlocks, bool kJac = false, bool kEv = false>
+// kOut: t_eval output and step trace compiled in (false: the lean variant of a plain solve)
+template <class P, int G, int kThreads, int kMinBlocks, bool kJac = false, bool kEv = false, bool kOut = true>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     constexpr int N = P::N, NP = P::NP;
@@ -142,7 +143,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     int64_t ie = 0;
     int32_t nst = 0;
 
-    if (L.out.t_steps != nullptr && L.out.steps_cap > 0) {
+    if (kOut && L.out.t_steps != nullptr && L.out.steps_cap > 0) {
         if (lane == 0) L.out.t_steps[inst] = t;
         if (act) {
             if (L.out.y_steps) L.out.y_steps[lane * ld + inst] = y;
@@ -425,7 +426,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
                 yp = bv;
             }
         }
-        if (L.out.t_eval != nullptr) {
+        if (kOut && L.out.t_eval != nullptr) {
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
                 if (!(dir > 0.0 ? te <= t : te >= t)) break;
@@ -438,7 +439,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
                 ++ie;
             }
         }
-        if (L.out.t_steps != nullptr && nst < L.out.steps_cap) {
+        if (kOut && L.out.t_steps != nullptr && nst < L.out.steps_cap) {
             if (lane == 0) L.out.t_steps[(int64_t)nst * ld + inst] = t;
             if (act) {
                 if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + lane) * ld + inst] = y;

@@ -158,7 +158,7 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-template <class P, bool J = false, bool E = false>
+template <class P, bool J = false, bool E = false, bool O = true>
 static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
     constexpr int G = GroupSize<P::N>::value;
     constexpr int T = (G == 32) ? 32 : 64;
@@ -166,7 +166,7 @@ static int launch_bdf_group(const BdfLaunch& L, cudaStream_t st) {
     constexpr size_t smem = (size_t)(T / G) * Lay::doubles(P::NP) * sizeof(double);
     static_assert(smem <= 227 * 1024, "per-block shared memory");
     constexpr int MB = B200DAE_GROUP_MINBLOCKS(G);
-    auto kern = bdf_group_kernel<P, G, T, MB, J, E>;
+    auto kern = bdf_group_kernel<P, G, T, MB, J, E, O>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -185,9 +185,11 @@ static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
     if constexpr (!Regime<P::N>::kReg) {
         if (!force_thread_regime()) {
             const bool ev = L.ev.spec.n_events > 0;      // the event code is compiled out otherwise
+            const bool plain = !ev && L.out.t_eval == nullptr && L.out.t_steps == nullptr;   // ... and t_eval / trace
             if constexpr (P::kHasJac) {
                 if (L.analytic_jac) return ev ? launch_bdf_group<P, true, true>(L, st) : launch_bdf_group<P, true, false>(L, st);
             }
+            if (plain) return launch_bdf_group<P, false, false, false>(L, st);
             return ev ? launch_bdf_group<P, false, true>(L, st) : launch_bdf_group<P, false, false>(L, st);
         }
         if (L.analytic_jac) return kErrNoJac;
