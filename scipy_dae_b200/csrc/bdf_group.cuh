@@ -172,7 +172,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         }
         // ---- phase B (bdf.py:269-293) -----------------------------------------------------------
         if (step_begin) {
-            min_step = 10.0 * fabs(nextafter(t, dir * INFINITY) - t);
+            min_step = 10.0 * fabs(next_toward(t, dir) - t);
             if (h_abs > L.max_step) {
                 hl = L.max_step;
                 change_D_call(D, order, L.max_step / h_abs, L.U);

@@ -157,6 +157,19 @@ __device__ __forceinline__ double fast_sqrt_rsqrt(double x, double& rsq) {
     return ok ? g : ((x < 0.0) ? nan("") : x);
 }
 
+// nextafter(t, dir * inf) for finite t (radau.py:489, bdf.py:269) on the integer pipe: one step of the bit
+// pattern away from zero when t and dir have the same sign, towards zero otherwise.
+__device__ __forceinline__ double next_toward(double t, double dir) {
+#if B200DAE_FASTMATH_LITE
+    const long long b = __double_as_longlong(t);
+    const bool away = (t > 0.0) == (dir > 0.0);
+    const double nt = __longlong_as_double(b + (away ? 1LL : -1LL));
+    return (t == 0.0) ? copysign(4.9406564584124654e-324, dir) : nt;
+#else
+    return nextafter(t, dir * INFINITY);
+#endif
+}
+
 // x ** k for 0 <= k < 32 without a loop
 __device__ __forceinline__ double powi32(double x, int k) {
     const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8;

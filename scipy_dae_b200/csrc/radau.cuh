@@ -47,19 +47,6 @@ __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931
 
 __device__ __forceinline__ double powi(double x, int k) { return powi32(x, k); }   // 0 <= k < 32
 
-// nextafter(t, dir * inf) for finite t (radau.py:489) on the integer pipe: one step of the bit
-// pattern away from zero when t and dir have the same sign, towards zero otherwise.
-__device__ __forceinline__ double next_toward(double t, double dir) {
-#if B200DAE_FASTMATH_LITE
-    const long long b = __double_as_longlong(t);
-    const bool away = (t > 0.0) == (dir > 0.0);
-    const double nt = __longlong_as_double(b + (away ? 1LL : -1LL));
-    return (t == 0.0) ? copysign(4.9406564584124654e-324, dir) : nt;
-#else
-    return nextafter(t, dir * INFINITY);
-#endif
-}
-
 // predict_factor, radau.py:198-240 (KAPPA = 1).  inv_sp1 = 1 / (s + 1).
 template <int S>
 __device__ __forceinline__ double root_sp1(double x) {      // x ** (1 / (S + 1))

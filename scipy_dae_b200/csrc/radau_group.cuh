@@ -116,16 +116,17 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
             xc[cc] = xp_try;
             eval_shared<P>(t, wrt_yp ? sy : xc, wrt_yp ? xc : syp, p, fnew);
             if (want) {
-                double best = -1.0, f_at = 0.0, fn_at = 0.0, d_at = 0.0;
-                for (int r = 0; r < N; ++r) {
+                // running argmax on the raw differences; a NaN difference (np.argmax: the first NaN
+                // wins, max_diff = NaN) is restored through the sum, see fd_probe in fd_jacobian.cuh
+                double f_at = sf[0], fn_at = fnew[0], bd = fn_at - f_at, sum = 0.0;
+                for (int r = 1; r < N; ++r) {
                     const double fr = sf[r], fn = fnew[r];
                     const double dr = fn - fr;
-                    const double a = fabs(dr);
-                    if (a > best || (a != a && best == best)) { best = a; f_at = fr; fn_at = fn; d_at = dr; }
+                    sum += dr;
+                    if (fabs(dr) > fabs(bd)) { bd = dr; f_at = fr; fn_at = fn; }
                 }
-                const double md2 = fabs(d_at);
-                double sc2 = amax_sel(f_at, fn_at);
-                if (f_at != f_at || fn_at != fn_at) sc2 = nan("");
+                const double md2 = fma(0.0, sum, fabs(bd));
+                const double sc2 = amax_sel(f_at, fn_at);
                 if (attempt == 0 || max_diff * sc2 < md2 * scale) {
                     fac = fac_try;
                     h = h_try;
@@ -284,7 +285,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         }
         // ---- phase B (radau.py:489-512) -----------------------------------------------------
         if (step_begin) {
-            min_step = 10.0 * fabs(nextafter(t, dir * INFINITY) - t);
+            min_step = 10.0 * fabs(next_toward(t, dir) - t);
             if (h_abs > L.max_step) { hl = L.max_step; havel_old = false; }
             else if (h_abs < min_step) { hl = min_step; havel_old = false; }
             else { hl = h_abs; havel_old = have_old; }
