@@ -207,10 +207,17 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             h = t_new - t;
             hl = fabs(h);
             const double rh = fast_rcp(h);
+            // loops over the order unrolled and masked (lanes of a warp run different orders, so a
+            // rolled loop runs to the largest one anyway and pays the loop overhead on top)
+#pragma unroll U
             for (int j = 0; j < N; ++j) {
                 double acc = 0.0, ps = 0.0;
-                for (int i = 0; i <= order; ++i) acc += D[i * N + j];
-                for (int i = 1; i <= order; ++i) ps = fma(D[i * N + j], L.gamma[i], ps);
+#pragma unroll
+                for (int i = 0; i < kBdfQ; ++i)
+                    if (i <= order) acc += D[i * N + j];
+#pragma unroll
+                for (int i = 1; i < kBdfQ; ++i)
+                    if (i <= order) ps = fma(D[i * N + j], L.gamma[i], ps);
                 y_predict[j] = acc;
                 inv_scale[j] = fast_rcp(fma(rtol, fabs(acc), L.atol[j]));
                 psi[j] = ps * rh;
@@ -326,8 +333,12 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             D[(order + 2) * N + j] = d[j] - D[(order + 1) * N + j];
             D[(order + 1) * N + j] = d[j];
         }
-        for (int i = order; i >= 0; --i)
-            for (int j = 0; j < N; ++j) D[i * N + j] += D[(i + 1) * N + j];
+#pragma unroll
+        for (int i = kBdfQ - 1; i >= 0; --i)
+            if (i <= order) {
+#pragma unroll U
+                for (int j = 0; j < N; ++j) D[i * N + j] += D[(i + 1) * N + j];
+            }
 
         if (n_equal_steps >= order + 1) {          // order / step selection, bdf.py:379-413
             double norms[3];
