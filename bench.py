@@ -15,8 +15,9 @@ Timed regions
   e2e   : the public API call a user makes (solve_dae_batched) with HOST (pinned) inputs, every
           step including the host->device copies, the AoS->SoA relayout, the launch and the
           device->host read-back of states, status and counters.
-  cpu_baseline : the CPU oracle (plain-C port of the reference's step loop, oracle/) over a
-          bounded sample of the same ensemble on the host cores of this box.
+  cpu_baseline : the UNMODIFIED Python reference (oracle/_ref) over the first 16 384 instances of the
+          same ensemble on a multiprocessing.Pool(os.cpu_count()) (kind "reference"); beside it
+          cpu_baseline_port, the plain-C oracle port on the same cores.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -195,15 +196,43 @@ def cpu_port_run(params, y0, yp0, nthreads):
     return dt, r
 
 
+def reference_pool_run(sample: int, budget_s: float, steps: int = 1, warmup: int = 0):
+    """The UNMODIFIED Python reference (oracle/_ref, copied by oracle/make_ref.sh) over the first
+    instances of the rank-0 ensemble: solve_dae(F, ..., args=(k1, k2, k3)) on a
+    multiprocessing.Pool(os.cpu_count()) with BLAS threads pinned to 1.  Runs as its
+    own process: the thread-count environment must be in place before NumPy loads, and a process
+    that holds a CUDA context must not fork."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    env.pop("CUDA_VISIBLE_DEVICES", None)
+    cmd = [sys.executable, "-m", "oracle.reference", "--bench", "--problem", WORKLOAD["problem"],
+           "--method", WORKLOAD["method"], "--rtol", repr(WORKLOAD["rtol"]), "--atol", repr(WORKLOAD["atol"]),
+           "--t-span", repr(WORKLOAD["t_span"][0]), repr(WORKLOAD["t_span"][1]), "--sigma", repr(WORKLOAD["sigma"]),
+           "--seed", "0", "--sample", str(sample), "--budget-s", repr(budget_s), "--steps", str(steps),
+           "--warmup", str(warmup)]
+    r = subprocess.run(cmd, cwd=REPO, env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"oracle.reference failed: {r.stderr[-2000:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def cpu_baseline(sample: int, nthreads: int):
-    """Oracle port on the host cores over the first `sample` instances of rank 0's ensemble."""
+    """The reference on the host cores of this box: the first 16 384 instances of the rank-0
+    ensemble, bounded to about 20 s of wall time."""
+    d = reference_pool_run(sample if sample > 0 else 16384, 20.0)
+    return {"value": d["value"], "unit": UNIT, "cores": d["cores"], "kind": "reference",
+            "sample": d["sample"], "instances": d["instances"], "source": d["source"],
+            "all_finished": d["all_finished"]}
+
+
+def cpu_baseline_port(nthreads: int):
+    """The plain-C oracle port (oracle/dae_oracle.c) on the same host cores: the stronger CPU
+    baseline (compiled code, POSIX threads), reported beside the reference."""
     from scipy_dae_b200 import perturbed_params, initial_conditions
-    if sample <= 0:
-        probe = 2048
-        p = perturbed_params("robertson", probe, WORKLOAD["sigma"], 0)
-        y0, yp0 = initial_conditions("robertson", p)
-        dt, _ = cpu_port_run(p, y0, yp0, nthreads)
-        sample = int(min(1 << 20, max(4096, 12.0 * probe / dt)))      # ~12 s of CPU work
+    probe = 2048
+    p = perturbed_params("robertson", probe, WORKLOAD["sigma"], 0)
+    y0, yp0 = initial_conditions("robertson", p)
+    dt, _ = cpu_port_run(p, y0, yp0, nthreads)
+    sample = int(min(1 << 20, max(4096, 8.0 * probe / dt)))           # ~8 s of CPU work
     p = perturbed_params("robertson", sample, WORKLOAD["sigma"], 0)
     y0, yp0 = initial_conditions("robertson", p)
     dt, _ = cpu_port_run(p, y0, yp0, nthreads)
@@ -213,36 +242,24 @@ def cpu_baseline(sample: int, nthreads: int):
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path (the unmodified Python
+    solve_dae from oracle/_ref) on this box's host cores, each step a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
-    from scipy_dae_b200 import perturbed_params, initial_conditions
-    O.build()
-    nthreads = os.cpu_count() or 1
-    # bounded sample per step so that the whole run ends within a few minutes
-    probe = 2048
-    p = perturbed_params("robertson", probe, WORKLOAD["sigma"], 0)
-    y0, yp0 = initial_conditions("robertson", p)
-    dt, _ = cpu_port_run(p, y0, yp0, nthreads)
-    budget_s = 120.0 / max(1, args.steps + args.warmup)
-    sample = int(min(args.instances, max(4096, budget_s * probe / dt)))
-    p = perturbed_params("robertson", sample, WORKLOAD["sigma"], 0)
-    y0, yp0 = initial_conditions("robertson", p)
-    for _ in range(args.warmup):
-        cpu_port_run(p, y0, yp0, nthreads)
-    times = [cpu_port_run(p, y0, yp0, nthreads)[0] for _ in range(args.steps)]
-    total = float(sum(times))
-    value = sample * args.steps / total
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    d = reference_pool_run(min(args.instances, args.cpu_sample if args.cpu_sample > 0 else 16384), budget_s,
+                           steps=args.steps, warmup=args.warmup)
+    value = d["value"]
+    cfg = workload_config(args.instances, args.gpus)
+    cfg["reference_sample"] = (f"{d['instances']} instances per step (bounded sample of the "
+                               f"{args.instances}-instance workload: the first indices of the seed-0 ensemble)")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * d["seconds_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "impl": "reference", "config": workload_config(args.instances, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
-                             "sample": f"{sample} instances per step (bounded sample of the "
-                                       f"{args.instances}-instance workload), oracle/dae_oracle.c, "
-                                       f"{nthreads} POSIX threads"},
+            "impl": "reference", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": d["cores"], "kind": "reference",
+                             "sample": d["sample"], "instances": d["instances"], "source": d["source"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -534,6 +551,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample, os.cpu_count() or 1)
+            line["cpu_baseline_port"] = cpu_baseline_port(os.cpu_count() or 1)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

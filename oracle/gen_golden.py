@@ -11,15 +11,15 @@ instance by instance, recording for each instance what the parity contract needs
     n_accepted, n_newton_calls, n_newton_fail, n_newton_iter, n_err_rejected
     and, when a t_eval grid is part of the case, y(t_eval), yp(t_eval).
 
-Accepted / rejected counts are not exposed by the reference; they are derived
-without editing it by rebinding the module-level ``solve_collocation_system`` /
-``solve_bdf_system`` (looked up as globals inside ``_step_impl``: radau.py:540,
-bdf.py:323).
+The per-instance runner (with the accepted / rejected counts derived by rebinding the
+module-level Newton solvers) lives in ``oracle/reference.py``, which the live-reference tests on
+the GPU box share.
 
 Output: ``tests/golden/<case>.npz`` (small, committed).  Usage::
 
     python oracle/gen_golden.py            # all cases
     python oracle/gen_golden.py robertson  # cases whose name contains the substring
+    python oracle/gen_golden.py -transamp1 # all cases but those
 """
 import json
 import os
@@ -31,108 +31,56 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-sys.path.insert(0, "/root/reference")
 
 import scipy  # noqa: E402
-import scipy_dae.integrate._dae.radau as R  # noqa: E402
-import scipy_dae.integrate._dae.bdf as B  # noqa: E402
-from scipy_dae.integrate import solve_dae  # noqa: E402
 
+from oracle.reference import import_reference, run_instance, ref_source  # noqa: E402
 from scipy_dae_b200.problems import (  # noqa: E402
     get_problem, perturbed_params, initial_conditions)
 
+import_reference()            # the unmodified reference, from oracle/_ref (checksummed) or /root/reference
 GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
 
-_cnt = dict(calls=0, nonconv=0, iters=0)
+
+TWIN_EPS = 1e-15
+TWINS = (1, -1, 2, -2)          # parameters * (1 + k * TWIN_EPS): the reference against itself
+TWIN_KEYS = ("status", "t_final", "y_final", "nfev", "njev", "nlu", "n_accepted", "n_newton_fail", "n_err_rejected",
+             "n_eval_valid", "y_eval", "t_events", "n_events_found")
 
 
-def _wrap(orig):
-    def w(*a, **k):
-        out = orig(*a, **k)  # out[0] = converged, out[1] = n_iter
-        _cnt["calls"] += 1
-        _cnt["nonconv"] += (not out[0])
-        _cnt["iters"] += out[1]
-        return out
-    return w
+def _run_all(problem, params, y0, yp0, t_span, method, rtol, atol, t_eval, options, record_steps):
+    return [run_instance(problem, params[i], y0[i], yp0[i], t_span, method, rtol, atol,
+                         t_eval, options, record_steps=record_steps and i == 0)
+            for i in range(params.shape[0])]
 
 
-R.solve_collocation_system = _wrap(R.solve_collocation_system)
-B.solve_bdf_system = _wrap(B.solve_bdf_system)
-
-
-def run_instance(problem, params, y0, yp0, t_span, method, rtol, atol, t_eval, options,
-                 record_steps=False):
-    for k in _cnt:
-        _cnt[k] = 0
-    options = dict(options)
-    ev_spec = options.pop("events", None)
-    ev_cap = options.pop("event_cap", 16)
-    if ev_spec:                               # threshold events as the reference's event callables
-        def make(e):
-            j, c, of_yp = int(e["component"]), float(e["value"]), e.get("of", "y") == "yp"
-            fn = (lambda t, y, yp, *a: yp[j] - c) if of_yp else (lambda t, y, yp, *a: y[j] - c)
-            fn.direction = float(e.get("direction", 0))
-            fn.terminal = e.get("terminal", False)
-            return fn
-        options["events"] = [make(e) for e in ev_spec]
-    if options.get("jac") == "analytic":     # the problem's analytic Jacobians as the `jac` callable
-        options["jac"] = problem.jacobian
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        # pass 1: t_eval=None => sol.t are the step ends => accepted count, final state
-        sol = solve_dae(problem.residual, t_span, y0, yp0, method=method, rtol=rtol,
-                        atol=atol, args=tuple(params), **options)
-    accepted = len(sol.t) - 1
-    out = dict(
-        status=sol.status, t_final=sol.t[-1], y_final=sol.y[:, -1], yp_final=sol.yp[:, -1],
-        nfev=sol.nfev, njev=sol.njev, nlu=sol.nlu, n_accepted=accepted,
-        n_newton_calls=_cnt["calls"], n_newton_fail=_cnt["nonconv"],
-        n_newton_iter=_cnt["iters"],
-        n_err_rejected=_cnt["calls"] - _cnt["nonconv"] - accepted,
-    )
-    if record_steps:
-        out["t_steps"] = sol.t
-        out["y_steps"] = sol.y
-    if ev_spec:
-        ne = len(ev_spec)
-        te = np.full((ne, ev_cap), np.nan); yev = np.full((ne, ev_cap, problem.n), np.nan)
-        ypev = np.full((ne, ev_cap, problem.n), np.nan); nf = np.zeros(ne, dtype=np.int64)
-        for k in range(ne):
-            nf[k] = len(sol.t_events[k])
-            for i in range(min(nf[k], ev_cap)):
-                te[k, i] = sol.t_events[k][i]; yev[k, i] = sol.y_events[k][i]; ypev[k, i] = sol.yp_events[k][i]
-        out.update(t_events=te, y_events=yev, yp_events=ypev, n_events_found=nf)
-    if t_eval is not None:
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            sol2 = solve_dae(problem.residual, t_span, y0, yp0, method=method, rtol=rtol,
-                             atol=atol, args=tuple(params), t_eval=t_eval, **options)
-        m = len(t_eval)
-        ye = np.full((problem.n, m), np.nan)
-        ype = np.full((problem.n, m), np.nan)
-        nv = 0 if isinstance(sol2.t, list) else len(sol2.t)
-        if nv:
-            ye[:, :nv] = sol2.y
-            ype[:, :nv] = sol2.yp
-        out["n_eval_valid"] = nv
-        out["y_eval"] = ye
-        out["yp_eval"] = ype
-    return out
+def _job(args):
+    return _run_all(get_problem(args[0]), *args[1:])
 
 
 def run_case(name, problem, params, method, rtol, atol, t_span=None, t_eval=None,
-             options=None, record_steps=False, y0=None, yp0=None):
+             options=None, record_steps=False, y0=None, yp0=None, twins=TWINS, pool=None):
+    """One golden file: the case itself plus its TWINS, the same case with every parameter multiplied
+    by (1 + k * 1e-15) and the consistent initial values recomputed from them.  The twins measure how
+    far the UNMODIFIED reference moves against itself under a perturbation at rounding level; the
+    parity tests (tests/parity.py) allow the CUDA path and the oracle the north_star band or twice that
+    self-distance, whichever is larger, so every widened band is a measured quantity of this file."""
     problem = get_problem(problem)
     options = dict(options or {})
     params = np.atleast_2d(np.asarray(params, dtype=float))
     N = params.shape[0]
-    if y0 is None:
+    given_ic = y0 is not None
+    if not given_ic:
         y0, yp0 = initial_conditions(problem, params)
     t_span = tuple(t_span or problem.t_span)
     t0 = time.perf_counter()
-    res = [run_instance(problem, params[i], y0[i], yp0[i], t_span, method, rtol, atol,
-                        t_eval, options, record_steps=record_steps and i == 0)
-           for i in range(N)]
+    jobs = [(problem.name, params, y0, yp0, t_span, method, rtol, atol, t_eval, options, record_steps)]
+    for k in twins:
+        pk = params * (1.0 + k * TWIN_EPS)
+        yk, ypk = (y0, yp0) if given_ic else initial_conditions(problem, pk)
+        jobs.append((problem.name, pk, yk, ypk, t_span, method, rtol, atol, t_eval, options, False))
+    runs = pool.map(_job, jobs) if pool is not None else [_job(j) for j in jobs]
+    res = runs[0]
     wall = time.perf_counter() - t0
     arrays = dict(params=params, y0=y0, yp0=yp0)
     for key in ("status", "t_final", "nfev", "njev", "nlu", "n_accepted", "n_newton_calls",
@@ -151,16 +99,22 @@ def run_case(name, problem, params, method, rtol, atol, t_span=None, t_eval=None
     if "t_events" in res[0]:
         for key in ("t_events", "y_events", "yp_events", "n_events_found"):
             arrays[key] = np.stack([r[key] for r in res])
+    if twins:
+        arrays["twin_factor"] = np.array([1.0 + k * TWIN_EPS for k in twins])
+        for key in TWIN_KEYS:
+            if key in res[0]:
+                arrays["twin_" + key] = np.stack([np.stack([np.asarray(r[key]) for r in run]) for run in runs[1:]])
     meta = dict(case=name, problem=problem.name, method=method, rtol=rtol,
                 atol=atol if np.isscalar(atol) else list(atol), t_span=list(t_span),
-                options=options, N=N, reference="JonasBreuling/scipy_dae v0.1.0 (/root/reference)",
+                options=options, N=N, reference="JonasBreuling/scipy_dae v0.1.0 (" + ref_source() + ")",
                 scipy=scipy.__version__, numpy=np.__version__, wall_s=round(wall, 3),
+                twins=[f"params * (1 + {k}e-15)" for k in twins],
                 generator="oracle/gen_golden.py")
     arrays["meta"] = np.array(json.dumps(meta))
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrays)
     print(f"{name}: N={N} wall={wall:.2f}s status={arrays['status'].tolist()[:8]} "
-          f"acc={arrays['n_accepted'].tolist()[:8]} nfev={arrays['nfev'].tolist()[:4]}")
+          f"acc={arrays['n_accepted'].tolist()[:8]} nfev={arrays['nfev'].tolist()[:4]}", flush=True)
 
 
 def cases():
@@ -288,6 +242,36 @@ def cases():
     yield dict(name="transamp_radau3_jac", problem="transamp",
                params=perturbed_params("transamp", 4, 0.02, 1), method="Radau",
                rtol=1e-10, atol=1e-6, options=dict(jac="analytic"))
+    # --- failure paths (dae.py:451-453: solve_dae breaks BEFORE recording the failed step)
+    # deterministic: y' = p y^2 blows up at t* = 1/p inside t_span; both methods end with
+    # TOO_SMALL_STEP (base.py:158, radau.py:515-516, bdf.py:297-298) just before t*
+    yield dict(name="blowup_radau3_fail", problem="blowup", params=np.array([[1.0], [0.8], [1.25], [0.6]]),
+               method="Radau", rtol=1e-6, atol=1e-8, t_eval=np.linspace(0.0, 2.0, 41))
+    yield dict(name="blowup_bdf_fail", problem="blowup", params=np.array([[1.0], [0.8], [1.25], [0.6]]),
+               method="BDF", rtol=1e-6, atol=1e-8, t_eval=np.linspace(0.0, 2.0, 41))
+    # the reference's own n = 5 circuit (examples/daes/stiff_transistor_amplifier.py) fails at
+    # rtol = atol = 1e-6 with both methods (BASELINE.md §2 caveat); WHERE it fails is chaotic in the
+    # reference itself (the twins of this file end between t = 8e-4 and 0.1)
+    yield dict(name="transamp1_radau3_fail", problem="transamp1", params=perturbed_params("transamp1", 6, 0.02, 1),
+               method="Radau", rtol=1e-6, atol=1e-6, t_eval=np.linspace(0.0, 0.2, 41))
+    yield dict(name="transamp1_bdf_fail", problem="transamp1", params=perturbed_params("transamp1", 4, 0.02, 1),
+               method="BDF", rtol=1e-6, atol=1e-6, t_eval=np.linspace(0.0, 0.2, 41))
+    # ... and succeeds with the example's own settings (atol = 1e-3, rtol = 1e-6, stages = 5)
+    yield dict(name="transamp1_radau5_example", problem="transamp1", params=perturbed_params("transamp1", 4, 0.02, 1),
+               method="Radau", rtol=1e-6, atol=1e-3, options=dict(stages=5), t_eval=np.linspace(0.0, 0.2, 21))
+    # non-finite iteration matrix: scipy's lu_factor(check_finite=True) raises ValueError (base.py:234)
+    # from DaeSolver.__init__ / _step_impl; recorded as status -2
+    p_nan = perturbed_params("robertson", 3, 0.1, 0); p_nan[1, 1] = np.nan
+    yield dict(name="robertson_radau3_nonfinite", problem="robertson", params=p_nan, method="Radau",
+               rtol=1e-6, atol=1e-6, twins=())
+    yield dict(name="robertson_bdf_nonfinite", problem="robertson", params=p_nan, method="BDF",
+               rtol=1e-6, atol=1e-6, twins=())
+    # --- tighter tolerances where the step sequences of the n > 4 problems are NOT chaotic: the
+    # unwidened north_star band has to hold per instance (measured: twin distances << 1)
+    yield dict(name="andrews_radau5_tight", problem="andrews", params=perturbed_params("andrews", 4, 0.05, 2),
+               method="Radau", rtol=1e-8, atol=1e-8, options=dict(stages=5), t_eval=np.linspace(0, 0.03, 7))
+    yield dict(name="transamp_bdf_tight", problem="transamp", params=perturbed_params("transamp", 4, 0.02, 1),
+               method="BDF", rtol=1e-12, atol=1e-9)
     # backward integration (direction = -1) of a non-stiff stretch
     yield dict(name="robertson_radau3_backward", problem="robertson",
                params=rob_nom, method="Radau", rtol=1e-6, atol=1e-8, t_span=(1e-3, 0.0),
@@ -296,20 +280,23 @@ def cases():
 
 
 def main():
-    sel = sys.argv[1:]
-    for c in cases():
-        if sel and not any(s in c["name"] for s in sel):
-            continue
-        if c["name"] == "robertson_radau3_backward":
-            # consistent yp0 for the given y0 (differential rows explicit, algebraic row's yp3 = -(yp1+yp2))
-            y = c["y0"][0]
-            k1, k2, k3 = c["params"][0]
-            yp = np.array([-k1 * y[0] + k2 * y[1] * y[2],
-                           k1 * y[0] - k2 * y[1] * y[2] - k3 * y[1] ** 2, 0.0])
-            yp[2] = -(yp[0] + yp[1])
-            y[2] = 1.0 - y[0] - y[1]
-            c["yp0"] = yp[None, :]
-        run_case(**c)
+    import multiprocessing as mp
+    sel = [a for a in sys.argv[1:] if not a.startswith("-")]
+    skip = [a[1:] for a in sys.argv[1:] if a.startswith("-")]      # -substring: leave those cases alone
+    with mp.get_context("fork").Pool(min(5, os.cpu_count() or 1)) as pool:
+        for c in cases():
+            if (sel and not any(s in c["name"] for s in sel)) or any(s in c["name"] for s in skip):
+                continue
+            if c["name"] == "robertson_radau3_backward":
+                # consistent yp0 for the given y0 (differential rows explicit, algebraic row's yp3 = -(yp1+yp2))
+                y = c["y0"][0]
+                k1, k2, k3 = c["params"][0]
+                yp = np.array([-k1 * y[0] + k2 * y[1] * y[2],
+                               k1 * y[0] - k2 * y[1] * y[2] - k3 * y[1] ** 2, 0.0])
+                yp[2] = -(yp[0] + yp[1])
+                y[2] = 1.0 - y[0] - y[1]
+                c["yp0"] = yp[None, :]
+            run_case(pool=pool, **c)
 
 
 if __name__ == "__main__":

@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Mint golden vectors for consistent_initial_conditions from the UNMODIFIED reference
-(/root/reference, scipy_dae/integrate/_dae/common.py:186-372).  TEST INFRASTRUCTURE.
+(oracle/_ref or /root/reference, scipy_dae/integrate/_dae/common.py:186-372).  TEST INFRASTRUCTURE.
 
-    PYTHONPATH=/root/reference python oracle/gen_golden_cic.py
+    python oracle/gen_golden_cic.py
 
 Writes tests/golden/cic/<case>.npz: the inconsistent guesses (y0_in, yp0_in), the reference's
 outputs (y0, yp0, f) and a status per instance (0 ok, -1 RuntimeError "Convergence failed.",
@@ -16,7 +16,10 @@ import scipy
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-from scipy_dae.integrate import consistent_initial_conditions  # noqa: E402  (the reference)
+from oracle.reference import import_reference, ref_source  # noqa: E402
+
+import_reference()
+from scipy_dae.integrate import consistent_initial_conditions  # noqa: E402  (the unmodified reference)
 from scipy_dae_b200.problems import get_problem, perturbed_params, initial_conditions  # noqa: E402
 
 OUT = os.path.join(REPO, "tests", "golden", "cic")
@@ -43,7 +46,7 @@ def run(name, problem, N, sigma, seed, rel_y, rel_yp, jac=None, fixed_y0=None, f
             y, yp, f, code = (np.full(pr.n, np.nan),) * 3 + (-2 if "Too many" in str(e) else -3,)
         ys.append(y); yps.append(yp); fs.append(f); st.append(code)
     meta = dict(case=name, problem=pr.name, jac=jac, fixed_y0=fixed_y0, fixed_yp0=fixed_yp0, options=kw,
-                reference="JonasBreuling/scipy_dae v0.1.0 (/root/reference)", scipy=scipy.__version__,
+                reference="JonasBreuling/scipy_dae v0.1.0 (" + ref_source() + ")", scipy=scipy.__version__,
                 numpy=np.__version__, generator="oracle/gen_golden_cic.py")
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), params=P, y0_in=Y0, yp0_in=YP0, y0=np.stack(ys),

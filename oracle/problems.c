@@ -49,17 +49,21 @@ static void transamp(double t, const double *y, const double *yp, const double *
     const double UF = 0.026, ALPHA = 0.99, R = 9000.0;
     const double C1 = 1e-6, C2 = 2e-6, C3 = 3e-6, C4 = 4e-6, C5 = 5e-6;
     double Ub = p[0], R0 = p[1], beta = p[2];
-    double Ue = 0.1 * sin(200.0 * M_PI * t);
-    double g23 = beta * (exp((y[1] - y[2]) / UF) - 1.0);
-    double g56 = beta * (exp((y[4] - y[5]) / UF) - 1.0);
-    double f0 = -Ue / R0 + y[0] / R0;
-    double f1 = -Ub / R + y[1] * (2.0 / R) - (ALPHA - 1.0) * g23;
-    double f2 = -g23 + y[2] / R;
-    double f3 = -Ub / R + y[3] / R + ALPHA * g23;
-    double f4 = -Ub / R + y[4] * (2.0 / R) - (ALPHA - 1.0) * g56;
-    double f5 = -g56 + y[5] / R;
-    double f6 = -Ub / R + y[6] / R + ALPHA * g56;
-    double f7 = y[7] / R;
+    /* reciprocal forms, operation by operation as in problems.py and problems.cuh */
+    const double rUF = 1.0 / UF, rR = 1.0 / R, r2R = 2.0 / R;
+    double rR0 = 1.0 / R0;
+    double Ue = 0.1 * sin((200.0 * M_PI) * t);
+    double g23 = beta * (exp((y[1] - y[2]) * rUF) - 1.0);
+    double g56 = beta * (exp((y[4] - y[5]) * rUF) - 1.0);
+    double UbR = Ub * rR;
+    double f0 = (y[0] - Ue) * rR0;
+    double f1 = -UbR + y[1] * r2R - (ALPHA - 1.0) * g23;
+    double f2 = -g23 + y[2] * rR;
+    double f3 = -UbR + y[3] * rR + ALPHA * g23;
+    double f4 = -UbR + y[4] * r2R - (ALPHA - 1.0) * g56;
+    double f5 = -g56 + y[5] * rR;
+    double f6 = -UbR + y[6] * rR + ALPHA * g56;
+    double f7 = y[7] * rR;
     out[0] = (-C1 * yp[0] + C1 * yp[1]) - f0;
     out[1] = (C1 * yp[0] - C1 * yp[1]) - f1;
     out[2] = (-C2 * yp[2]) - f2;
@@ -213,6 +217,28 @@ static void brenan(double t, const double *y, const double *yp, const double *p,
     out[1] = y[1] - p[0] * sin(t);
 }
 
+/* one-transistor amplifier of the reference's examples/daes/stiff_transistor_amplifier.py:20-50,
+ * p = (Ub, R0, beta) */
+static void transamp1(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    const double UF = 0.026, ALPHA = 0.99, R = 9000.0;
+    const double C1 = 1e-6, C2 = 2e-6, C3 = 3e-6;
+    double Ub = p[0], R0 = p[1], beta = p[2];
+    double Ue = 0.4 * sin((200.0 * M_PI) * t);
+    double f23 = beta * (exp((y[1] - y[2]) / UF) - 1.0);
+    out[0] = (Ue - y[0]) / R0 + C1 * (yp[1] - yp[0]);
+    out[1] = (Ub - y[1]) / R - y[1] / R + C1 * (yp[0] - yp[1]) - (1.0 - ALPHA) * f23;
+    out[2] = f23 - y[2] / R - C2 * yp[2];
+    out[3] = (Ub - y[3]) / R + C3 * (yp[4] - yp[3]) - ALPHA * f23;
+    out[4] = -y[4] / R + C3 * (yp[3] - yp[4]);
+}
+/* y' = p y^2 (finite-time blow-up: the deterministic failure-path problem) */
+static void blowup(double t, const double *y, const double *yp, const double *p, double *out)
+{
+    (void)t;
+    out[0] = yp[0] - p[0] * y[0] * y[0];
+}
+
 /* ---- analytic Jacobians (the reference's `jac=` callable, base.py:299-331), row-major n*n;
  * twins of problems.py: robertson_jacobian, akzo_jacobian, transamp_jacobian ---- */
 static void robertson_jac(double t, const double *y, const double *yp, const double *p,
@@ -302,6 +328,8 @@ static const struct {
     {"cosine", 1, 1, cosine, 0},
     {"weissinger", 1, 1, weissinger, 0},
     {"brenan", 2, 1, brenan, 0},
+    {"transamp1", 5, 3, transamp1, 0},
+    {"blowup", 1, 1, blowup, 0},
 };
 #define N_PROBLEMS ((int)(sizeof(REGISTRY) / sizeof(REGISTRY[0])))
 

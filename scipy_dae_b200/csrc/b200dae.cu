@@ -24,7 +24,7 @@ static int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
 static const ProblemEntry* registry(int* count) {
     static const ProblemEntry table[] = {entry_robertson(), entry_akzo_nobel(), entry_transamp(), entry_andrews(),
                                          entry_rational(), entry_linear(), entry_cosine(), entry_weissinger(),
-                                         entry_brenan()};
+                                         entry_brenan(), entry_transamp1(), entry_blowup()};
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;
 }

@@ -54,6 +54,8 @@ ProblemEntry entry_linear();
 ProblemEntry entry_cosine();
 ProblemEntry entry_weissinger();
 ProblemEntry entry_brenan();
+ProblemEntry entry_transamp1();
+ProblemEntry entry_blowup();
 
 // threads per block: register-regime kernels keep ~255 registers per thread live, so 128
 // threads x 2 blocks fill an SM's register file; the local-memory regime prefers fewer

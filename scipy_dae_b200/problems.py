@@ -99,11 +99,12 @@ AKZO_HEN = 737.0
 
 def akzo_rhs(y, k1, k2, k3, k4, kbig, kla, ks):
     sq = np.sqrt(y[1])
-    r1 = k1 * (y[0] ** 4) * sq
+    y0sq = y[0] * y[0]
+    r1 = k1 * (y0sq * y0sq) * sq
     r2 = k2 * y[2] * y[3]
     r3 = k2 / kbig * y[0] * y[4]
-    r4 = k3 * y[0] * (y[3] ** 2)
-    r5 = k4 * (y[5] ** 2) * sq
+    r4 = k3 * y[0] * (y[3] * y[3])
+    r5 = k4 * (y[5] * y[5]) * sq
     fin = kla * (AKZO_PO2 / AKZO_HEN - y[1])
     return np.array([
         -2.0 * r1 + r2 - r3 - r4,
@@ -166,21 +167,31 @@ TA_ALPHA = 0.99
 TA_R = 9000.0
 
 
+TA_RUF = 1.0 / TA_UF
+TA_RR = 1.0 / TA_R
+TA_R2R = 2.0 / TA_R
+
+
 def transamp_residual(t, y, yp, Ub, R0, beta):
+    """Divisions by the constants UF, R and by the parameter R0 are written as multiplications by
+    their reciprocals, operation by operation as in the device functor and the C twin: the three
+    are bit-identical up to exp / sin (the problem is restated here)."""
     C1, C2, C3, C4, C5 = 1e-6, 2e-6, 3e-6, 4e-6, 5e-6
-    R = TA_R
-    Ue = 0.1 * np.sin(200.0 * np.pi * t)
-    g23 = beta * (np.exp((y[1] - y[2]) / TA_UF) - 1.0)
-    g56 = beta * (np.exp((y[4] - y[5]) / TA_UF) - 1.0)
+    rUF, rR, r2R = TA_RUF, TA_RR, TA_R2R
+    rR0 = 1.0 / R0
+    Ue = 0.1 * np.sin((200.0 * np.pi) * t)
+    g23 = beta * (np.exp((y[1] - y[2]) * rUF) - 1.0)
+    g56 = beta * (np.exp((y[4] - y[5]) * rUF) - 1.0)
+    UbR = Ub * rR
     f = np.array([
-        -Ue / R0 + y[0] / R0,
-        -Ub / R + y[1] * (2.0 / R) - (TA_ALPHA - 1.0) * g23,
-        -g23 + y[2] / R,
-        -Ub / R + y[3] / R + TA_ALPHA * g23,
-        -Ub / R + y[4] * (2.0 / R) - (TA_ALPHA - 1.0) * g56,
-        -g56 + y[5] / R,
-        -Ub / R + y[6] / R + TA_ALPHA * g56,
-        y[7] / R,
+        (y[0] - Ue) * rR0,
+        -UbR + y[1] * r2R - (TA_ALPHA - 1.0) * g23,
+        -g23 + y[2] * rR,
+        -UbR + y[3] * rR + TA_ALPHA * g23,
+        -UbR + y[4] * r2R - (TA_ALPHA - 1.0) * g56,
+        -g56 + y[5] * rR,
+        -UbR + y[6] * rR + TA_ALPHA * g56,
+        y[7] * rR,
     ])
     My = np.array([
         -C1 * yp[0] + C1 * yp[1],
@@ -313,11 +324,24 @@ def _andrews_terms(q, v, mom, c0):
     return M, h, g, G
 
 
+# rows k of G = g_q with a structural non-zero in column i
+_AND_NZ = {0: range(6), 1: range(6), 2: (0, 1), 3: (2, 3), 4: (2, 3), 5: (4, 5), 6: (4, 5)}
+
+
 def andrews_residual(t, y, yp, mom, c0):
     q, v = y[:7], y[7:14]
     qd, vd, la, mu = yp[:7], yp[7:14], yp[14:20], yp[20:26]
     M, h, g, G = _andrews_terms(q, v, mom, c0)
-    return np.concatenate([qd - v + G.T @ mu, M @ vd - h - G.T @ la, G @ v, g])
+    # products written out term by term in row order (the structural non-zeros of M and G), the
+    # order of the C and device twins; a BLAS matvec would sum in an implementation-defined order
+    gtm = [sum((G[k, i] * mu[k] for k in range(6) if k in _AND_NZ[i]), 0.0) for i in range(7)]
+    gtl = [sum((G[k, i] * la[k] for k in range(6) if k in _AND_NZ[i]), 0.0) for i in range(7)]
+    Mvd = [M[0, 0] * vd[0] + M[0, 1] * vd[1], M[0, 1] * vd[0] + M[1, 1] * vd[1], M[2, 2] * vd[2],
+           M[3, 3] * vd[3] + M[3, 4] * vd[4], M[3, 4] * vd[3] + M[4, 4] * vd[4],
+           M[5, 5] * vd[5] + M[5, 6] * vd[6], M[5, 6] * vd[5] + M[6, 6] * vd[6]]
+    Gv = [sum((G[k, i] * v[i] for i in range(7) if k in _AND_NZ[i]), 0.0) for k in range(6)]
+    return np.array([qd[i] - v[i] + gtm[i] for i in range(7)] + [Mvd[i] - h[i] - gtl[i] for i in range(7)]
+                    + Gv + list(g))
 
 
 def andrews_initial(params):
@@ -386,7 +410,7 @@ def cosine_solution(t, a=1.0):
 def weissinger_residual(t, y, yp, a):
     """benchmarks/weissinger/weissinger.py:11-17 for z = a*y."""
     u, up = y[0] / a, yp[0] / a
-    return np.array([t * u ** 2 * up ** 3 - u ** 3 * up ** 2 + t * (t ** 2 + 1) * up - t ** 2 * u])
+    return np.array([t * (u * u) * (up * up * up) - (u * u * u) * (up * up) + t * (t * t + 1) * up - (t * t) * u])
 
 
 def weissinger_solution(t, a=1.0):
@@ -404,6 +428,47 @@ def brenan_solution(t, A=1.0, C=1.0):
     t = np.asarray(t, dtype=float)
     return (np.array([C * np.exp(-t) + A * t * np.sin(t), A * np.sin(t)]),
             np.array([-C * np.exp(-t) + A * (np.sin(t) + t * np.cos(t)), A * np.cos(t)]))
+
+
+# --------------------------------------------------------------------------- #
+# One-transistor amplifier of the reference's examples/daes/stiff_transistor_amplifier.py (n = 5)
+# --------------------------------------------------------------------------- #
+def transamp1_residual(t, y, yp, Ub, R0, beta):
+    """examples/daes/stiff_transistor_amplifier.py:20-50 with (Ub, R0, beta) as parameters."""
+    U1, U2, U3, U4, U5 = y
+    Up1, Up2, Up3, Up4, Up5 = yp
+    R = TA_R
+    C1, C2, C3 = 1e-6, 2e-6, 3e-6
+    Ue = 0.4 * np.sin((200.0 * np.pi) * t)
+    f23 = beta * (np.exp((U2 - U3) / TA_UF) - 1.0)
+    return np.array([
+        (Ue - U1) / R0 + C1 * (Up2 - Up1),
+        (Ub - U2) / R - U2 / R + C1 * (Up1 - Up2) - (1.0 - TA_ALPHA) * f23,
+        f23 - U3 / R - C2 * Up3,
+        (Ub - U4) / R + C3 * (Up5 - Up4) - TA_ALPHA * f23,
+        -U5 / R + C3 * (Up4 - Up5),
+    ])
+
+
+def transamp1_initial(params):
+    """The example's start values (stiff_transistor_amplifier.py:33-37,64-65): they satisfy
+    F(0, y0, yp0) = 0 for every (Ub, R0, beta) because f(0) = 0 and Ue(0) = 0."""
+    Ub = params[0]
+    y0 = np.array([0.0, Ub / 2.0, Ub / 2.0, Ub, 0.0])
+    yp0 = np.array([0.0, 0.0, -(Ub / 2.0) / TA_R / 2e-6, 0.0, 0.0])
+    return y0, yp0
+
+
+# --------------------------------------------------------------------------- #
+# y' = p y^2: finite-time blow-up at t* = 1 / (p y0), the deterministic failure-path problem
+# --------------------------------------------------------------------------- #
+def blowup_residual(t, y, yp, p):
+    return np.array([yp[0] - p * y[0] * y[0]])
+
+
+def blowup_solution(t, p=1.0):
+    t = np.asarray(t, dtype=float)
+    return np.array([1.0 / (1.0 - p * t)]), np.array([p / (1.0 - p * t) ** 2])
 
 
 def _ic_from_solution(sol, t0):
@@ -477,6 +542,19 @@ BRENAN = _register(Problem(
     initial=_ic_from_solution(brenan_solution, 0.0), t_span=(0.0, 10.0),
     solution=brenan_solution, t0_default=0.0, param_names=("A",),
     doc="Brenan's index-1 DAE with a time-dependent leading matrix (amplitude A)"))
+
+
+TRANSAMP1 = _register(Problem(
+    name="transamp1", n=5, n_params=3, residual=transamp1_residual,
+    default_params=(6.0, 1000.0, 1e-6), initial=transamp1_initial, t_span=(0.0, 0.2),
+    param_names=("Ub", "R0", "beta"),
+    doc="One-transistor amplifier of the reference's examples/daes/stiff_transistor_amplifier.py (n = 5)"))
+
+BLOWUP = _register(Problem(
+    name="blowup", n=1, n_params=1, residual=blowup_residual, default_params=(1.0,),
+    initial=_ic_from_solution(blowup_solution, 0.0), t_span=(0.0, 2.0),
+    solution=blowup_solution, t0_default=0.0, param_names=("p",),
+    doc="y' = p y^2, y(0) = 1: blows up at t = 1 / p (failure-path test problem)"))
 
 
 def get_problem(name_or_problem) -> Problem:

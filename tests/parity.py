@@ -1,81 +1,51 @@
-"""Parity criteria shared by the oracle-vs-golden and CUDA-vs-oracle/golden tests.
+"""Parity criteria shared by the oracle-vs-golden, CUDA-vs-golden and CUDA-vs-live-reference tests.
 
 BASELINE.json north_star: "instance by instance, the final and t_eval states agree with the
 reference solve_dae on the same inputs within max(10*rtol*|y|, atol), and accepted/rejected
 step counts agree within 5%".
+
+That band is applied unchanged wherever the reference is reproducible at its own rounding level.
+Where it is not (BDF at loose tolerances, the transistor circuits, Andrews' squeezer: adaptive
+step sequences that amplify a 1e-16 perturbation), the allowance is MEASURED, not chosen: every
+golden file carries TWINS, the unmodified reference run on the same case with all parameters
+multiplied by (1 + k * 1e-15), k = +-1, +-2 (oracle/gen_golden.py).  A path under test may be as far
+from the reference as
+
+    max(north_star band, C_TWIN * distance of the reference from its own twins)        C_TWIN = 2
+
+compared quantile by quantile over the instances of the case (median, 90 %, maximum).  The same rule
+covers step counts, rejected attempts, the time at which a failing instance gives up, and -- with
+twins computed live on the GPU box -- the large-ensemble tests of test_live_reference.py.
 """
 import numpy as np
 
 STEP_BAND = 0.05
-
-# Cases where the reference itself is chaotic at its own tolerance: two runs of the
-# UNMODIFIED reference that differ only in the association order of one residual expression
-# end 1.2e-6 apart at t = 1e7 (2.0677e-4 vs 2.0801e-4 in y1; SURVEY.md §6 vs the golden), i.e.
-# more than atol = 1e-6.  For those the state band is widened by the factor below and the
-# test says so; everything else uses the north_star band unchanged.
-STATE_SLACK = {
-    "robertson_bdf_c1": 4.0,
-    "robertson_bdf_ens01": 4.0,
-    "robertson_bdf_variants": 4.0,
-    # Newton-failure-heavy circuit at loose rtol: any rounding-level change in a linear solve
-    # moves the state by the solver's own global error (SURVEY.md App. A.3 second experiment:
-    # 1.7e-6 with atol = 1e-6 for an explicit-inverse solve inside the reference)
-    "transamp_radau3_loose": 4.0,
-    "transamp_bdf_ens": 4.0,
-}
-# Dense output between step ends is only O(h^(s+1)) accurate, so t_eval states depend on where
-# the mesh points fall.  Measured with the UNMODIFIED reference: perturbing the transamp
-# parameters by 1e-15 (relative) moves its own y(t_eval) at t = 0.05, 0.1, 0.15 (steepest input
-# slope) by 9, 17 and 17 bands (1.7e-5 absolute with atol = 1e-6) while y(0.2) stays within 0.06
-# bands.  The t_eval band of that case is widened accordingly; its final-state band is not.
-EVAL_SLACK = {
-    "transamp_radau3_ens": 40.0,
-    # Akzo Nobel with BDF at rtol = atol = 1e-8: the band (1e-7 relative) is at the level of the
-    # method's own sensitivity to rounding.  Measured: the CPU oracle built WITH FMA contraction
-    # (gcc -ffp-contract=fast -mfma, otherwise identical) moves y(t_eval) by 0.78 bands against the
-    # reference; two CUDA builds of the same source (different inlining contexts of the residual)
-    # gave < 1 and 2.76 bands.  The final state stays inside the unwidened band (0.39).
-    "akzo_bdf_ens": 4.0,
-}
-
-# Andrews' squeezer: the reference's step sequence is itself chaotic at these tolerances.
-# Measured with the UNMODIFIED reference (s=5, rtol=atol=1e-4): a 1e-15 relative perturbation of
-# (mom, c0) changes its accepted-step count 78 -> 61 (22 %) and 77 -> 64 (17 %), and at
-# s=3, rtol=atol=1e-6 moves its own y(0.03) by 1.55 bands.  Per-instance step-count parity is
-# therefore checked with the band below and the 5 % band is applied to the ensemble mean.
-STEP_BAND_CASE = {
-    "andrews_radau5_ens": 0.30,
-    "andrews_radau3_ens": 0.10,
-}
-# State bands for Andrews: CUDA vs oracle on 128 seeded instances (scripts/parity_report.py, s=5,
-# tol 1e-4) has median 0.13 bands, 93 % inside the band, worst 7.3 bands, ensemble-mean steps 68.0 vs
-# 67.4 -- the same spread the reference shows against itself.
-STATE_SLACK.update({"andrews_radau5_ens": 10.0, "andrews_radau3_ens": 4.0})
-EVAL_SLACK.update({"andrews_radau5_ens": 10.0})
-# Andrews with BDF at rtol = atol = 1e-5: the UNMODIFIED reference run twice with a 1e-15 relative
-# parameter perturbation ends 47.8 bands apart and changes its accepted steps 360 -> 342 / 368 and
-# 378 -> 355 (measured, oracle/gen_golden.py case andrews_bdf_ens); the bands are set to that.
-STATE_SLACK.update({"andrews_bdf_ens": 100.0})
-EVAL_SLACK.update({"andrews_bdf_ens": 100.0})
-STEP_BAND_CASE.update({"andrews_bdf_ens": 0.10})
+C_TWIN = 2.0
+QUANTILES = (0.5, 0.9, 1.0)
 
 
 def state_band(y_ref, rtol, atol):
     return np.maximum(10.0 * rtol * np.abs(y_ref), np.asarray(atol, dtype=float))
 
 
-def worst_state_violation(y, y_ref, rtol, atol):
-    """max over entries of |y - y_ref| / band (<= 1 means inside the north_star band)."""
+def instance_ratios(y, y_ref, rtol, atol):
+    """[N]: max over the trailing axes of |y - y_ref| / band; entries where the reference has no
+    value (NaN: t_eval points it did not reach) are skipped, a NaN of the path under test where the
+    reference has a value counts as inf."""
+    y, y_ref = np.asarray(y, dtype=float), np.asarray(y_ref, dtype=float)
     band = state_band(y_ref, rtol, atol)
-    mask = np.isfinite(y_ref)
-    if not mask.any():
-        return 0.0
     with np.errstate(invalid="ignore"):
         r = np.abs(y - y_ref) / band
-    r = np.where(mask, r, 0.0)
-    if np.isnan(r).any():
-        return float("inf")
-    return float(r.max())
+    r = np.where(np.isfinite(y_ref), np.where(np.isnan(r), np.inf, r), 0.0)
+    return r.reshape(r.shape[0], -1).max(axis=1) if r.ndim > 1 else r
+
+
+def worst_state_violation(y, y_ref, rtol, atol):
+    """max over entries of |y - y_ref| / band (<= 1 means inside the north_star band)."""
+    y_ref = np.asarray(y_ref, dtype=float)
+    if not np.isfinite(y_ref).any():
+        return 0.0
+    return float(np.max(instance_ratios(np.asarray(y)[None], y_ref[None], rtol, atol)))
 
 
 def counts_within_band(a, b, band=STEP_BAND, slack=2):
@@ -85,45 +55,119 @@ def counts_within_band(a, b, band=STEP_BAND, slack=2):
     return np.abs(a - b) <= band * np.maximum(b, 1.0) + slack
 
 
-def compare(res, ref, meta, case, atol_vec, have_eval, eval_axes_ref="nm", eval_axes_res="mn"):
-    """res/ref: dicts with y_final[N,n], status, n_accepted, n_err_rejected, n_newton_fail,
-    optional y_eval.  Returns a list of human-readable failures (empty = parity)."""
-    rtol = meta["rtol"]
-    slack = STATE_SLACK.get(case, 1.0)
+def quantile_check(r, d, floor, what, c=C_TWIN):
+    """r: per-instance distance of the path under test from the reference; d: per-instance distance
+    of the reference from its twins (None: no twins); floor: the north_star allowance (scalar or
+    per instance).  Returns failure strings for every quantile with r_q > max(floor_q, c * d_q)."""
+    r = np.asarray(r, dtype=float)
+    if r.size == 0:
+        return []
+    floor = np.broadcast_to(np.asarray(floor, dtype=float), r.shape)
+    d = np.zeros_like(r) if d is None else np.asarray(d, dtype=float)
     fails = []
-    if not np.array_equal(np.asarray(res["status"]), np.asarray(ref["status"])):
-        fails.append(f"status {res['status']} != {ref['status']}")
-    ok = np.asarray(ref["status"]) == 0
+    for q in QUANTILES:
+        rq, dq, fq = np.quantile(r, q), np.quantile(d, q), np.quantile(floor, q)
+        if not rq <= max(fq, c * dq):
+            fails.append(f"{what}: q{int(100 * q)} = {rq:.3g} > max(band {fq:.3g}, {c:g} x reference-vs-twin {dq:.3g})")
+    return fails
+
+
+def _twin(ref, key):
+    return ref.get("twin_" + key) if hasattr(ref, "get") else None
+
+
+def compare(res, ref, meta, case, atol_vec, have_eval, eval_axes_ref="nm", eval_axes_res="mn", t_eval=None):
+    """res / ref: dicts with status, t_final, y_final[N, n], n_accepted, n_err_rejected,
+    n_newton_fail, optional y_eval and n_eval_valid; ref may carry twin_* arrays [K, N, ...].
+    Returns a list of human-readable failures (empty = parity)."""
+    rtol = meta["rtol"]
+    fails = []
+    st_res, st_ref = np.asarray(res["status"]), np.asarray(ref["status"])
+    tw_st = _twin(ref, "status")
+    # an instance's status must be the reference's, unless the reference flips it against a twin
+    flips = np.zeros(st_ref.shape, dtype=bool) if tw_st is None else (np.asarray(tw_st) != st_ref[None]).any(axis=0)
+    bad = (st_res != st_ref) & ~flips
+    if bad.any():
+        fails.append(f"status {st_res} != {st_ref} (instances {np.nonzero(bad)[0].tolist()})")
+    ok = (st_ref == 0) & (st_res == 0)
+    failed = (st_ref == -1) & (st_res == -1)
+
+    def twin_dist(key, fn, sel):
+        """per selected instance: max over the twins that ended like the reference of fn(twin, ref)"""
+        tw = _twin(ref, key)
+        if tw is None:
+            return None
+        tw = np.asarray(tw, dtype=float)
+        same = (np.asarray(tw_st) == st_ref[None])[:, sel]
+        d = np.stack([fn(tw[k][sel], np.asarray(ref[key], dtype=float)[sel]) for k in range(tw.shape[0])])
+        return np.where(same, d, 0.0).max(axis=0)
+
     if ok.any():
-        w = worst_state_violation(np.asarray(res["y_final"])[ok], np.asarray(ref["y_final"])[ok],
-                                  rtol, atol_vec)
-        if not w <= slack:
-            fails.append(f"y_final outside band: worst ratio {w:.3g} (allowed {slack})")
-    band = STEP_BAND_CASE.get(case, STEP_BAND)
-    if not counts_within_band(res["n_accepted"], ref["n_accepted"], band=band).all():
-        fails.append(f"accepted steps {res['n_accepted']} vs {ref['n_accepted']}")
-    if band != STEP_BAND:   # chaotic case: the north_star band holds for the ensemble mean
-        ma, mb = np.mean(res["n_accepted"]), np.mean(ref["n_accepted"])
-        if abs(ma - mb) > 2 * STEP_BAND * mb:
-            fails.append(f"mean accepted steps {ma:.1f} vs {mb:.1f}")
-    rej_a = np.asarray(res["n_err_rejected"]) + np.asarray(res["n_newton_fail"])
-    rej_b = np.asarray(ref["n_err_rejected"]) + np.asarray(ref["n_newton_fail"])
-    # rejected attempts (error rejections + Newton failures) are a small count (5..30 for the
-    # Robertson cases); "within 5 %" is taken relative to the attempts made (accepted + rejected)
-    attempts = np.asarray(ref["n_accepted"], dtype=float) + rej_b
-    if not (np.abs(rej_a - rej_b) <= band * attempts + 2).all():
-        fails.append(f"rejected attempts {rej_a} vs {rej_b}")
+        r = instance_ratios(np.asarray(res["y_final"])[ok], np.asarray(ref["y_final"])[ok], rtol, atol_vec)
+        d = twin_dist("y_final", lambda a, b: instance_ratios(a, b, rtol, atol_vec), ok)
+        fails += quantile_check(r, d, 1.0, "y_final / band")
+
+    # accepted steps within 5 % (+2 absorbs tiny counts), rejected attempts within 5 % of the attempts
+    both = ok | failed
+    if both.any():
+        acc_ref = np.asarray(ref["n_accepted"], dtype=float)[both]
+        rel = lambda a, b: np.abs(a - b) / np.maximum(b, 1.0)          # noqa: E731
+        r = rel(np.asarray(res["n_accepted"], dtype=float)[both], acc_ref)
+        d = twin_dist("n_accepted", rel, both)
+        fails += quantile_check(r, d, STEP_BAND + 2.0 / np.maximum(acc_ref, 1.0), "accepted steps (relative)")
+        rej = lambda x: (np.asarray(x["n_err_rejected"], dtype=float) + np.asarray(x["n_newton_fail"], dtype=float))  # noqa: E731
+        attempts = acc_ref + rej(ref)[both]
+        r = np.abs(rej(res)[both] - rej(ref)[both]) / attempts
+        d = None
+        if _twin(ref, "n_err_rejected") is not None:
+            tw = np.asarray(ref["twin_n_err_rejected"], dtype=float) + np.asarray(ref["twin_n_newton_fail"], dtype=float)
+            same = (np.asarray(tw_st) == st_ref[None])[:, both]
+            d = np.where(same, np.abs(tw[:, both] - rej(ref)[both][None]) / attempts[None], 0.0).max(axis=0)
+        fails += quantile_check(r, d, STEP_BAND + 2.0 / attempts, "rejected attempts / attempts")
+
     if have_eval:
-        ye = np.asarray(res["y_eval"])
-        yr = np.asarray(ref["y_eval"])
+        ye, yr = np.asarray(res["y_eval"]), np.asarray(ref["y_eval"])
         if eval_axes_res != eval_axes_ref:
-            yr = np.swapaxes(yr, 1, 2)
-        band_atol = np.asarray(atol_vec, dtype=float)
-        band_atol = band_atol[None, None, :] if eval_axes_res == "mn" else band_atol[None, :, None]
-        w = worst_state_violation(ye, yr, rtol, band_atol)
-        slack = max(slack, EVAL_SLACK.get(case, 1.0))
-        if not w <= slack:
-            fails.append(f"y(t_eval) outside band: worst ratio {w:.3g} (allowed {slack})")
+            ye = np.swapaxes(ye, 1, 2)               # -> the reference's [N, n, m]
+        band_atol = np.asarray(atol_vec, dtype=float)[None, :, None]
+        sel = ok | failed
+        if sel.any():
+            # a failing instance is compared on the t_eval points BOTH reached
+            nv = np.minimum(np.asarray(res["n_eval_valid"]), np.asarray(ref["n_eval_valid"]))
+            yr_c = yr.copy()
+            for i in np.nonzero(failed)[0]:
+                yr_c[i, :, nv[i]:] = np.nan
+            r = instance_ratios(ye[sel], yr_c[sel], rtol, band_atol)
+            tw = _twin(ref, "y_eval")
+            d = None
+            if tw is not None:
+                tw_nv = np.asarray(ref["twin_n_eval_valid"])
+                ds = []
+                for k in range(tw.shape[0]):
+                    yk = yr_c.copy()
+                    for i in np.nonzero(failed)[0]:
+                        yk[i, :, min(nv[i], tw_nv[k, i]):] = np.nan
+                    dk = instance_ratios(np.asarray(tw[k])[sel], yk[sel], rtol, band_atol)
+                    ds.append(np.where((np.asarray(tw_st)[k] == st_ref)[sel], dk, 0.0))
+                d = np.stack(ds).max(axis=0)
+            fails += quantile_check(r, d, 1.0, "y(t_eval) / band")
+        if ok.any() and not np.array_equal(np.asarray(res["n_eval_valid"])[ok], np.asarray(ref["n_eval_valid"])[ok]):
+            fails.append(f"n_eval_valid {res['n_eval_valid']} != {ref['n_eval_valid']}")
+
+    if failed.any():
+        # where the integration gives up (solve_dae breaks before recording the failed step,
+        # dae.py:451-453): t_final = end of the last accepted step
+        tf, tr = np.asarray(res["t_final"], dtype=float)[failed], np.asarray(ref["t_final"], dtype=float)[failed]
+        span = abs(meta["t_span"][1] - meta["t_span"][0])
+        d = twin_dist("t_final", lambda a, b: np.abs(a - b) / span, failed)
+        fails += quantile_check(np.abs(tf - tr) / span, d, 1e-9, "t_final of failed instances / |t_span|")
+        if have_eval and t_eval is not None:
+            te = np.asarray(t_eval, dtype=float)
+            direction = 1.0 if meta["t_span"][1] >= meta["t_span"][0] else -1.0
+            want = np.array([np.count_nonzero(direction * (te - t) <= 0) for t in np.asarray(res["t_final"], dtype=float)])
+            got = np.asarray(res["n_eval_valid"])
+            if not np.array_equal(got[failed], want[failed]):
+                fails.append(f"n_eval_valid {got[failed]} is not the number of t_eval points up to t_final {want[failed]}")
     return fails
 
 

@@ -1,11 +1,10 @@
 """DaeSolver adapters: the B200 path behind the reference's plug-in API
 ``solve_dae(..., method=<DaeSolver subclass>)``.
 
-CPU: the adapters subclass the REAL reference DaeSolver and run through the reference's own
-solve_dae driver (dae.py:446-518) with the CPU oracle injected as the solve hook, where the
-reference is importable (/root/reference, i.e. the build container).
-GPU: the same adapters on a stand-in base class that restates DaeSolver.step / dense_output
-(base.py:361-411) drive the CUDA path, because the GPU box has no /root/reference."""
+The adapters subclass the REAL reference DaeSolver and run through the reference's own solve_dae
+driver (dae.py:446-518).  The unmodified reference comes from oracle/_ref (copied and checksummed
+by oracle/make_ref.sh; it travels to the GPU box) or from /root/reference.
+CPU: the CPU oracle is injected as the solve hook.  GPU: the CUDA path (the default hook)."""
 import os
 import sys
 import types
@@ -13,7 +12,9 @@ import types
 import numpy as np
 import pytest
 
-REF = "/root/reference"
+from oracle import reference as REFMOD
+
+needs_reference = pytest.mark.skipif(not REFMOD.available(), reason="oracle/_ref is missing: run oracle/make_ref.sh")
 
 
 def _oracle_solve(O):
@@ -33,15 +34,11 @@ def _oracle_solve(O):
     return solve
 
 
-@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference is only mounted in the build container")
+@needs_reference
 @pytest.mark.parametrize("method", ["Radau", "BDF"])
 def test_adapter_through_the_reference_driver(method, oracle):
-    sys.path.insert(0, REF)
-    try:
-        from scipy_dae.integrate import solve_dae
-        from scipy_dae.integrate._dae.base import DaeSolver, DAEDenseOutput
-    finally:
-        sys.path.remove(REF)
+    solve_dae, _, _, BASE = REFMOD.import_reference()
+    DaeSolver, DAEDenseOutput = BASE.DaeSolver, BASE.DAEDenseOutput
     from scipy_dae_b200.adapter import make_dae_solver_adapters
     from scipy_dae_b200.problems import get_problem
     B200Radau, B200BDF = make_dae_solver_adapters(DaeSolver, DAEDenseOutput, solve=_oracle_solve(oracle))
@@ -75,66 +72,54 @@ def test_adapter_through_the_reference_driver(method, oracle):
         solve_dae(pr.residual, (0.0, 1.0), y0, yp0, method=cls, rtol=1e-6, atol=1e-6)
 
 
-class _StandInDaeSolver:
-    """DaeSolver.step / dense_output / step_size restated (base.py:355-411) for the GPU box."""
-    @property
-    def step_size(self):
-        return None if self.t_old is None else np.abs(self.t - self.t_old)
-
-    def step(self):
-        if self.status != "running":
-            raise RuntimeError("Attempt to step on a failed or finished solver.")
-        if self.n == 0 or self.t == self.t_bound:
-            self.t_old, self.t, self.status = self.t, self.t_bound, "finished"
-            return None
-        t = self.t
-        success, message = self._step_impl()
-        if not success:
-            self.status = "failed"
-        else:
-            self.t_old = t
-            if self.direction * (self.t - self.t_bound) >= 0:
-                self.status = "finished"
-        return message
-
-    def dense_output(self):
-        if self.t_old is None:
-            raise RuntimeError("Dense output is available after a successful step was made.")
-        return self._dense_output_impl()
-
-
-class _StandInDenseOutput:
-    def __init__(self, t_old, t):
-        self.t_old, self.t, self.t_min, self.t_max = t_old, t, min(t, t_old), max(t, t_old)
-
-    def __call__(self, t):
-        return self._call_impl(np.asarray(t))
-
-
+@needs_reference
 @pytest.mark.gpu
 @pytest.mark.parametrize("method", ["Radau", "BDF"])
 def test_adapter_drives_the_cuda_path(method):
-    from conftest import load_golden
+    """The reference's own solve_dae (dae.py:405-518) drives the CUDA path through its plug-in point
+    method=<DaeSolver subclass> (dae.py:359-361): step ends, t_eval slicing through every step's
+    dense_output(), DaeSolution, counters and the final message come out of the reference's driver."""
+    solve_dae, _, _, BASE = REFMOD.import_reference()
+    from scipy_dae_b200 import _lib
     from scipy_dae_b200.adapter import make_dae_solver_adapters
     from scipy_dae_b200.problems import get_problem
-    Radau, BDF = make_dae_solver_adapters(_StandInDaeSolver, _StandInDenseOutput)
-    g, meta = load_golden("robertson_radau3_c1" if method == "Radau" else "robertson_bdf_c1")
+    B200Radau, B200BDF = make_dae_solver_adapters(BASE.DaeSolver, BASE.DAEDenseOutput)
+    cls = B200Radau if method == "Radau" else B200BDF
     pr = get_problem("robertson")
-    solver = (Radau if method == "Radau" else BDF)(pr, 0.0, g["y0"][0], g["yp0"][0], 1e7, rtol=1e-6, atol=1e-6,
-                                                 params=g["params"][0])
-    ts, ys = [solver.t], [solver.y]
-    mids = []
-    while solver.status == "running":                    # the loop of dae.py:446-518
-        assert solver.step() is None
-        ts.append(solver.t); ys.append(solver.y)
-        if len(ts) in (5, 30):
-            tm = 0.5 * (solver.t_old + solver.t)
-            y_mid, yp_mid = solver.dense_output()(tm)
-            mids.append((tm, y_mid))
-    assert solver.status == "finished" and solver.t == 1e7
-    assert abs(len(ts) - len(g["t_steps"])) <= 0.05 * len(g["t_steps"]) + 2
-    band = np.maximum(1e-5 * np.abs(g["y_final"][0]), 1e-6) * (4.0 if method == "BDF" else 1.0)
-    assert (np.abs(ys[-1] - g["y_final"][0]) <= band).all()
-    assert abs(solver.nfev - g["nfev"][0]) <= 0.05 * g["nfev"][0]
-    for tm, y_mid in mids:
-        assert abs(y_mid.sum() - 1.0) < 1e-5                  # interpolant respects the constraint
+    y0, yp0 = pr.initial(pr.default_params)
+    ref = solve_dae(pr.residual, (0.0, 1e7), y0, yp0, method=method, rtol=1e-6, atol=1e-6, args=pr.default_params)
+    n0 = _lib.launch_count()
+    sol = solve_dae(pr, (0.0, 1e7), y0, yp0, method=cls, rtol=1e-6, atol=1e-6, params=pr.default_params)
+    assert _lib.launch_count() - n0 == 1                       # one launch for the whole integration
+    assert sol.status == 0 and sol.success and sol.message == ref.message
+    slack = 4.0 if method == "BDF" else 1.0
+    band = slack * np.maximum(1e-5 * np.abs(ref.y[:, -1]), 1e-6)
+    assert sol.t[-1] == ref.t[-1] == 1e7 and (np.abs(sol.y[:, -1] - ref.y[:, -1]) <= band).all()
+    assert abs(sol.t.size - ref.t.size) <= 0.05 * ref.t.size + 2
+    for a, b in ((sol.nfev, ref.nfev), (sol.njev, ref.njev), (sol.nlu, ref.nlu)):
+        assert abs(a - b) <= 0.05 * b + 2, (a, b)
+    if method == "Radau":
+        assert sol.t.shape == ref.t.shape and np.allclose(sol.t[:16], ref.t[:16], rtol=1e-5)
+    # t_eval + dense_output=True: every step's interpolant comes from the device's coefficient trace
+    te = np.logspace(-5, 7, 25)
+    ref2 = solve_dae(pr.residual, (0.0, 1e7), y0, yp0, method=method, rtol=1e-6, atol=1e-6, args=pr.default_params,
+                     t_eval=te, dense_output=True)
+    n0 = _lib.launch_count()
+    sol2 = solve_dae(pr, (0.0, 1e7), y0, yp0, method=cls, rtol=1e-6, atol=1e-6, params=pr.default_params,
+                     t_eval=te, dense_output=True)
+    tt = np.array([3.0, 0.02, 5e5])
+    a, b = sol2.sol(tt), ref2.sol(tt)
+    assert _lib.launch_count() - n0 == 1                       # no replays: the trace holds the coefficients
+    assert (np.abs(sol2.y - ref2.y) <= slack * np.maximum(1e-5 * np.abs(ref2.y), 1e-6)).all()
+    assert a[0].shape == b[0].shape == (3, 3)
+    assert (np.abs(a[0] - b[0]) <= slack * np.maximum(1e-5 * np.abs(b[0]), 1e-6)).all()
+    assert np.allclose(a[1], b[1], rtol=1e-2, atol=1e-9)        # y' of the interpolant
+    # failure path through the reference's driver: the n = 5 circuit fails at rtol = atol = 1e-6
+    # (examples/daes/stiff_transistor_amplifier.py), solve_dae returns status -1 and the reached points
+    p5 = get_problem("transamp1")
+    y5, yp5 = p5.initial(p5.default_params)
+    te5 = np.linspace(0.0, p5.t_span[1], 41)
+    r5 = solve_dae(p5.residual, p5.t_span, y5, yp5, method=method, rtol=1e-6, atol=1e-6, args=p5.default_params, t_eval=te5)
+    s5 = solve_dae(p5, p5.t_span, y5, yp5, method=cls, rtol=1e-6, atol=1e-6, params=p5.default_params, t_eval=te5)
+    assert r5.status == -1 and s5.status == -1 and s5.message == r5.message
+    assert abs(len(s5.t) - len(r5.t)) <= 1

@@ -39,12 +39,11 @@ def test_cuda_matches_reference_golden(case):
         check_events(rn.t_events, rn.y_events, rn.n_events_found, rn.t_final, g, meta)
     n = g["y0"].shape[1]
     atol_vec = np.broadcast_to(np.asarray(meta["atol"], dtype=float), (n,))
-    fails = compare(res, g, meta, case, atol_vec, te is not None, eval_axes_ref="nm", eval_axes_res="nm")
+    fails = compare(res, g, meta, case, atol_vec, te is not None, eval_axes_ref="nm", eval_axes_res="nm", t_eval=te)
     assert not fails, "; ".join(fails)
-    if te is not None:
-        assert np.array_equal(res["n_eval_valid"], g["n_eval_valid"])
     if "events" not in meta["options"]:
-        assert np.allclose(res["t_final"], g["t_final"], rtol=0, atol=0)
+        done = g["status"] == 0
+        assert np.array_equal(res["t_final"][done], g["t_final"][done])
     # work counters are not part of the north_star contract (only accepted / rejected steps are);
     # they are chaotic at tight tolerances (the oracle itself differs from the golden by 9 % in nlu
     # on robertson_radau3_tight), so they only get a coarse sanity band
