@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200DAE_VERSION 102
+#define B200DAE_VERSION 103
 #define B200DAE_MAX_STAGES 7
 #define B200DAE_MAX_ORDER 6
 #define B200DAE_MAX_N 32
@@ -123,7 +123,9 @@ typedef struct b200dae_bdf_opts {
 
 /* Events of solve_dae (dae.py:30-109, 426-490).  A Python event callable cannot run inside the
  * device step loop; the device offers THRESHOLD events g_k(t, y, y') = x[component_k] - value_k,
- * x = y (of_yp = 0) or y' (of_yp = 1), with the attributes of a solve_dae event function:
+ * x = y (of_yp = 0) or y' (of_yp = 1), and the event functions registered with the problem's device
+ * functor, g_k = event_{component_k}(t, y, y'; p) - value_k (of_yp = 2; b200dae_problem_num_events
+ * says how many a problem has), with the attributes of a solve_dae event function:
  * direction (> 0 only - to +, < 0 only + to -, 0 both) and terminal (max_events <= 0: never
  * terminal, 1: `terminal = True`, k: `terminal = k`, i.e. stop at the k-th occurrence).  Roots are
  * located on the step's dense output with Brent's method, xtol = rtol = 4 EPS (dae.py:30-55).
@@ -160,6 +162,21 @@ typedef struct b200dae_events {
  *   t_steps           [steps_cap][ld]     accepted step ends incl. t0 (what solve_dae returns as
  *   y_steps, yp_steps [steps_cap][n][ld]   DaeResult.t/y/yp when t_eval is None, dae.py:492-495)
  *   n_steps           [ld]      number of rows written to the step trace
+ *
+ * Dense-output trace (solve_dae(dense_output=True) -> DaeSolution, common.py:9-126, and the
+ * DaeSolver.dense_output() of every step, base.py:394-411): with dense_coef != NULL row k >= 1 of
+ * the step trace also carries the data of the reference's per-step interpolant object,
+ *   h_steps     [steps_cap][2][ld]  [0] the interpolant's h: Radau t - t_old (RadauDenseOutput,
+ *                                   radau.py:672-679), BDF h_abs * direction AFTER the step's
+ *                                   rescale (bdf.py:417-419); [1] the step end the interpolant is
+ *                                   anchored at (differs from t_steps[k] only when a terminal event
+ *                                   cut the step short, dae.py:484-487)
+ *   order_steps [steps_cap][ld]     BDF: order of the interpolant (bdf.py:418); Radau: s
+ *   dense_coef  [steps_cap][coef_rows][ld]
+ *               Radau: ZP = (Y - y_old).T @ P, entry (j, k) in row j * s + k, coef_rows = n * s
+ *                      (radau.py:661-666; y(t) = y_old + ZP @ x^(1..s), x = (t - t_old) / h)
+ *               BDF:   D[:order + 1], entry (i, j) in row i * n + j, coef_rows = 7 * n (rows of
+ *                      orders above order_steps[k] are left untouched) (bdf.py:525-548)
  */
 typedef struct b200dae_outputs {
     double *y_final, *yp_final, *t_final;
@@ -172,6 +189,10 @@ typedef struct b200dae_outputs {
     int64_t steps_cap;
     double *t_steps, *y_steps, *yp_steps;
     int32_t *n_steps;
+    double *h_steps;
+    int32_t *order_steps;
+    double *dense_coef;
+    int64_t coef_rows;
     const b200dae_events *events;   /* HOST pointer, NULL = no events */
 } b200dae_outputs;
 
@@ -183,6 +204,7 @@ const char *b200dae_last_error(void);
  * Returns the problem id (>= 0) or B200DAE_ENOPROBLEM. */
 int b200dae_num_problems(void);
 int b200dae_problem_lookup(const char *name, int32_t *n, int32_t *n_params);
+int b200dae_problem_num_events(int problem_id);   /* event functions g(t, y, y'; p) of the functor */
 const char *b200dae_problem_name(int problem_id);
 
 /* Evaluate the registered residual on the device for N instances (SoA, ld): out[n][ld].

@@ -686,24 +686,28 @@ typedef struct {
     int32_t *n_found;                            /* [ne] */
     double g[ORC_MAX_EVENTS];
     int64_t count[ORC_MAX_EVENTS];
+    orc_event_fn fn;                             /* the problem's event functions (of_yp = 2) */
+    const double *p;
 } event_ctx;
 
 static __thread event_ctx *tl_ev = NULL;
 
-static double event_value(const orc_events *e, int k, const double *y, const double *yp)
+static double event_value(const event_ctx *c, int k, double t, const double *y, const double *yp)
 {
+    const orc_events *e = c->spec;
+    if (e->of_yp[k] == 2) return c->fn(e->component[k], t, y, yp, c->p) - e->value[k];
     return (e->of_yp[k] ? yp[e->component[k]] : y[e->component[k]]) - e->value[k];
 }
 
 /* scipy/optimize/Zeros/brentq.c (maxiter = 100); f(t) = event k on the dense output */
-static double brentq_event(const orc_events *e, int k, dense_fn dense, const void *st, int n,
+static double brentq_event(const event_ctx *e, int k, dense_fn dense, const void *st, int n,
                            double xa, double xb, double *ytmp, double *yptmp)
 {
     const double xtol = 4 * EPS, rtol = 4 * EPS;
     double xpre = xa, xcur = xb, xblk = 0., fpre, fcur, fblk = 0., spre = 0., scur = 0., sbis, delta, stry, dpre, dblk;
     (void)n;
-    dense(st, xpre, ytmp, yptmp); fpre = event_value(e, k, ytmp, yptmp);
-    dense(st, xcur, ytmp, yptmp); fcur = event_value(e, k, ytmp, yptmp);
+    dense(st, xpre, ytmp, yptmp); fpre = event_value(e, k, xpre, ytmp, yptmp);
+    dense(st, xcur, ytmp, yptmp); fcur = event_value(e, k, xcur, ytmp, yptmp);
     if (fpre == 0) return xpre;
     if (fcur == 0) return xcur;
     if (signbit(fpre) == signbit(fcur)) return NAN;                          /* ValueError in scipy */
@@ -735,7 +739,7 @@ static double brentq_event(const orc_events *e, int k, dense_fn dense, const voi
         xpre = xcur; fpre = fcur;
         if (fabs(scur) > delta) xcur += scur;
         else xcur += (sbis > 0 ? delta : -delta);
-        dense(st, xcur, ytmp, yptmp); fcur = event_value(e, k, ytmp, yptmp);
+        dense(st, xcur, ytmp, yptmp); fcur = event_value(e, k, xcur, ytmp, yptmp);
     }
     return xcur;
 }
@@ -751,7 +755,7 @@ static int handle_events_step(event_ctx *c, dense_fn dense, const void *st, int 
     double gnew[ORC_MAX_EVENTS], roots[ORC_MAX_EVENTS];
     double *ytmp = malloc(sizeof(double) * n), *yptmp = malloc(sizeof(double) * n);
     for (int k = 0; k < ne; ++k) {
-        gnew[k] = event_value(e, k, y, yp);
+        gnew[k] = event_value(c, k, t, y, yp);
         int up = (c->g[k] <= 0) && (gnew[k] >= 0), down = (c->g[k] >= 0) && (gnew[k] <= 0);
         int d = e->direction[k];
         if ((up && d > 0) || (down && d < 0) || ((up || down) && d == 0)) act[na++] = k;
@@ -762,7 +766,7 @@ static int handle_events_step(event_ctx *c, dense_fn dense, const void *st, int 
         for (int a = 0; a < na; ++a) {
             int k = act[a];
             c->count[k] += 1;
-            roots[a] = brentq_event(e, k, dense, st, n, t_old, t, ytmp, yptmp);
+            roots[a] = brentq_event(c, k, dense, st, n, t_old, t, ytmp, yptmp);
         }
         for (int a = 0; a < na; ++a)
             if (e->max_events[act[a]] > 0 && c->count[act[a]] >= e->max_events[act[a]]) any_term = 1;
@@ -851,7 +855,7 @@ int orc_solve_radau(orc_residual_fn fn, int n, const double *p,
         /* base.py:376-381: degenerate, finishes immediately */
     } else {
         event_ctx *ec = tl_ev;
-        if (ec) for (int k = 0; k < ec->spec->n_events; ++k) ec->g[k] = event_value(ec->spec, k, y0, yp0);
+        if (ec) for (int k = 0; k < ec->spec->n_events; ++k) ec->g[k] = event_value(ec, k, t0, y0, yp0);
         for (;;) {
             double t_prev = b->t;
             if (!radau_step(&st)) { status = st.status; break; }
@@ -1197,7 +1201,7 @@ int orc_solve_bdf(orc_residual_fn fn, int n, const double *p,
     }
     if (!(n == 0 || t0 == t_bound)) {
         event_ctx *ec = tl_ev;
-        if (ec) for (int k = 0; k < ec->spec->n_events; ++k) ec->g[k] = event_value(ec->spec, k, y0, yp0);
+        if (ec) for (int k = 0; k < ec->spec->n_events; ++k) ec->g[k] = event_value(ec, k, t0, y0, yp0);
         for (;;) {
             double t_prev = b->t;
             if (!bdf_step(&st)) { status = st.status; break; }
@@ -1280,6 +1284,7 @@ static void *ens_worker(void *arg)
                 ec.y_events = J->y_events + i * ne * J->ev_cap * n;
                 ec.yp_events = J->yp_events + i * ne * J->ev_cap * n;
                 ec.n_found = J->n_found + i * ne;
+                ec.fn = orc_event_of(fn); ec.p = J->params + i * J->np;
                 for (int k = 0; k < ne; ++k) ec.n_found[k] = 0;
                 tl_ev = &ec;
             } else {

@@ -105,7 +105,13 @@ int orc_solve_bdf(orc_residual_fn fn, int n, const double *p,
                   double *y_final, double *yp_final, double *t_final, int64_t *counters,
                   double *t_steps, double *y_steps, int64_t steps_cap, int64_t *n_steps);
 
-/* Threshold events g_k(t, y, yp) = x[component_k] - value_k, x = y (of_yp = 0) or yp (of_yp = 1);
+/* event functions of a problem (twins of Problem.events / the device functor's event()) */
+typedef double (*orc_event_fn)(int which, double t, const double *y, const double *yp, const double *p);
+orc_event_fn orc_problem_event(int problem_id);
+orc_event_fn orc_event_of(orc_residual_fn fn);
+
+/* Events g_k(t, y, yp) = x[component_k] - value_k, x = y (of_yp = 0) or yp (of_yp = 1), or the
+ * problem's event function number component_k minus value_k (of_yp = 2);
  * direction / terminal as the attributes of a solve_dae event function (dae.py:226-247):
  * max_events <= 0 = never terminal, 1 = `terminal = True`, k = `terminal = k`. */
 #define ORC_MAX_EVENTS 4

@@ -226,6 +226,24 @@ def cases():
     yield dict(name="akzo_bdf_events", problem="akzo_nobel",
                params=perturbed_params("akzo_nobel", 8, 0.05, 0), method="BDF", rtol=1e-8, atol=1e-8,
                options=dict(events=[dict(component=0, value=0.2, terminal=True), dict(component=2, value=0.1)]))
+    # event functions that are not thresholds on one component (the problem functor's own g(t, y, y'; p),
+    # given to the reference as the NumPy twins Problem.events[k]): y - y' and y - a t / 2 on the event
+    # test problem of tests/test_events.py, y1 - y3 and a y' combination on Robertson / Akzo Nobel
+    yield dict(name="cosine_radau3_functor_events", problem="cosine", params=np.array([[1.0], [1.3]]),
+               method="Radau", rtol=1e-10, atol=1e-10,
+               options=dict(events=[dict(functor=0), dict(functor=1, direction=-1), dict(functor=0, direction=1, terminal=2)]))
+    yield dict(name="cosine_bdf_functor_events", problem="cosine", params=np.array([[1.0], [1.3]]),
+               method="BDF", rtol=1e-10, atol=1e-10,
+               options=dict(events=[dict(functor=0), dict(functor=1, direction=-1)]))
+    yield dict(name="robertson_radau3_functor_events", problem="robertson",
+               params=perturbed_params("robertson", 8, 0.1, 0), method="Radau", rtol=1e-6, atol=1e-6,
+               options=dict(events=[dict(functor=1), dict(functor=0, terminal=True)]))
+    yield dict(name="akzo_radau3_functor_events", problem="akzo_nobel",
+               params=perturbed_params("akzo_nobel", 4, 0.05, 0), method="Radau", rtol=1e-8, atol=1e-8,
+               options=dict(events=[dict(functor=0), dict(component=1, value=1e-3, direction=-1)]))
+    yield dict(name="akzo_bdf_functor_events", problem="akzo_nobel",
+               params=perturbed_params("akzo_nobel", 4, 0.05, 0), method="BDF", rtol=1e-8, atol=1e-8,
+               options=dict(events=[dict(functor=0, terminal=True)]))
     # --- row N2 of SURVEY §8f: analytic Jacobian callables (base.py:299-331)
     yield dict(name="robertson_radau3_jac", problem="robertson",
                params=perturbed_params("robertson", 16, 0.1, 0), method="Radau",

@@ -117,13 +117,17 @@ class Events(ctypes.Structure):
 
 
 def events_struct(events, cls=Events):
-    """events: list of dicts(component, value, of='y'|'yp', direction=0, terminal=False|True|int)."""
+    """events: list of dicts(component, value, of='y'|'yp', direction=0, terminal=False|True|int) or
+    dicts(functor=index, value=0, direction, terminal) for the problem's own event functions."""
     ev = cls()
     ev.n_events = len(events)
     for k, e in enumerate(events):
-        ev.of_yp[k] = 1 if e.get("of", "y") == "yp" else 0
-        ev.component[k] = int(e["component"])
-        ev.value[k] = float(e["value"])
+        if "functor" in e:
+            ev.of_yp[k], ev.component[k] = 2, int(e["functor"])
+        else:
+            ev.of_yp[k] = 1 if e.get("of", "y") == "yp" else 0
+            ev.component[k] = int(e["component"])
+        ev.value[k] = float(e.get("value", 0.0))
         ev.direction[k] = int(np.sign(e.get("direction", 0)))
         term = e.get("terminal", False)
         ev.max_events[k] = 0 if term in (False, None) else (1 if term is True else int(term))

@@ -313,23 +313,40 @@ static void transamp_jac(double t, const double *y, const double *yp, const doub
     for (int k = 0; k < 64; ++k) Jy[k] = -df[k];
 }
 
+/* ---- event functions (twins of problems.py: *_EVENTS and of the device functors' event()) ---- */
+static double robertson_event(int which, double t, const double *y, const double *yp, const double *p)
+{
+    (void)t;
+    return which == 0 ? y[0] - y[2] : yp[0] + yp[1] + p[0] * y[0] * 0.5;
+}
+static double akzo_nobel_event(int which, double t, const double *y, const double *yp, const double *p)
+{
+    (void)which; (void)t; (void)yp; (void)p;
+    return y[0] - y[2];
+}
+static double cosine_event(int which, double t, const double *y, const double *yp, const double *p)
+{
+    return which == 0 ? y[0] - yp[0] : y[0] - p[0] * t * 0.5;
+}
+
 static const struct {
     const char *name;
     int n, n_params;
     orc_residual_fn fn;
     orc_jacobian_fn jac;
+    orc_event_fn event;
 } REGISTRY[] = {
-    {"robertson", 3, 3, robertson, robertson_jac},
-    {"akzo_nobel", 6, 7, akzo_nobel, akzo_nobel_jac},
-    {"transamp", 8, 3, transamp, transamp_jac},
-    {"andrews", 26, 2, andrews, 0},
-    {"rational", 2, 0, rational, rational_jac},
-    {"linear", 2, 0, linear, linear_jac},
-    {"cosine", 1, 1, cosine, 0},
-    {"weissinger", 1, 1, weissinger, 0},
-    {"brenan", 2, 1, brenan, 0},
-    {"transamp1", 5, 3, transamp1, 0},
-    {"blowup", 1, 1, blowup, 0},
+    {"robertson", 3, 3, robertson, robertson_jac, robertson_event},
+    {"akzo_nobel", 6, 7, akzo_nobel, akzo_nobel_jac, akzo_nobel_event},
+    {"transamp", 8, 3, transamp, transamp_jac, 0},
+    {"andrews", 26, 2, andrews, 0, 0},
+    {"rational", 2, 0, rational, rational_jac, 0},
+    {"linear", 2, 0, linear, linear_jac, 0},
+    {"cosine", 1, 1, cosine, 0, cosine_event},
+    {"weissinger", 1, 1, weissinger, 0, 0},
+    {"brenan", 2, 1, brenan, 0, 0},
+    {"transamp1", 5, 3, transamp1, 0, 0},
+    {"blowup", 1, 1, blowup, 0, 0},
 };
 #define N_PROBLEMS ((int)(sizeof(REGISTRY) / sizeof(REGISTRY[0])))
 
@@ -356,6 +373,19 @@ orc_residual_fn orc_problem_residual(int problem_id)
 {
     if (problem_id < 0 || problem_id >= N_PROBLEMS) return 0;
     return REGISTRY[problem_id].fn;
+}
+
+orc_event_fn orc_problem_event(int problem_id)
+{
+    if (problem_id < 0 || problem_id >= N_PROBLEMS) return 0;
+    return REGISTRY[problem_id].event;
+}
+
+orc_event_fn orc_event_of(orc_residual_fn fn)
+{
+    for (int i = 0; i < N_PROBLEMS; ++i)
+        if (REGISTRY[i].fn == fn) return REGISTRY[i].event;
+    return 0;
 }
 
 orc_jacobian_fn orc_problem_jacobian(int problem_id)

@@ -3,12 +3,12 @@
 Importing the package does not need a GPU; calling a solver does, and fails loudly when
 libb200dae.so (the sm_100a CUDA library) is missing — there is no CPU fallback.
 """
-from .batched import BatchedDaeResult, ThresholdEvent, solve_dae_batched, device_residual
+from .batched import BatchedDaeResult, FunctorEvent, ThresholdEvent, solve_dae_batched, device_residual
 from .host_pipeline import solve_dae_batched_host, alloc_host_result, HostResultBuffers
 from .consistent_ic import consistent_initial_conditions_batched, ConsistentICResult
 from .problems import PROBLEMS, Problem, get_problem, perturbed_params, initial_conditions
 
-__all__ = ["solve_dae_batched", "ThresholdEvent", "solve_dae_batched_host", "alloc_host_result", "HostResultBuffers",
+__all__ = ["solve_dae_batched", "ThresholdEvent", "FunctorEvent", "solve_dae_batched_host", "alloc_host_result", "HostResultBuffers",
            "consistent_initial_conditions_batched", "ConsistentICResult", "BatchedDaeResult", "device_residual", "PROBLEMS", "Problem",
            "get_problem", "perturbed_params", "initial_conditions"]
 __version__ = "0.1.0"

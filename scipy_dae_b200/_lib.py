@@ -21,7 +21,8 @@ ST_FINISHED, ST_TOO_SMALL_STEP, ST_NONFINITE, ST_MAX_STEPS, ST_RUNNING, ST_EVENT
 EXPORTS = ("b200dae_version", "b200dae_last_error", "b200dae_num_problems",
            "b200dae_problem_lookup", "b200dae_problem_name", "b200dae_residual",
            "b200dae_solve_radau", "b200dae_solve_bdf", "b200dae_launch_count",
-           "b200dae_fp64_peak_kernel", "b200dae_selftest_fastmath", "b200dae_consistent_ic")
+           "b200dae_fp64_peak_kernel", "b200dae_selftest_fastmath", "b200dae_consistent_ic",
+           "b200dae_problem_num_events")
 
 
 class B200DaeLibraryError(ImportError):
@@ -63,6 +64,8 @@ class Outputs(ctypes.Structure):
                 ("n_eval_valid", ctypes.c_void_p), ("steps_cap", ctypes.c_int64),
                 ("t_steps", ctypes.c_void_p), ("y_steps", ctypes.c_void_p),
                 ("yp_steps", ctypes.c_void_p), ("n_steps", ctypes.c_void_p),
+                ("h_steps", ctypes.c_void_p), ("order_steps", ctypes.c_void_p),
+                ("dense_coef", ctypes.c_void_p), ("coef_rows", ctypes.c_int64),
                 ("events", ctypes.c_void_p)]
 
 
@@ -109,6 +112,8 @@ def load():
     L.b200dae_problem_lookup.argtypes = [ctypes.c_char_p, i32p, i32p]
     L.b200dae_problem_name.restype = ctypes.c_char_p
     L.b200dae_problem_name.argtypes = [ctypes.c_int]
+    L.b200dae_problem_num_events.restype = ctypes.c_int
+    L.b200dae_problem_num_events.argtypes = [ctypes.c_int]
     L.b200dae_launch_count.restype = i64
     L.b200dae_residual.restype = ctypes.c_int
     L.b200dae_residual.argtypes = [ctypes.c_int, i64, i64, dbl, vp, vp, vp, vp, vp]
@@ -126,8 +131,8 @@ def load():
     L.b200dae_fp64_peak_kernel.argtypes = [ctypes.c_int, ctypes.c_int, i64, vp, vp]
     L.b200dae_selftest_fastmath.restype = ctypes.c_int
     L.b200dae_selftest_fastmath.argtypes = [i64, vp, vp, vp, vp]
-    if L.b200dae_version() != 102:
-        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 102")
+    if L.b200dae_version() != 103:
+        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 103")
     _lib = L
     return L
 

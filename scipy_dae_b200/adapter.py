@@ -15,8 +15,10 @@ that protocol for ONE registered system:
                     rtol=1e-6, atol=1e-6, params=(0.04, 1e4, 3e7), t_eval=...)
 
 The device integrates the whole interval in one launch, so the adapter runs it on the first
-``step()`` with the accepted steps recorded and then hands them to the driver one by one; a step's
-``dense_output()`` evaluates that step's interpolant by a deterministic replay with ``t_eval``.
+``step()`` with the accepted steps AND their dense-output coefficients recorded
+(``record_dense``) and then hands them to the driver one by one; a step's ``dense_output()`` is
+that step's interpolant built from the recorded coefficients (scipy_dae_b200/dense.py): ONE launch
+per ``solve_dae`` call, whatever ``t_eval`` / ``dense_output`` ask for.
 ``fun`` must be a registered ``Problem`` (it is callable like the reference's ``fun``) or the
 keyword ``problem=`` must name one; parameters go in ``params=`` (with ``args=`` the reference
 wraps ``fun`` in a lambda, dae.py:380-381, and the functor could not be identified).
@@ -25,13 +27,19 @@ from __future__ import annotations
 
 import numpy as np
 
+from .dense import step_interpolants
 from .problems import Problem, get_problem
+
+MESSAGES = {-1: "Required step size is less than spacing between numbers.",
+            -2: "array must not contain infs or NaNs",
+            -3: "max_steps accepted steps were taken before reaching t_bound."}
 
 
 def _device_solve(problem, t_span, y0, yp0, params, method, t_eval=None, record_steps=0, **options):
     from .batched import solve_dae_batched
     return solve_dae_batched(problem, t_span, y0[None, :], yp0[None, :], params[None, :], method=method,
-                             t_eval=t_eval, record_steps=record_steps, **options).numpy()
+                             t_eval=t_eval, record_steps=record_steps, record_dense=record_steps > 0,
+                             **options).numpy()
 
 
 def make_dae_solver_adapters(DaeSolver, DAEDenseOutput, solve=_device_solve):
@@ -41,7 +49,18 @@ def make_dae_solver_adapters(DaeSolver, DAEDenseOutput, solve=_device_solve):
     return an object with the fields of ``BatchedDaeResult.numpy()`` for one instance; the default
     runs the CUDA path (tests on a machine without a GPU inject the CPU oracle here)."""
 
+    class _TraceDenseOutput(DAEDenseOutput):
+        """A step's interpolant from the device's coefficient trace (no launch)."""
+        def __init__(self, t_old, t, interpolant):
+            super().__init__(t_old, t)
+            self._ip = interpolant
+
+        def _call_impl(self, t):
+            return self._ip(t)
+
     class _ReplayDenseOutput(DAEDenseOutput):
+        """Fallback for solve hooks that return no coefficient trace (the CPU-oracle hook of the
+        tests): evaluates by a deterministic replay with t_eval."""
         def __init__(self, t_old, t, owner):
             super().__init__(t_old, t)
             self._owner = owner
@@ -99,13 +118,18 @@ def make_dae_solver_adapters(DaeSolver, DAEDenseOutput, solve=_device_solve):
             k = int(r.n_steps[0])
             self._trace = (r.t_steps[0, :k], r.y_steps[0, :, :k], r.yp_steps[0, :, :k], int(r.status[0]),
                            (int(r.nfev[0]), int(r.njev[0]), int(r.nlu[0])))
+            self._interpolants = None
+            if getattr(r, "dense_coef", None) is not None:
+                self._interpolants = step_interpolants(
+                    self._method, int(self._opts.get("stages", 3)), r.t_steps[0, :k], r.y_steps[0, :, :k],
+                    r.h_steps[0, :k], r.t_anchor_steps[0, :k], r.order_steps[0, :k], r.dense_coef[0, :k])
 
         def _step_impl(self):
             self._ensure_trace()
             ts, ys, yps, status, counters = self._trace
             if self._k + 1 >= ts.shape[0]:                 # the device run stopped here (dae.py:451-453)
                 self.nfev, self.njev, self.nlu = counters
-                return False, self.TOO_SMALL_STEP
+                return False, MESSAGES.get(status, self.TOO_SMALL_STEP)
             self._k += 1
             self.t = float(ts[self._k])
             self.y = ys[:, self._k].copy()
@@ -128,6 +152,8 @@ def make_dae_solver_adapters(DaeSolver, DAEDenseOutput, solve=_device_solve):
             return y[:, inv], yp[:, inv]
 
         def _dense_output_impl(self):
+            if self._interpolants is not None:
+                return _TraceDenseOutput(self.t_old, self.t, self._interpolants[self._k - 1])
             return _ReplayDenseOutput(self.t_old, self.t, self)
 
     class B200RadauDAE(_B200Solver):

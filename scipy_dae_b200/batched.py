@@ -57,23 +57,41 @@ class ThresholdEvent:
     terminal: object = False
 
 
-def _events_struct(events, n):
+@dataclass(frozen=True)
+class FunctorEvent:
+    """Event function number ``index`` of the problem's device functor, ``g(t, y, y'; p) - value``
+    (``Problem.events[index]`` is its NumPy twin, the callable the reference would be given), with
+    the ``direction`` / ``terminal`` attributes of a ``solve_dae`` event function."""
+    index: int
+    value: float = 0.0
+    direction: float = 0.0
+    terminal: object = False
+
+
+def _events_struct(events, n, n_functor_events=0):
     ev = _lib.Events()
     if len(events) > _lib.MAX_EVENTS:
         raise ValueError(f"at most {_lib.MAX_EVENTS} device events are supported")
     ev.spec.n_events = len(events)
     for k, e in enumerate(events):
         if isinstance(e, dict):
-            e = ThresholdEvent(**e)
-        if not isinstance(e, ThresholdEvent):
-            raise TypeError("device events are ThresholdEvent instances (or dicts with the same fields): "
-                            "a Python event callable cannot run inside the device step loop")
-        if e.of not in ("y", "yp"):
-            raise ValueError("ThresholdEvent.of must be 'y' or 'yp'")
-        if not 0 <= int(e.component) < n:
-            raise ValueError("ThresholdEvent.component out of range")
-        ev.spec.of_yp[k] = 1 if e.of == "yp" else 0
-        ev.spec.component[k] = int(e.component)
+            e = (FunctorEvent(index=e["functor"], **{a: b for a, b in e.items() if a != "functor"})
+                 if "functor" in e else ThresholdEvent(**e))
+        if isinstance(e, FunctorEvent):
+            if not 0 <= int(e.index) < n_functor_events:
+                raise ValueError(f"the problem's functor has {n_functor_events} event functions; got index {e.index}")
+            ev.spec.of_yp[k] = 2
+            ev.spec.component[k] = int(e.index)
+        elif isinstance(e, ThresholdEvent):
+            if e.of not in ("y", "yp"):
+                raise ValueError("ThresholdEvent.of must be 'y' or 'yp'")
+            if not 0 <= int(e.component) < n:
+                raise ValueError("ThresholdEvent.component out of range")
+            ev.spec.of_yp[k] = 1 if e.of == "yp" else 0
+            ev.spec.component[k] = int(e.component)
+        else:
+            raise TypeError("device events are ThresholdEvent / FunctorEvent instances (or dicts with the same "
+                            "fields): a Python event callable cannot run inside the device step loop")
         ev.spec.value[k] = float(e.value)
         ev.spec.direction[k] = int(np.sign(e.direction))
         term = e.terminal
@@ -110,6 +128,10 @@ class BatchedDaeResult:
     y_steps: object = None
     yp_steps: object = None
     n_steps: object = None
+    h_steps: object = None         # [N, K]  h of step k's interpolant (record_dense)
+    t_anchor_steps: object = None  # [N, K]  step end the interpolant is anchored at
+    order_steps: object = None     # [N, K]  BDF order of the interpolant (Radau: stages)
+    dense_coef: object = None      # [N, K, rows]  Radau ZP[n, s] / BDF D[7, n] flattened (include/b200dae.h)
     t_events: object = None        # [N, n_events, cap] (NaN beyond n_events_found)
     y_events: object = None        # [N, n_events, cap, n]
     yp_events: object = None
@@ -128,6 +150,12 @@ class BatchedDaeResult:
 
     def message(self, i: int) -> str:
         return MESSAGES.get(int(self.status[i]), "")
+
+    def solution(self, i: int = 0):
+        """The continuous solution of instance ``i`` (``solve_dae(dense_output=True).sol``,
+        common.py:9-126) from the recorded per-step interpolants; needs ``record_dense=True``."""
+        from .dense import solution_from_trace
+        return solution_from_trace(self, i)
 
     def numpy(self) -> "BatchedDaeResult":
         """Copy every tensor to host NumPy arrays (one device->host transfer per field)."""
@@ -195,7 +223,8 @@ def _warn_extraneous(extraneous):
 
 def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="Radau",
                       t_eval=None, rtol=1e-3, atol=1e-6, *, device=None, stream=None,
-                      record_steps: int = 0, max_steps: int = 0, check_finite: bool = True,
+                      record_steps: int = 0, record_dense: bool = False, max_steps: int = 0,
+                      check_finite: bool = True,
                       events=None, event_cap: int = 16, **options) -> BatchedDaeResult:
     """Integrate ``N`` instances of a registered problem from ``t_span[0]`` to ``t_span[1]``.
 
@@ -206,8 +235,12 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
     params  : [N, p] or [p]    per-instance parameters (the reference's ``args``)
     device  : torch device     default: current CUDA device
     record_steps : int         > 0: also return up to that many accepted steps per instance
+    record_dense : bool        with record_steps: also return every recorded step's dense-output
+                               coefficients (the reference's per-step RadauDenseOutput /
+                               BdfDenseOutput objects); ``result.solution(i)`` is then instance i's
+                               ``DaeSolution`` without any re-integration
     max_steps : int            > 0: stop every instance after that many accepted steps (status -3)
-    events : list of ThresholdEvent   located on the dense output with Brent's method as in the
+    events : list of ThresholdEvent / FunctorEvent   located on the dense output with Brent's method as in the
                                reference (dae.py:30-109, 466-490); a terminal event ends the instance
                                with status 1; up to ``event_cap`` occurrences per event are stored
 
@@ -286,10 +319,20 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
             out.steps_cap = K
             out.t_steps, out.y_steps, out.yp_steps = t_steps.data_ptr(), y_steps.data_ptr(), yp_steps.data_ptr()
             out.n_steps = n_steps.data_ptr()
+        h_steps = order_steps = dense_coef = None
+        if record_dense:
+            if t_steps is None:
+                raise ValueError("`record_dense` needs `record_steps` > 0.")
+            rows = n * int(options.get("stages", 3)) if method == "Radau" else 7 * n
+            h_steps = torch.full((K, 2, ld), float("nan"), **f64)
+            order_steps = torch.zeros((K, ld), **i32)
+            dense_coef = torch.full((K, rows, ld), float("nan"), **f64)
+            out.h_steps, out.order_steps = h_steps.data_ptr(), order_steps.data_ptr()
+            out.dense_coef, out.coef_rows = dense_coef.data_ptr(), rows
 
         ev_struct = t_events = y_events = yp_events = n_found = None
         if events:
-            ev_struct = _events_struct(list(events), n)
+            ev_struct = _events_struct(list(events), n, L.b200dae_problem_num_events(pid))
             ne, cap = ev_struct.spec.n_events, int(event_cap)
             t_events = torch.full((ne, cap, ld), float("nan"), **f64)
             y_events = torch.full((ne, cap, n, ld), float("nan"), **f64)
@@ -381,6 +424,12 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
         res.y_steps = y_steps.permute(2, 1, 0)
         res.yp_steps = yp_steps.permute(2, 1, 0)
         res.n_steps = n_steps
+    if dense_coef is not None:
+        res.h_steps = h_steps[:, 0].t()              # [N, K]
+        res.t_anchor_steps = h_steps[:, 1].t()
+        res.order_steps = order_steps.t()
+        res.dense_coef = dense_coef.permute(2, 0, 1)  # [N, K, rows]
+        res.extra["stages"] = int(options.get("stages", 3)) if method == "Radau" else 0
     if ev_struct is not None:
         res.t_events = t_events.permute(2, 0, 1)            # [N, ne, cap]
         res.y_events = y_events.permute(3, 0, 1, 2)         # [N, ne, cap, n]

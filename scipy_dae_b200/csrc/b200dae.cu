@@ -51,6 +51,8 @@ static int check_common(const ProblemEntry* e, int64_t N, int64_t ld, const doub
         return fail(B200DAE_EINVAL, "m > 0 needs t_eval and y_eval%s", "");
     if (out->steps_cap < 0 || (out->steps_cap > 0 && !out->t_steps))
         return fail(B200DAE_EINVAL, "steps_cap > 0 needs t_steps%s", "");
+    if (out->dense_coef && (out->steps_cap <= 0 || !out->h_steps || !out->y_steps))
+        return fail(B200DAE_EINVAL, "dense_coef needs a step trace (steps_cap > 0, t_steps, y_steps) and h_steps%s", "");
     return 0;
 }
 
@@ -60,9 +62,12 @@ static int check_events(const ProblemEntry* e, const b200dae_outputs* out, Event
     if (!s || s->spec.n_events == 0) return 0;
     if (s->spec.n_events < 0 || s->spec.n_events > B200DAE_MAX_EVENTS)
         return fail(B200DAE_EINVAL, "need 0 <= n_events <= 4%s", "");
-    for (int k = 0; k < s->spec.n_events; ++k)
-        if (s->spec.component[k] < 0 || s->spec.component[k] >= e->n)
-            return fail(B200DAE_EINVAL, "event component out of range%s", "");
+    for (int k = 0; k < s->spec.n_events; ++k) {
+        const int kind = s->spec.of_yp[k];
+        if (kind < 0 || kind > 2) return fail(B200DAE_EINVAL, "event kind must be 0 (y), 1 (y') or 2 (functor event)%s", "");
+        if (s->spec.component[k] < 0 || s->spec.component[k] >= (kind == 2 ? e->n_events : e->n))
+            return fail(B200DAE_EINVAL, kind == 2 ? "problem '%s' has no such event function" : "event component out of range%s", e->name);
+    }
     if (s->cap <= 0 || !s->t_events || !s->n_found)
         return fail(B200DAE_EINVAL, "events need cap > 0, t_events and n_found%s", "");
     ev->spec = s->spec;
@@ -78,7 +83,8 @@ static b200dae_outputs normalise(const b200dae_outputs* out) {
     b200dae_outputs o = *out;
     o.events = nullptr;
     if (o.m == 0) { o.t_eval = nullptr; o.y_eval = nullptr; o.yp_eval = nullptr; }
-    if (o.steps_cap == 0) { o.t_steps = nullptr; o.y_steps = nullptr; o.yp_steps = nullptr; }
+    if (o.steps_cap == 0) { o.t_steps = nullptr; o.y_steps = nullptr; o.yp_steps = nullptr; o.dense_coef = nullptr; }
+    if (o.dense_coef == nullptr) { o.h_steps = nullptr; o.order_steps = nullptr; }
     return o;
 }
 
@@ -127,6 +133,11 @@ int b200dae_num_problems(void) {
     int cnt;
     registry(&cnt);
     return cnt;
+}
+
+int b200dae_problem_num_events(int problem_id) {
+    const ProblemEntry* e = find_problem(problem_id);
+    return e ? e->n_events : B200DAE_ENOPROBLEM;
 }
 
 int b200dae_problem_lookup(const char* name, int32_t* n, int32_t* n_params) {
@@ -187,6 +198,8 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
         if (tb->T[(s - 1) * s + l] != ((l % 2 == 0) ? 1.0 : 0.0) || tb->TI[l] == 0.0)
             return fail(B200DAE_EINVAL, "Radau tables are not in the reference's normalisation (radau.py:72-84)%s", "");
     }
+    if (out->dense_coef && out->coef_rows != (int64_t)e->n * s)
+        return fail(B200DAE_EINVAL, "Radau dense_coef needs coef_rows = n * stages%s (got %lld)", "", (long long)out->coef_rows);
     if (N == 0) return 0;
 
     RadauLaunch L;
@@ -239,6 +252,8 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
         return fail(B200DAE_EINVAL, "Ensure that 1 <= max_order <= 6.%s", "");
     if (!(opts->max_step > 0)) return fail(B200DAE_EINVAL, "`max_step` must be positive.%s", "");
     if (opts->first_step > fabs(t_bound - t0)) return fail(B200DAE_EINVAL, "`first_step` exceeds bounds.%s", "");
+    if (out->dense_coef && (out->coef_rows != (int64_t)e->n * kBdfQ || !out->order_steps))
+        return fail(B200DAE_EINVAL, "BDF dense_coef needs order_steps and coef_rows = 7 * n%s (got %lld)", "", (long long)out->coef_rows);
     if (N == 0) return 0;
 
     BdfLaunch L;

@@ -161,9 +161,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
     EventState evs;                  // g = event(t0, y0, yp0), dae.py:436
     if (!kLean) for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
         evs.count[k] = evs.found[k] = 0;
-        evs.g[k] = (k < L.ev.spec.n_events)
-            ? (L.ev.spec.of_yp[k] ? pick<N>(yp, L.ev.spec.component[k]) : pick<N>(y, L.ev.spec.component[k])) - L.ev.spec.value[k]
-            : 0.0;
+        evs.g[k] = (k < L.ev.spec.n_events) ? event_quantity<P, N>(L.ev.spec, k, t, y, yp, p) - L.ev.spec.value[k] : 0.0;
     }
 
     double hl = 0.0, min_step = 0.0, h = 0.0, t_new = 0.0, c = 0.0;
@@ -402,10 +400,13 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
         // events on this step's dense output (dae.py:466-490); a terminal one moves the step end
         bool ev_stop = false;
         if (!kLean && L.ev.spec.n_events > 0) {
-            auto dense = [&](double te, int comp, bool of_yp) -> double {
+            auto dense = [&](double te, int comp, int kind) -> double {
                 double ya[N], ypa[N];
                 dense_all(te, ya, ypa);
-                return of_yp ? ypa[comp] : ya[comp];
+                if constexpr (EventOf<P>::kNum > 0) {
+                    if (kind == 2) return EventOf<P>::eval(comp, te, ya, ypa, p);
+                }
+                return kind == 1 ? ypa[comp] : ya[comp];
             };
             auto record = [&](int k, int idx, double tr) {
                 double ya[N], ypa[N];
@@ -419,7 +420,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             };
             double gnew[B200DAE_MAX_EVENTS];
             for (int k = 0; k < B200DAE_MAX_EVENTS; ++k)
-                gnew[k] = (L.ev.spec.of_yp[k] ? pick<N>(yp, L.ev.spec.component[k]) : pick<N>(y, L.ev.spec.component[k])) - L.ev.spec.value[k];
+                gnew[k] = event_quantity<P, N>(L.ev.spec, k, t, y, yp, p) - L.ev.spec.value[k];
             double ts = t;
             if (handle_events(L.ev, evs, t_prev, t, dir, gnew, dense, record, ts)) {
                 ev_stop = true;
@@ -449,6 +450,14 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             for (int j = 0; j < N; ++j) {
                 if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + j) * ld + inst] = y[j];
                 if (L.out.yp_steps) L.out.yp_steps[((int64_t)nst * N + j) * ld + inst] = yp[j];
+            }
+            if (L.out.dense_coef != nullptr) {     // this step's BdfDenseOutput (bdf.py:417-419)
+                L.out.h_steps[((int64_t)nst * 2) * ld + inst] = hh;
+                L.out.h_steps[((int64_t)nst * 2 + 1) * ld + inst] = t_end;
+                if (L.out.order_steps) L.out.order_steps[(int64_t)nst * ld + inst] = order;
+                for (int i = 0; i <= order; ++i)
+                    for (int j = 0; j < N; ++j)
+                        L.out.dense_coef[((int64_t)nst * (kBdfQ * N) + i * N + j) * ld + inst] = D[i * N + j];
             }
             ++nst;
         }

@@ -156,7 +156,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     if (kEv) for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
         evs.count[k] = evs.found[k] = 0;
         evs.g[k] = (k < L.ev.spec.n_events)
-            ? g.bcast(L.ev.spec.of_yp[k] ? yp : y, L.ev.spec.component[k]) - L.ev.spec.value[k] : 0.0;
+            ? event_quantity_group<P, N>(g, L.ev.spec, k, t, y, yp, p) - L.ev.spec.value[k] : 0.0;
     }
 
     double hl = 0.0, min_step = 0.0, h = 0.0, t_new = 0.0, c = 0.0;
@@ -398,10 +398,18 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         // events on this step's dense output (dae.py:466-490); a terminal one moves the step end
         bool ev_stop = false;
         if (kEv && L.ev.spec.n_events > 0) {
-            auto dense = [&](double te, int comp, bool of_yp) -> double {
+            auto dense = [&](double te, int comp, int kind) -> double {
                 double av, bv;
                 dense_lane(te, av, bv);
-                return g.bcast(of_yp ? bv : av, comp);
+                if constexpr (EventOf<P>::kNum > 0) {
+                    if (kind == 2) {
+                        double ya[N], ypa[N];
+#pragma unroll
+                        for (int j = 0; j < N; ++j) { ya[j] = g.bcast(av, j); ypa[j] = g.bcast(bv, j); }
+                        return EventOf<P>::eval(comp, te, ya, ypa, p);
+                    }
+                }
+                return g.bcast(kind == 1 ? bv : av, comp);
             };
             auto record = [&](int k, int idx, double tr) {
                 double av, bv;
@@ -415,7 +423,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             };
             double gnew[B200DAE_MAX_EVENTS];
             for (int k = 0; k < B200DAE_MAX_EVENTS; ++k)
-                gnew[k] = g.bcast(L.ev.spec.of_yp[k] ? yp : y, L.ev.spec.component[k]) - L.ev.spec.value[k];
+                gnew[k] = event_quantity_group<P, N>(g, L.ev.spec, k, t, y, yp, p) - L.ev.spec.value[k];
             double ts = t;
             if (handle_events(L.ev, evs, t_prev, t, dir, gnew, dense, record, ts)) {
                 ev_stop = true;
@@ -444,6 +452,18 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             if (act) {
                 if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + lane) * ld + inst] = y;
                 if (L.out.yp_steps) L.out.yp_steps[((int64_t)nst * N + lane) * ld + inst] = yp;
+            }
+            if (L.out.dense_coef != nullptr) {     // this step's BdfDenseOutput (bdf.py:417-419)
+                if (lane == 0) {
+                    L.out.h_steps[((int64_t)nst * 2) * ld + inst] = hh;
+                    L.out.h_steps[((int64_t)nst * 2 + 1) * ld + inst] = t_end;
+                    if (L.out.order_steps) L.out.order_steps[(int64_t)nst * ld + inst] = order;
+                }
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < kBdfQ; ++i)
+                        if (i <= order) L.out.dense_coef[((int64_t)nst * (kBdfQ * N) + i * N + lane) * ld + inst] = D[i];
+                }
             }
             ++nst;
         }

@@ -3,13 +3,16 @@
 // Replaces, per instance, the event part of solve_dae's loop (dae.py:426-443, 466-490) with
 // handle_events (dae.py:58-109), solve_event_equation (dae.py:30-55: scipy.optimize.brentq with
 // xtol = rtol = 4 EPS on the step's dense output) and scipy's find_active_events
-// (scipy/integrate/_ivp/ivp.py).  A Python event callable cannot run on the device; events are
-// THRESHOLD events  g_k(t, y, y') = x[component_k] - value_k,  x = y or y',  with the
-// reference's `direction` and `terminal` attributes (terminal = k stops at the k-th occurrence).
+// (scipy/integrate/_ivp/ivp.py).  A Python event callable cannot run on the device; an event is
+// either a THRESHOLD  g_k(t, y, y') = x[component_k] - value_k,  x = y (kind 0) or y' (kind 1), or
+// one of the problem functor's own event functions  g_k = P::event(component_k, t, y, y', p) - value_k
+// (kind 2, problems.cuh: EventOf), with the reference's `direction` and `terminal` attributes
+// (terminal = k stops at the k-th occurrence).  The kind is spec.of_yp[k].
 #pragma once
 #include <math.h>
 #include <stdint.h>
 #include "../../include/b200dae.h"
+#include "problems.cuh"
 
 namespace b200dae {
 
@@ -73,7 +76,8 @@ __device__ __forceinline__ double brentq_dev(F f, double xa, double xb) {
 
 // After an accepted step [t_old, t_new].
 //   gnew[k]                    event values at the step end
-//   dense(t, comp, of_yp)      one component of the step's dense output (uniform across a group)
+//   dense(t, comp, kind)       the event quantity on the step's dense output at t (uniform across a
+//                              group): y[comp], y'[comp] or the functor's event function `comp`
 //   record(k, idx, t_root)     store y(t_root), y'(t_root) as occurrence idx of event k
 // Returns true when a terminal event fired; t_stop is then the event time that replaces t_new.
 template <class Dense, class Record>
@@ -94,9 +98,9 @@ __device__ __forceinline__ bool handle_events(const EventLaunch& E, EventState& 
             const int k = act[a];
             S.count[k] += 1;
             const int comp = E.spec.component[k];
-            const bool of_yp = E.spec.of_yp[k] != 0;
+            const int kind = E.spec.of_yp[k];
             const double c = E.spec.value[k];
-            roots[a] = brentq_dev([&](double tt) { return dense(tt, comp, of_yp) - c; }, t_old, t_new);
+            roots[a] = brentq_dev([&](double tt) { return dense(tt, comp, kind) - c; }, t_old, t_new);
         }
         bool any_term = false;
         for (int a = 0; a < na; ++a)
@@ -132,6 +136,34 @@ __device__ __forceinline__ double pick(const double* a, int j) {
 #pragma unroll
     for (int i = 1; i < N; ++i) r = (j == i) ? a[i] : r;
     return r;
+}
+
+// event quantity k at a point where the whole state is at hand (thread-per-system kernels)
+template <class P, int N>
+__device__ __forceinline__ double event_quantity(const b200dae_event_spec& sp, int k, double t, const double* y,
+                                                 const double* yp, const double* p) {
+    const int kind = sp.of_yp[k], comp = sp.component[k];
+    if constexpr (EventOf<P>::kNum > 0) {
+        if (kind == 2) return EventOf<P>::eval(comp, t, y, yp, p);
+    }
+    return kind == 1 ? pick<N>(yp, comp) : pick<N>(y, comp);
+}
+
+// the same in the group kernels: lane j holds component j (yv, ypv); the event functor needs the whole
+// vectors, which every lane gathers by shuffles (the kind is uniform across the group)
+template <class P, int N, class Grp>
+__device__ __forceinline__ double event_quantity_group(const Grp& g, const b200dae_event_spec& sp, int k, double t,
+                                                       double yv, double ypv, const double* p) {
+    const int kind = sp.of_yp[k], comp = sp.component[k];
+    if constexpr (EventOf<P>::kNum > 0) {
+        if (kind == 2) {
+            double ya[N], ypa[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) { ya[j] = g.bcast(yv, j); ypa[j] = g.bcast(ypv, j); }
+            return EventOf<P>::eval(comp, t, ya, ypa, p);
+        }
+    }
+    return g.bcast(kind == 1 ? ypv : yv, comp);
 }
 
 }  // namespace b200dae

@@ -38,7 +38,7 @@ typedef int (*residual_launcher)(int64_t, int64_t, double, const double*, const 
 
 struct ProblemEntry {
     const char* name;
-    int n, n_params;
+    int n, n_params, n_events;                      // n_events: event functions of the functor (EventOf)
     radau_launcher radau[B200DAE_MAX_STAGES + 1];   // indexed by the number of stages
     bdf_launcher bdf;
     residual_launcher residual;
@@ -252,6 +252,7 @@ static ProblemEntry make_entry() {
     e.name = P::name();
     e.n = P::N;
     e.n_params = P::NP;
+    e.n_events = EventOf<P>::kNum;
     e.radau[3] = launch_radau<P, 3>;
     if constexpr (S1) e.radau[1] = launch_radau<P, 1>;
     if constexpr (S5) e.radau[5] = launch_radau<P, 5>;

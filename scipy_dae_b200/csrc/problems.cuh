@@ -43,6 +43,23 @@ __device__ __forceinline__ R64 rcos(R64 a) { return R64(cos(a.v)); }
 __device__ __forceinline__ R64 rexp(R64 a) { return R64(exp(a.v)); }
 __device__ __forceinline__ R64 rsqrt64(R64 a) { return R64(sqrt(a.v)); }
 
+// Event functions g(t, y, y'; p) of a problem (the reference's `events=` callables, dae.py:226-247,
+// 426-443): a functor may provide  kNumEvents  and
+//   static __device__ double event(int which, double t, const double* y, const double* yp, const double* p).
+// EventOf<P> answers for functors that provide none.
+template <class P, class = void>
+struct EventOf {
+    static constexpr int kNum = 0;
+    __device__ __forceinline__ static double eval(int, double, const double*, const double*, const double*) { return nan(""); }
+};
+template <class P>
+struct EventOf<P, decltype((void)P::kNumEvents)> {
+    static constexpr int kNum = P::kNumEvents;
+    __device__ __forceinline__ static double eval(int which, double t, const double* y, const double* yp, const double* p) {
+        return P::event(which, t, y, yp, p);
+    }
+};
+
 struct Robertson {
     static constexpr int N = 3, NP = 3;
     static constexpr const char* name() { return "robertson"; }
@@ -64,6 +81,11 @@ struct Robertson {
         out[0] = __dadd_rn(yp[0], b);
         out[1] = __dsub_rn(yp[1], __dsub_rn(b, __dmul_rn(__dmul_rn(k3, y[1]), y[1])));
         out[2] = __dsub_rn(__dadd_rn(__dadd_rn(y[0], y[1]), y[2]), 1.0);
+    }
+    // event 0: y1 - y3 (the reactant and the product cross), event 1: y1' + y2' + k1 y1 / 2
+    static constexpr int kNumEvents = 2;
+    __device__ __forceinline__ static double event(int which, double, const double* y, const double* yp, const double* p) {
+        return which == 0 ? (R64(y[0]) - R64(y[2])).v : (R64(yp[0]) + R64(yp[1]) + R64(p[0]) * R64(y[0]) * 0.5).v;
     }
     static constexpr bool kHasJac = true;      // reference: examples/daes/robertson.py:38-47
     template <class M>
@@ -100,6 +122,10 @@ struct AkzoNobel {
         out[3] = (R64(yp[3]) - (-r2 + r3 - 2.0 * r4)).v;
         out[4] = (R64(yp[4]) - (r2 - r3 + r5)).v;
         out[5] = (-(ks * y0 * y3 - y5)).v;
+    }
+    static constexpr int kNumEvents = 1;       // event 0: y1 - y3
+    __device__ __forceinline__ static double event(int, double, const double* y, const double*, const double*) {
+        return (R64(y[0]) - R64(y[2])).v;
     }
     static constexpr bool kHasJac = true;      // reference: examples/daes/akzo_nobel.py:52-103
     template <class M>
@@ -242,6 +268,12 @@ struct Cosine {
     __device__ __forceinline__ static void eval(double t, const double*, const double* yp, const double* p,
                                                 double* out) {
         out[0] = (R64(yp[0]) - R64(p[0]) * rcos(R64(t))).v;
+    }
+    // events that are not thresholds on one component: 0: y - y' (a sin t = a cos t at t = pi/4 + k pi),
+    // 1: y - a t / 2 (depends on t)
+    static constexpr int kNumEvents = 2;
+    __device__ __forceinline__ static double event(int which, double t, const double* y, const double* yp, const double* p) {
+        return which == 0 ? (R64(y[0]) - R64(yp[0])).v : (R64(y[0]) - R64(p[0]) * R64(t) * 0.5).v;
     }
     static constexpr bool kHasJac = false;
 };

@@ -187,9 +187,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
 #pragma unroll
         for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
             evs.count[k] = evs.found[k] = 0;
-            evs.g[k] = (k < L.ev.spec.n_events)
-                ? (L.ev.spec.of_yp[k] ? pick<N>(yp, L.ev.spec.component[k]) : pick<N>(y, L.ev.spec.component[k])) - L.ev.spec.value[k]
-                : 0.0;
+            evs.g[k] = (k < L.ev.spec.n_events) ? event_quantity<P, N>(L.ev.spec, k, t, y, yp, p) - L.ev.spec.value[k] : 0.0;
         }
     }
 
@@ -558,10 +556,13 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     ypa[j] = b;
                 }
             };
-            auto dense = [&](double te, int comp, bool of_yp) -> double {
+            auto dense = [&](double te, int comp, int kind) -> double {
                 double ya[N], ypa[N];
                 dense_all(te, ya, ypa);
-                return of_yp ? pick<N>(ypa, comp) : pick<N>(ya, comp);
+                if constexpr (EventOf<P>::kNum > 0) {
+                    if (kind == 2) return EventOf<P>::eval(comp, te, ya, ypa, p);
+                }
+                return kind == 1 ? pick<N>(ypa, comp) : pick<N>(ya, comp);
             };
             auto record = [&](int k, int idx, double tr) {
                 double ya[N], ypa[N];
@@ -577,8 +578,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
             double gnew[B200DAE_MAX_EVENTS];
 #pragma unroll
             for (int k = 0; k < B200DAE_MAX_EVENTS; ++k)
-                gnew[k] = (L.ev.spec.of_yp[k] ? pick<N>(Yp[S - 1], L.ev.spec.component[k])
-                                              : pick<N>(Y[S - 1], L.ev.spec.component[k])) - L.ev.spec.value[k];
+                gnew[k] = event_quantity<P, N>(L.ev.spec, k, t_new, Y[S - 1], Yp[S - 1], p) - L.ev.spec.value[k];
             double ts = t_new;
             if (handle_events(L.ev, evs, t, t_new, dir, gnew, dense, record, ts)) {
                 ev_stop = true;
@@ -624,6 +624,14 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
             for (int j = 0; j < N; ++j) {
                 if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + j) * ld + inst] = y[j];
                 if (L.out.yp_steps) L.out.yp_steps[((int64_t)nst * N + j) * ld + inst] = yp[j];
+            }
+            if (L.out.dense_coef != nullptr) {     // this step's RadauDenseOutput (radau.py:661-679)
+                L.out.h_steps[((int64_t)nst * 2) * ld + inst] = h;
+                L.out.h_steps[((int64_t)nst * 2 + 1) * ld + inst] = t_new;
+                if (L.out.order_steps) L.out.order_steps[(int64_t)nst * ld + inst] = S;
+#pragma unroll U
+                for (int k = 0; k < N * S; ++k)
+                    L.out.dense_coef[((int64_t)nst * (N * S) + k) * ld + inst] = ZP[k];
             }
             ++nst;
         }

@@ -268,7 +268,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     if (!kLean) for (int k = 0; k < B200DAE_MAX_EVENTS; ++k) {
         evs.count[k] = evs.found[k] = 0;
         evs.g[k] = (k < L.ev.spec.n_events)
-            ? g.bcast(L.ev.spec.of_yp[k] ? yp : y, L.ev.spec.component[k]) - L.ev.spec.value[k] : 0.0;
+            ? event_quantity_group<P, N>(g, L.ev.spec, k, t, y, yp, p) - L.ev.spec.value[k] : 0.0;
     }
 
     double hl = 0.0, hl_old = 0.0, errl_old = 0.0, min_step = 0.0, factor = 0.0;
@@ -574,10 +574,18 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         double t_lim = t_new, y_stop = 0.0, yp_stop = 0.0;
         bool ev_stop = false;
         if (!kLean && L.ev.spec.n_events > 0) {
-            auto dense = [&](double te, int comp, bool of_yp) -> double {
+            auto dense = [&](double te, int comp, int kind) -> double {
                 double av, bv;
                 dense_lane(te, av, bv);
-                return g.bcast(of_yp ? bv : av, comp);
+                if constexpr (EventOf<P>::kNum > 0) {
+                    if (kind == 2) {
+                        double ya[N], ypa[N];
+#pragma unroll
+                        for (int j = 0; j < N; ++j) { ya[j] = g.bcast(av, j); ypa[j] = g.bcast(bv, j); }
+                        return EventOf<P>::eval(comp, te, ya, ypa, p);
+                    }
+                }
+                return g.bcast(kind == 1 ? bv : av, comp);
             };
             auto record = [&](int k, int idx, double tr) {
                 double av, bv;
@@ -591,7 +599,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
             };
             double gnew[B200DAE_MAX_EVENTS];
             for (int k = 0; k < B200DAE_MAX_EVENTS; ++k)
-                gnew[k] = g.bcast(L.ev.spec.of_yp[k] ? Yp[S - 1] : Y[S - 1], L.ev.spec.component[k]) - L.ev.spec.value[k];
+                gnew[k] = event_quantity_group<P, N>(g, L.ev.spec, k, t_new, Y[S - 1], Yp[S - 1], p) - L.ev.spec.value[k];
             double ts = t_new;
             if (handle_events(L.ev, evs, t, t_new, dir, gnew, dense, record, ts)) {
                 ev_stop = true;
@@ -621,6 +629,18 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
             if (act) {
                 if (L.out.y_steps) L.out.y_steps[((int64_t)nst * N + lane) * ld + inst] = y;
                 if (L.out.yp_steps) L.out.yp_steps[((int64_t)nst * N + lane) * ld + inst] = yp;
+            }
+            if (L.out.dense_coef != nullptr) {     // this step's RadauDenseOutput (radau.py:661-679)
+                if (lane == 0) {
+                    L.out.h_steps[((int64_t)nst * 2) * ld + inst] = h;
+                    L.out.h_steps[((int64_t)nst * 2 + 1) * ld + inst] = t_new;
+                    if (L.out.order_steps) L.out.order_steps[(int64_t)nst * ld + inst] = S;
+                }
+                if (act) {
+#pragma unroll
+                    for (int k = 0; k < S; ++k)
+                        L.out.dense_coef[((int64_t)nst * (N * S) + lane * S + k) * ld + inst] = ZP[k];
+                }
             }
             ++nst;
         }

@@ -11,41 +11,8 @@ from __future__ import annotations
 import numpy as np
 
 from .batched import MESSAGES, METHODS, solve_dae_batched
+from .dense import DaeSolution  # noqa: F401  (re-exported: the type of DaeResult.sol)
 from .problems import Problem, get_problem
-
-
-class ReplayDaeSolution:
-    """Continuous solution ``sol(t) -> (y, yp)`` with the call signature of the reference's
-    ``DaeSolution`` (common.py:9-126).
-
-    The reference keeps one interpolant object per step.  The device step loop is deterministic,
-    so the same piecewise interpolant is obtained by replaying the integration with the requested
-    times as ``t_eval`` (dae.py:496-515 evaluates exactly the per-step dense output there; a time
-    equal to a step end belongs to the earlier step, as in ``DaeSolution``).  Each call costs one
-    launch; times outside ``[t_min, t_max]`` are rejected instead of extrapolated.
-    """
-
-    def __init__(self, solve, t_span, t_reached, n):
-        self._solve, self.n = solve, n
-        t0, t1 = float(t_span[0]), float(t_reached)
-        self.ascending = t1 >= t0
-        self.t_min, self.t_max = (t0, t1) if self.ascending else (t1, t0)
-
-    def __call__(self, t):
-        t = np.asarray(t, dtype=float)
-        if t.ndim > 1:
-            raise ValueError("`t` must be a float or a 1-D array.")
-        ts = np.atleast_1d(t)
-        if np.any(ts < self.t_min) or np.any(ts > self.t_max):
-            raise ValueError(f"`t` must lie in [{self.t_min}, {self.t_max}] (no extrapolation on the device path)")
-        uniq, inv = np.unique(ts, return_inverse=True)
-        order = uniq if self.ascending else uniq[::-1]
-        r = self._solve(order)
-        y, yp = r.y[0], r.yp[0]                                  # [n, m] in integration order
-        if not self.ascending:
-            y, yp = y[:, ::-1], yp[:, ::-1]
-        y, yp = y[:, inv], yp[:, inv]
-        return (y[:, 0], yp[:, 0]) if t.ndim == 0 else (y, yp)
 
 
 class DaeResult(dict):
@@ -94,11 +61,12 @@ def solve_dae(fun, t_span, y0=None, yp0=None, method="Radau", t_eval=None, dense
     y0b = None if y0 is None else np.asarray(y0, dtype=float)[None, :]
     yp0b = None if yp0 is None else np.asarray(yp0, dtype=float)[None, :]
 
-    cap = 0 if t_eval is not None else int(max_steps_recorded)
+    cap = 0 if (t_eval is not None and not dense_output) else int(max_steps_recorded)
     while True:
         r = solve_dae_batched(prob, t_span, y0b, yp0b, params[None, :], method=method, t_eval=t_eval,
-                              device=device, record_steps=cap, events=events, **options).numpy()
-        if t_eval is not None or r.n_steps[0] < cap or r.n_accepted[0] + 1 <= cap:
+                              device=device, record_steps=cap, record_dense=bool(dense_output and cap),
+                              events=events, **options).numpy()
+        if cap == 0 or r.n_steps[0] < cap or r.n_accepted[0] + 1 <= cap:
             break
         cap *= 4       # the step trace overflowed: rerun with a larger trace
 
@@ -119,10 +87,9 @@ def solve_dae(fun, t_span, y0=None, yp0=None, method="Radau", t_eval=None, dense
         yp_ev = [r.yp_events[0, k, :nf[k]] for k in range(len(events))]
     sol = None
     if dense_output:
-        def _replay(times, _o=dict(options)):
-            return solve_dae_batched(prob, t_span, y0b, yp0b, params[None, :], method=method, t_eval=times,
-                                     device=device, events=events, **_o).numpy()
-        sol = ReplayDaeSolution(_replay, t_span, r.t_final[0], prob.n)
+        # DaeSolution over the accepted steps (dae.py:520-526 with common.py:9-126), built from the
+        # per-step coefficients the same launch recorded: no re-integration
+        sol = r.solution(0) if int(r.n_steps[0]) > 1 else None
     return DaeResult(t=t, y=y, yp=yp, sol=sol, t_events=t_ev, y_events=y_ev, yp_events=yp_ev,
                      nfev=int(r.nfev[0]), njev=int(r.njev[0]), nlu=int(r.nlu[0]),
                      status=-1 if status < 0 else status,

@@ -46,6 +46,19 @@ class Problem:
     jacobian: Callable = None        # optional analytic jac(t, y, yp, *params) -> (Jy[n, n], Jyp[n, n])
     solution: Callable = None        # optional exact solution(t, *params) -> (y[n, ...], yp[n, ...])
     t0_default: float = None         # start of t_span (for problems whose ICs depend on it)
+    events: tuple = ()               # NumPy twins g(t, y, yp, *params) of the functor's event functions
+
+    def event_callable(self, index, spec=None):
+        """Event function `index` as the callable the reference's `events=` takes (dae.py:226-247),
+        with `value` subtracted and the `direction` / `terminal` attributes of `spec` set."""
+        spec = spec or {}
+        g, c = self.events[int(index)], float(spec.get("value", 0.0))
+        # (for n = 1 the reference's dense output hands a 0-d array to the event function: np.squeeze,
+        # radau.py:696-697)
+        fn = lambda t, y, yp, *a: g(t, np.atleast_1d(y), np.atleast_1d(yp), *a) - c          # noqa: E731
+        fn.direction = float(spec.get("direction", 0))
+        fn.terminal = spec.get("terminal", False)
+        return fn
 
     def __call__(self, t, y, yp, *params):
         if not params:
@@ -73,6 +86,12 @@ def robertson_jacobian(t, y, yp, k1, k2, k3):
                    [1.0, 1.0, 1.0]])
     Jyp = np.diag([1.0, 1.0, 0.0])
     return Jy, Jyp
+
+
+ROBERTSON_EVENTS = (lambda t, y, yp, k1, k2, k3: y[0] - y[2],
+                    lambda t, y, yp, k1, k2, k3: yp[0] + yp[1] + k1 * y[0] * 0.5)
+AKZO_EVENTS = (lambda t, y, yp, *p: y[0] - y[2],)
+COSINE_EVENTS = (lambda t, y, yp, a: y[0] - yp[0], lambda t, y, yp, a: y[0] - a * t * 0.5)
 
 
 def robertson_initial(params):
@@ -490,14 +509,14 @@ ROBERTSON = _register(Problem(
     name="robertson", n=3, n_params=3, residual=robertson_residual,
     default_params=(0.04, 1e4, 3e7), initial=robertson_initial, t_span=(0.0, 1e7),
     initial_batch=robertson_initial_batch, jacobian=robertson_jacobian,
-    param_names=("k1", "k2", "k3"),
+    param_names=("k1", "k2", "k3"), events=ROBERTSON_EVENTS,
     doc="Robertson chemical kinetics as an index-1 DAE"))
 
 AKZO_NOBEL = _register(Problem(
     name="akzo_nobel", n=6, n_params=7, residual=akzo_residual,
     default_params=(18.7, 0.58, 0.09, 0.42, 34.4, 3.3, 115.83),
     initial=akzo_initial, t_span=(0.0, 180.0), jacobian=akzo_jacobian,
-    param_names=("k1", "k2", "k3", "k4", "kbig", "kla", "ks"),
+    param_names=("k1", "k2", "k3", "k4", "kbig", "kla", "ks"), events=AKZO_EVENTS,
     doc="Akzo Nobel chemical reaction, index 1"))
 
 TRANSAMP = _register(Problem(
@@ -528,7 +547,7 @@ LINEAR = _register(Problem(
 COSINE = _register(Problem(
     name="cosine", n=1, n_params=1, residual=cosine_residual, default_params=(1.0,),
     initial=_ic_from_solution(cosine_solution, -0.1), t_span=(-0.1, -0.1 + 2 * np.pi),
-    solution=cosine_solution, t0_default=-0.1, param_names=("a",),
+    solution=cosine_solution, t0_default=-0.1, param_names=("a",), events=COSINE_EVENTS,
     doc="y' = a cos t, the problem of the reference's test_events.py"))
 
 WEISSINGER = _register(Problem(

@@ -262,10 +262,11 @@ def test_group_and_thread_regimes_agree():
 
 def test_single_system_surface_events_and_dense_output():
     """scipy_dae_b200.integrate.solve_dae: the reference's single-system signature with events
-    (ThresholdEvent) and dense_output=True (sol(t) by deterministic replay)."""
-    from scipy_dae_b200 import ThresholdEvent
+    (ThresholdEvent) and dense_output=True (sol(t) from the dense-output trace of the same launch)."""
+    from scipy_dae_b200 import ThresholdEvent, _lib
     from scipy_dae_b200.integrate import solve_dae
     ev = [ThresholdEvent(component=0, value=0.9), ThresholdEvent(component=2, value=0.5, terminal=True)]
+    n0 = _lib.launch_count()
     r = solve_dae("robertson", (0.0, 1e7), method="Radau", rtol=1e-6, atol=1e-6, events=ev, dense_output=True)
     assert r.status == 1 and r.message == "A termination event occurred."
     assert len(r.t_events[0]) == 1 and len(r.t_events[1]) == 1
@@ -278,5 +279,13 @@ def test_single_system_surface_events_and_dense_output():
     Y, Yp = r.sol(tt[[2, 0, 1]])                             # any order, repeated times allowed
     assert Y.shape == (3, 3) and np.allclose(Y[:, 1], r.y[:, 3], rtol=1e-12, atol=1e-15)
     assert (np.abs(Y.sum(axis=0) - 1.0) < 1e-6).all()
-    with pytest.raises(ValueError):
-        r.sol(2 * r.t[-1])
+    assert _lib.launch_count() - n0 == 1                     # sol(t) costs no launch
+    # the last segment ends at the terminal event: its interpolant is the full step's, cut short
+    ye, _ = r.sol(r.t_events[1][0])
+    assert abs(ye[2] - 0.5) < 1e-9
+    # BDF: the Newton-form interpolant of every step
+    rb = solve_dae("robertson", (0.0, 1e5), method="BDF", rtol=1e-6, atol=1e-6, dense_output=True)
+    yb, ypb = rb.sol(rb.t[7])
+    assert np.allclose(yb, rb.y[:, 7], rtol=1e-12, atol=1e-15)
+    tm = 0.5 * (rb.t[20] + rb.t[21])
+    assert abs(rb.sol(tm)[0].sum() - 1.0) < 1e-6

@@ -29,6 +29,18 @@ EVENT_CASES = [   # tests/test_events.py:28-84: (events, t_events, y_events, yp_
 
 # ------------------------------------------------------------------------------------------------
 # CPU: oracle vs exact solutions
+@pytest.mark.parametrize("method", ["BDF", "Radau"])
+def test_oracle_functor_events_known_answers(method, oracle):
+    """Event functions of the problem functor (not thresholds on one component): y - y' and y - t / 2."""
+    pr = get_problem("cosine")
+    y0, yp0 = pr.initial((1.0,))
+    r = oracle.solve_ensemble("cosine", np.array([[1.0]]), y0[None, :], yp0[None, :], pr.t_span, method=method,
+                              rtol=1e-12, atol=1e-12, events=[dict(functor=0), dict(functor=1, direction=-1, terminal=True)])
+    assert r["status"][0] == 1 and r["n_events_found"][0].tolist() == [1, 1]
+    assert abs(r["t_events"][0, 0, 0] - np.pi / 4) < 1e-7 and abs(r["t_events"][0, 1, 0] - 1.8954942670339809) < 1e-7
+
+
+
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("method", ["Radau", "BDF"])
 @pytest.mark.parametrize("name,t_span", [("rational", (5.0, 9.0)), ("rational", (5.0, 1.0)), ("linear", (0.0, 2.0)),
@@ -126,6 +138,29 @@ def test_events(case, method):
         assert np.allclose(sol.t_events[k], t_ev[k], rtol=1e-7, atol=1e-7)
         assert np.allclose(np.ravel(sol.y_events[k]), y_ev[k], rtol=1e-7, atol=1e-7)
         assert np.allclose(np.ravel(sol.yp_events[k]), yp_ev[k], rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["BDF", "Radau"])
+def test_functor_events(method):
+    """tests/test_events.py restated with event functions that are NOT thresholds on one component:
+    the device functor's own g(t, y, y'; p) (FunctorEvent): y - y' = 0 at t = pi/4, 5pi/4 and, terminal,
+    y - t/2 = 0 (sin t = t / 2 at t = 1.895494267...)."""
+    from scipy_dae_b200 import FunctorEvent
+    from scipy_dae_b200.integrate import solve_dae
+    pr = get_problem("cosine")
+    y0, yp0 = pr.initial((1.0,))
+    sol = solve_dae("cosine", pr.t_span, y0, yp0, method=method, rtol=1e-12, atol=1e-12, events=[FunctorEvent(0)])
+    assert np.allclose(sol.t_events[0], [np.pi / 4, 5 * np.pi / 4], rtol=1e-7, atol=1e-7)
+    assert np.allclose(np.ravel(sol.y_events[0]), np.sin(sol.t_events[0]), rtol=1e-7, atol=1e-7)
+    assert np.allclose(np.ravel(sol.y_events[0]), np.ravel(sol.yp_events[0]), rtol=1e-7, atol=1e-7)
+    sol = solve_dae("cosine", pr.t_span, y0, yp0, method=method, rtol=1e-12, atol=1e-12,
+                    events=[FunctorEvent(0), FunctorEvent(1, direction=-1, terminal=True)])
+    t_star = 1.8954942670339809
+    assert sol.status == 1 and np.allclose(sol.t_events[1], [t_star], rtol=1e-7, atol=1e-7) and sol.t[-1] == sol.t_events[1][0]
+    assert np.allclose(sol.t_events[0], [np.pi / 4], rtol=1e-7, atol=1e-7)          # 5 pi / 4 lies beyond the stop
+    with pytest.raises(ValueError, match="event functions"):
+        solve_dae("cosine", pr.t_span, y0, yp0, method=method, rtol=1e-6, atol=1e-6, events=[FunctorEvent(5)])
 
 
 @pytest.mark.gpu
