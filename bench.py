@@ -217,8 +217,8 @@ def reference_pool_run(sample: int, budget_s: float, steps: int = 1, warmup: int
 
 def cpu_baseline(sample: int, nthreads: int):
     """The reference on the host cores of this box: the first 16 384 instances of the rank-0
-    ensemble, bounded to about 20 s of wall time."""
-    d = reference_pool_run(sample if sample > 0 else 16384, 20.0)
+    ensemble, bounded to about 30 s of wall time."""
+    d = reference_pool_run(sample if sample > 0 else 16384, 30.0)
     return {"value": d["value"], "unit": UNIT, "cores": d["cores"], "kind": "reference",
             "sample": d["sample"], "instances": d["instances"], "source": d["source"],
             "all_finished": d["all_finished"]}

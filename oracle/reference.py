@@ -264,7 +264,7 @@ def solve_ensemble(problem, params, y0, yp0, t_span, method="Radau", rtol=1e-3, 
 
 # ---- the CPU baseline of BASELINE.md §3 --------------------------------------------------------
 def bench(problem="robertson", method="Radau", rtol=1e-6, atol=1e-6, t_span=(0.0, 1e7), sigma=0.1, seed=0,
-          sample=16384, budget_s=20.0, steps=1, warmup=0, processes=None, options=None):
+          sample=16384, budget_s=30.0, steps=1, warmup=0, processes=None, options=None):
     """solve_dae over the first `sample` instances of the seeded ensemble (time-bounded: the sample
     shrinks to what `budget_s` seconds per step admit at the rate a probe measures), on a pool of
     `processes` (default os.cpu_count()) single-threaded workers; pool start-up is not timed."""
@@ -278,7 +278,7 @@ def bench(problem="robertson", method="Radau", rtol=1e-6, atol=1e-6, t_span=(0.0
     job = dict(problem=problem, params=params, y0=y0, yp0=yp0, t_span=tuple(t_span), method=method, rtol=rtol,
                atol=atol, t_eval=None, options=dict(options or {}))
     with _make_pool(job, P) as pool:
-        probe = min(sample, 4 * P)
+        probe = min(sample, 16 * P)
         pool.map(_pool_task_plain, range(min(sample, P)), chunksize=1)      # workers up, imports done
         t = time.perf_counter()
         pool.map(_pool_task_plain, range(probe), chunksize=1)
@@ -314,7 +314,7 @@ def main(argv=None):
     ap.add_argument("--sigma", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--sample", type=int, default=16384)
-    ap.add_argument("--budget-s", type=float, default=20.0)
+    ap.add_argument("--budget-s", type=float, default=30.0)
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--processes", type=int, default=0)

@@ -281,7 +281,17 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
             raise ValueError("`y0` and `yp0` must be of same shape.")
     rtol, atol_v = _validate_tol(rtol, atol, n)
 
-    with torch.cuda.device(device):
+    # every piece of device work of this call (copies, relayouts, output fills, the launch, the
+    # status post-processing) is queued on ONE stream: `stream` if given, after it has waited for
+    # the caller's current stream, else the current stream
+    import contextlib
+    if stream is not None:
+        if stream != torch.cuda.current_stream(device):
+            stream.wait_stream(torch.cuda.current_stream(device))
+        stream_ctx = torch.cuda.stream(stream)
+    else:
+        stream_ctx = contextlib.nullcontext()
+    with torch.cuda.device(device), stream_ctx:
         y0_d = _as_device_soa(y0, N, n, "y0", device, check_finite)
         yp0_d = _as_device_soa(yp0, N, n, "yp0", device, check_finite)
         p_d = _as_device_soa(params, N, npar, "params", device, False) if npar > 0 else None
@@ -369,8 +379,7 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
                 raise ValueError("`first_step` must be positive.")
             if first_step > abs(t_bound - t0):
                 raise ValueError("`first_step` exceeds bounds.")
-        cu_stream = ctypes.c_void_p(stream.cuda_stream if stream is not None
-                                    else torch.cuda.current_stream(device).cuda_stream)
+        cu_stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         atol_p = atol_v.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         p_ptr = p_d.data_ptr() if p_d is not None else None
         if method == "Radau":
@@ -379,6 +388,10 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
                 raise ValueError("`stages` must be odd.")
             db = opts.pop("controller_deadband", (1.0, 1.2))
             nmi = opts.pop("newton_max_iter", None)
+            if nmi is not None and not 1 <= int(nmi) <= 32:
+                # the reference asserts newton_max_iter >= 1 (radau.py:438-441); the device evaluates
+                # rate ** (newton_max_iter - k) with a 5-bit square-and-multiply, hence the upper bound
+                raise ValueError("`newton_max_iter` must be in 1 .. 32 on the device path.")
             ro = _lib.RadauOpts(
                 rtol=rtol, max_step=max_step, first_step=first_step or 0.0,
                 continuous_error_weight=float(opts.pop("continuous_error_weight", 0.0)),
@@ -406,9 +419,8 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
                                      t0, t_bound, atol_p, ctypes.byref(bo), ctypes.byref(out),
                                      cu_stream)
         _lib.check(rc)
-
-    if ev_struct is not None:      # device code 2 -> solve_dae's status 1 ("A termination event occurred.")
-        status = torch.where(status == _lib.ST_EVENT, torch.ones_like(status), status)
+        if ev_struct is not None:  # device code 2 -> solve_dae's status 1 ("A termination event occurred.")
+            status = torch.where(status == _lib.ST_EVENT, torch.ones_like(status), status)
     res = BatchedDaeResult(
         t_final=t_final, y_final=y_final.t(), yp_final=yp_final.t(), status=status,
         nfev=counters[0], njev=counters[1], nlu=counters[2], nsolve=counters[3],

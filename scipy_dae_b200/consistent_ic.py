@@ -79,7 +79,14 @@ def consistent_initial_conditions_batched(problem, t0, y0, yp0, params=None, jac
         if len(shp) == 2:
             N = int(shp[0])
             break
-    with torch.cuda.device(device):
+    import contextlib
+    if stream is not None:          # all device work of this call on ONE stream (see solve_dae_batched)
+        if stream != torch.cuda.current_stream(device):
+            stream.wait_stream(torch.cuda.current_stream(device))
+        stream_ctx = torch.cuda.stream(stream)
+    else:
+        stream_ctx = contextlib.nullcontext()
+    with torch.cuda.device(device), stream_ctx:
         y_d = _as_device_soa(y0, N, n, "y0", device, False).clone()
         yp_d = _as_device_soa(yp0, N, n, "yp0", device, False).clone()
         p_d = _as_device_soa(params, N, npar, "params", device, False) if npar > 0 else None
@@ -88,8 +95,7 @@ def consistent_initial_conditions_batched(problem, t0, y0, yp0, params=None, jac
         n_iter = torch.empty((N,), dtype=torch.int32, device=device)
         opts = _lib.CicOpts(rtol=float(rtol), safety=float(safety), newton_maxiter=int(newton_maxiter),
                             chord_iter=int(chord_iter), analytic_jac=1 if jac in (True, "analytic") else 0)
-        cu_stream = ctypes.c_void_p(stream.cuda_stream if stream is not None
-                                    else torch.cuda.current_stream(device).cuda_stream)
+        cu_stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         i32p = ctypes.POINTER(ctypes.c_int32)
         rc = L.b200dae_consistent_ic(pid, N, N, float(t0), y_d.data_ptr(), yp_d.data_ptr(),
                                      p_d.data_ptr() if p_d is not None else None,

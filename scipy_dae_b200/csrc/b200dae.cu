@@ -191,6 +191,8 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
     if (!(opts->deadband_lo > 0 && opts->deadband_lo <= opts->deadband_hi))
         return fail(B200DAE_EINVAL, "need 0 < controller_deadband[0] <= controller_deadband[1]%s", "");
     if (opts->newton_iter_embedded < 0) return fail(B200DAE_EINVAL, "need newton_iter_embedded >= 0%s", "");
+    // the kernels evaluate rate ** (newton_max_iter - k) (radau.py:186) with a 5-bit square-and-multiply
+    if (opts->newton_max_iter > 32) return fail(B200DAE_EINVAL, "need newton_max_iter <= 32%s (got %lld)", "", (long long)opts->newton_max_iter);
     // The thread-per-system kernel relies on the normalisation of the reference's eigen-transformation
     // (radau.py:72-84): eigenvectors scaled to a unit last row, so T[s-1] = (1, 0, 1, 0, ..., 1), and
     // on a dense first row of TI (a non-finite stage residual then shows in TI[0] @ F).

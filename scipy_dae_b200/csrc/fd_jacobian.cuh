@@ -154,7 +154,9 @@ __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y,
         for (int c = 0; c < NC; ++c) {
             const int col = C0 + c, i = col % N;
             const double xi = (col >= N) ? yp[i] : y[i];
-            while (h[c] == 0.0) {
+            // bounded: with atol = 0 and x = 0 the scale is 0 and scipy's `while h == 0` never ends; here
+            // h stays 0 after 400 trips (factor has overflowed), J becomes non-finite -> status -2
+            for (int trip = 0; h[c] == 0.0 && trip < 400; ++trip) {
                 fac[c] *= 10.0;
                 xp[c] = fma(fac[c], ysc[c], xi);
                 h[c] = xp[c] - xi;
@@ -248,7 +250,7 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
             double fac = factor[i];
             double xp = fma(fac, y_scale, xi);
             double h = xp - xi;
-            while (h == 0.0) {
+            for (int trip = 0; h == 0.0 && trip < 400; ++trip) {   // bounded, see fd_batch
                 fac *= 10.0;
                 xp = fma(fac, y_scale, xi);
                 h = xp - xi;

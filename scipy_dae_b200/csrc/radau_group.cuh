@@ -100,7 +100,7 @@ __device__ __forceinline__ void fd_jacobian_group(const Grp& g, double t, double
         double fac = wrt_yp ? fac_yp : fac_y;
         double xp = fma(fac, y_scale, xi);
         double h = xp - xi;
-        while (h == 0.0) {
+        for (int trip = 0; h == 0.0 && trip < 400; ++trip) {   // bounded, see fd_jacobian.cuh: fd_batch
             fac *= 10.0;
             xp = fma(fac, y_scale, xi);
             h = xp - xi;

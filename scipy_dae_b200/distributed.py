@@ -78,7 +78,13 @@ def solve_dae_sharded(problem, t_span, y0, yp0, params, method="Radau", t_eval=N
         return local
     if local is None:   # empty shard: fabricate zero-length tensors with the right trailing shapes
         n = y0.shape[1]
-        dev = torch.device(device) if device is not None else torch.device("cpu")
+        # on the device the other ranks' results live on: a CPU tensor in an NCCL gather errors or hangs
+        if device is not None:
+            dev = torch.device(device)
+        elif torch.cuda.is_available() and (not dist.is_initialized() or dist.get_backend(group) == "nccl"):
+            dev = torch.device("cuda", torch.cuda.current_device())
+        else:
+            dev = torch.device("cpu")
         local = {k: torch.zeros((0, n) if k in ("y_final", "yp_final") else (0,),
                                 dtype=torch.float64 if k in ("t_final", "y_final", "yp_final") else torch.int32,
                                 device=dev) for k in GATHER_FIELDS}

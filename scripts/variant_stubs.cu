@@ -21,5 +21,7 @@ B200DAE_STUB(linear)
 B200DAE_STUB(cosine)
 B200DAE_STUB(weissinger)
 B200DAE_STUB(brenan)
+B200DAE_STUB(transamp1)
+B200DAE_STUB(blowup)
 #endif
 }  // namespace b200dae

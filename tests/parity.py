@@ -130,12 +130,23 @@ def compare(res, ref, meta, case, atol_vec, have_eval, eval_axes_ref="nm", eval_
         if eval_axes_res != eval_axes_ref:
             ye = np.swapaxes(ye, 1, 2)               # -> the reference's [N, n, m]
         band_atol = np.asarray(atol_vec, dtype=float)[None, :, None]
-        sel = ok | failed
+        # a failed instance takes part with the t_eval points it reached only where the reference fails
+        # DETERMINISTICALLY (all twins give up at the same time, e.g. a finite-time blow-up); where the
+        # time of failure is chaotic in the reference itself (the n = 5 circuit: twins end between
+        # t = 8e-4 and 0.1), the trajectory towards the failure is not a reproducible quantity and only
+        # status, t_final (twin band) and the n_eval_valid structure below are compared
+        det = failed.copy()
+        if failed.any() and _twin(ref, "t_final") is not None:
+            span = abs(meta["t_span"][1] - meta["t_span"][0])
+            spread = np.abs(np.asarray(ref["twin_t_final"], dtype=float) - np.asarray(ref["t_final"], dtype=float)[None]).max(axis=0)
+            det &= (spread <= 1e-6 * span) & (np.asarray(tw_st) == st_ref[None]).all(axis=0)
+        sel = ok | det
+        failed_cmp = det
         if sel.any():
             # a failing instance is compared on the t_eval points BOTH reached
             nv = np.minimum(np.asarray(res["n_eval_valid"]), np.asarray(ref["n_eval_valid"]))
             yr_c = yr.copy()
-            for i in np.nonzero(failed)[0]:
+            for i in np.nonzero(failed_cmp)[0]:
                 yr_c[i, :, nv[i]:] = np.nan
             r = instance_ratios(ye[sel], yr_c[sel], rtol, band_atol)
             tw = _twin(ref, "y_eval")
@@ -145,7 +156,7 @@ def compare(res, ref, meta, case, atol_vec, have_eval, eval_axes_ref="nm", eval_
                 ds = []
                 for k in range(tw.shape[0]):
                     yk = yr_c.copy()
-                    for i in np.nonzero(failed)[0]:
+                    for i in np.nonzero(failed_cmp)[0]:
                         yk[i, :, min(nv[i], tw_nv[k, i]):] = np.nan
                     dk = instance_ratios(np.asarray(tw[k])[sel], yk[sel], rtol, band_atol)
                     ds.append(np.where((np.asarray(tw_st)[k] == st_ref)[sel], dk, 0.0))

@@ -122,4 +122,7 @@ def test_adapter_drives_the_cuda_path(method):
     r5 = solve_dae(p5.residual, p5.t_span, y5, yp5, method=method, rtol=1e-6, atol=1e-6, args=p5.default_params, t_eval=te5)
     s5 = solve_dae(p5, p5.t_span, y5, yp5, method=cls, rtol=1e-6, atol=1e-6, params=p5.default_params, t_eval=te5)
     assert r5.status == -1 and s5.status == -1 and s5.message == r5.message
-    assert abs(len(s5.t) - len(r5.t)) <= 1
+    # the driver breaks before recording the failed step (dae.py:451-453): only the t_eval points up to
+    # the last accepted step come back (WHERE this circuit gives up is chaotic in the reference itself,
+    # tests/golden/transamp1_*_fail: its twins end between t = 8e-4 and 0.1)
+    assert 0 < len(s5.t) < len(te5) and np.array_equal(s5.t, te5[:len(s5.t)]) and s5.y.shape == (5, len(s5.t))

@@ -47,8 +47,9 @@ def test_cuda_matches_reference_golden(case):
     # work counters are not part of the north_star contract (only accepted / rejected steps are);
     # they are chaotic at tight tolerances (the oracle itself differs from the golden by 9 % in nlu
     # on robertson_radau3_tight), so they only get a coarse sanity band
+    fin = (g["status"] == 0) & (res["status"] == 0)         # (where an instance gives up is chaotic, parity.py)
     for k in ("nfev", "njev", "nlu"):
-        assert counts_within_band(res[k], g[k], band=0.25, slack=4).all(), (k, res[k], g[k])
+        assert counts_within_band(res[k][fin], g[k][fin], band=0.25, slack=4).all(), (k, res[k], g[k])
 
 
 def test_headline_counters_match_reference():
