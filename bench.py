@@ -55,8 +55,13 @@ def parse_args():
     ap.add_argument("--jac", default="fd", choices=["fd", "analytic"],
                     help="fd = finite-difference Jacobian (the headline, jac=None in the reference); "
                          "analytic = the functor's analytic Jacobians (a `jac` callable in the reference)")
-    ap.add_argument("--t-eval-points", type=int, default=64,
-                    help="also time the ensemble with dense output at this many t_eval points (0 = skip)")
+    ap.add_argument("--t-eval-points", type=int, nargs="*", default=[64, 1000],
+                    help="also time the ensemble with dense output at these many t_eval points (none = skip); "
+                         "1000 log-spaced points is the reference README's own configuration (README.md:54)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3-5 (run at --gpus 1 only)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling measurement")
+    ap.add_argument("--strong-total", type=int, default=1 << 20,
+                    help="instances of the strong-scaling job (BASELINE configs[1]: 1M instances sharded over the GPUs)")
     ap.add_argument("--e2e-no-graph", action="store_true",
                     help="queue the host pipeline eagerly instead of replaying its CUDA graph")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="pipeline chunks of the host-facing call")
@@ -93,6 +98,86 @@ def algorithmic_flops(cnt: dict, n: int, s: int, c_f: int, fd: int = 1) -> float
     fl += it * (3 * 2 * s * s * n + 8 * s * n)                             # TI/T/A transforms, updates, norm
     fl += cnt["njev"] * 2 * n * 2 * n * fd                                 # FD quotients
     return float(fl)
+
+
+def algorithmic_flops_bdf(cnt: dict, n: int, c_f: int, fd: int = 1) -> float:
+    """BDF / NDF twin of algorithmic_flops: residuals, LUs of Jy + c Jyp, Newton
+    solves and updates, predictor / difference-array work per attempt and change_D rescalings
+    (bdf.py:14-29: two q x q by q x n products, q = order + 1; the number of rescalings is not a
+    counter, it is taken as one per LU refresh plus one per rejection, at the mean order 3)."""
+    attempts = cnt["n_accepted"] + cnt.get("n_err_rejected", 0) + cnt.get("n_newton_fail", 0)
+    n_f = cnt["nfev"] + cnt["njev"] * (2 * n + 1) * fd
+    fl = n_f * c_f
+    fl += cnt["nlu"] * ((2.0 / 3.0) * n ** 3 + 2 * n * n)            # LU + assembly
+    fl += cnt["nsolve"] * 2 * n * n                                   # triangular solves
+    fl += cnt["n_newton_iter"] * 7 * n                                # yp = c d + psi, y / d updates, norm
+    fl += attempts * 13 * n                                           # predictor, psi, error scale
+    fl += cnt["n_accepted"] * 8 * n                                   # difference update, order-selection norms
+    fl += (cnt["nlu"] + cnt.get("n_err_rejected", 0)) * 4 * 16 * n    # change_D at q = 4
+    fl += cnt["njev"] * 2 * n * 2 * n * fd                            # FD quotients
+    return float(fl)
+
+
+# BASELINE.json configs 3-5 (configs[2..4]): (label, problem, method, instances, sigma, rtol, atol, options, oracle sample)
+CONFIGS = [
+    ("C3 Akzo Nobel, BDF/NDF, rtol=atol=1e-8", "akzo_nobel", "BDF", 1 << 17, 0.05, 1e-8, 1e-8, {}, 512),
+    ("C3 Akzo Nobel, Radau s=3, rtol=atol=1e-8", "akzo_nobel", "Radau", 1 << 17, 0.05, 1e-8, 1e-8, {}, 512),
+    ("C4 Andrews squeezer (n=26), Radau s=5, rtol=atol=1e-4", "andrews", "Radau", 1 << 13, 0.05, 1e-4, 1e-4, {"stages": 5}, 64),
+    ("C5 transistor amplifier (n=8), Radau s=3, rtol=1e-10", "transamp", "Radau", 1 << 14, 0.02, 1e-10, 1e-6, {}, 32),
+    ("C5 transistor amplifier (n=8), BDF, rtol=1e-10", "transamp", "BDF", 1 << 14, 0.02, 1e-10, 1e-6, {}, 32),
+]
+
+
+def run_configs(dev, fp64_peak_tflops, nthreads):
+    """Configs 3-5 through the product API (device-resident inputs, CUDA events around the call that
+    launches ONE kernel), each with the roofline fraction of the same algorithmic flop model and a
+    parity sample against the CPU oracle on the first instances (north_star band, step counts)."""
+    import torch
+    from oracle import oracle as O
+    from scipy_dae_b200 import solve_dae_batched, perturbed_params, initial_conditions, get_problem
+    rows = []
+    for label, problem, method, N, sigma, rtol, atol, opts, n_par in CONFIGS:
+        pr = get_problem(problem)
+        params = perturbed_params(problem, N, sigma, seed=0)
+        y0, yp0 = initial_conditions(problem, params)
+        pd, yd, ypd = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (params, y0, yp0))
+        times, r = [], None
+        for it in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            r = solve_dae_batched(problem, pr.t_span, yd, ypd, pd, method=method, rtol=rtol, atol=atol,
+                                  check_finite=False, device=dev, **opts)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            times.append(e0.elapsed_time(e1))
+        ms = float(min(times[1:]))
+        ok = r.status == 0
+        cnt = {k: float(getattr(r, k)[ok].double().sum()) for k in
+               ("nfev", "njev", "nlu", "nsolve", "n_accepted", "n_err_rejected", "n_newton_fail", "n_newton_iter")}
+        s = int(opts.get("stages", 3))
+        flops = (algorithmic_flops(cnt, pr.n, s, pr.flops) if method == "Radau"
+                 else algorithmic_flops_bdf(cnt, pr.n, pr.flops))
+        ach = flops / (ms * 1e-3) / 1e12
+        ref = O.solve_ensemble(problem, params[:n_par], y0[:n_par], yp0[:n_par], pr.t_span, method=method, rtol=rtol,
+                               atol=atol, nthreads=nthreads, **opts)
+        rn = r.numpy()
+        both = (ref["status"] == 0) & (rn.status[:n_par] == 0)
+        ratio = (np.abs(rn.y_final[:n_par] - ref["y_final"]) / np.maximum(10 * rtol * np.abs(ref["y_final"]), atol)).max(axis=1)[both]
+        dacc = np.abs(rn.n_accepted[:n_par] - ref["n_accepted"])[both] / ref["n_accepted"][both]
+        rows.append({"config": label, "problem": problem, "method": method, "options": opts, "instances": N,
+                     "kernel": ("radau_group" if method == "Radau" else "bdf_group") + f"_kernel<{problem}>",
+                     "ms": ms, "value": N / (ms * 1e-3), "unit": UNIT, "n_unfinished": int((~ok).sum()),
+                     "work_per_solve": {k: v / max(int(ok.sum()), 1) for k, v in cnt.items()},
+                     "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                                  "frac": ach / fp64_peak_tflops, "flops_per_solve": flops / max(int(ok.sum()), 1)},
+                     "parity_vs_oracle": {"sample": int(n_par), "status_equal": bool((rn.status[:n_par] == ref["status"]).all()),
+                                          "state_ratio_median": float(np.median(ratio)), "state_ratio_max": float(ratio.max()),
+                                          "frac_in_band": float((ratio <= 1).mean()),
+                                          "accepted_rel_diff_max": float(dacc.max()),
+                                          "frac_accepted_within_5pct": float((dacc <= 0.05).mean())}})
+        del pd, yd, ypd, r
+    return rows
 
 
 def ncu_traffic(n_per_gpu: int):
@@ -444,40 +529,46 @@ def main():
     fp64_peak_tflops = 148 * 8 * 256 * iters * 16 / (a.elapsed_time(b) * 1e-3) / 1e12
 
     # ---- secondary: the same ensemble WITH t_eval output (the HBM-heavier mode) --------
-    te_mode = None
-    if args.t_eval_points > 0 and rank == 0:
-        m = int(args.t_eval_points)
-        te = torch.from_numpy(np.logspace(-6, 7, m)).to(dev)
-        y_eval = torch.empty((m, n, Nper), **f64)
-        yp_eval = torch.empty((m, n, Nper), **f64)
-        nev = torch.empty((Nper,), dtype=torch.int32, device=dev)
-        out2 = _lib.Outputs()
-        out2.y_final, out2.yp_final, out2.t_final = y_final.data_ptr(), yp_final.data_ptr(), t_final.data_ptr()
-        out2.status, out2.counters = status.data_ptr(), counters.data_ptr()
-        out2.t_eval, out2.m = te.data_ptr(), m
-        out2.y_eval, out2.yp_eval, out2.n_eval_valid = y_eval.data_ptr(), yp_eval.data_ptr(), nev.data_ptr()
+    te_modes = []
+    if rank == 0:
+        for m in [int(x) for x in (args.t_eval_points or []) if int(x) > 0]:
+            te = torch.from_numpy(np.logspace(-6, 7, m)).to(dev)
+            try:
+                y_eval = torch.empty((m, n, Nper), **f64)
+                yp_eval = torch.empty((m, n, Nper), **f64)
+            except RuntimeError as exc:          # not enough free HBM for 2 x 8 m n N bytes
+                te_modes.append({"t_eval_points": m, "skipped": f"{type(exc).__name__}"})
+                continue
+            nev = torch.empty((Nper,), dtype=torch.int32, device=dev)
+            out2 = _lib.Outputs()
+            out2.y_final, out2.yp_final, out2.t_final = y_final.data_ptr(), yp_final.data_ptr(), t_final.data_ptr()
+            out2.status, out2.counters = status.data_ptr(), counters.data_ptr()
+            out2.t_eval, out2.m = te.data_ptr(), m
+            out2.y_eval, out2.yp_eval, out2.n_eval_valid = y_eval.data_ptr(), yp_eval.data_ptr(), nev.data_ptr()
 
-        def launch_te():
-            _lib.check(L.b200dae_solve_radau(pid, Nper, Nper, d_y0.data_ptr(), d_yp0.data_ptr(), d_p.data_ptr(),
-                                             WORKLOAD["t_span"][0], WORKLOAD["t_span"][1], atol, ctypes.byref(ro),
-                                             ctypes.byref(tb), ctypes.byref(out2), ctypes.c_void_p(stream.cuda_stream)))
-        launch_te()
-        torch.cuda.synchronize(dev)
-        ts = []
-        for _ in range(2):
-            flush.fill_(1)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream); launch_te(); b.record(stream)
+            def launch_te():
+                _lib.check(L.b200dae_solve_radau(pid, Nper, Nper, d_y0.data_ptr(), d_yp0.data_ptr(), d_p.data_ptr(),
+                                                 WORKLOAD["t_span"][0], WORKLOAD["t_span"][1], atol, ctypes.byref(ro),
+                                                 ctypes.byref(tb), ctypes.byref(out2), ctypes.c_void_p(stream.cuda_stream)))
+            launch_te()
             torch.cuda.synchronize(dev)
-            ts.append(a.elapsed_time(b))
-        assert bool((nev == m).all())
-        ms = float(np.mean(ts))
-        nbytes = Nper * (compulsory_bytes(n, npar) + 16 * n * m)
-        te_mode = {"t_eval_points": m, "ms_per_launch": ms, "solves_per_s": Nper / (ms * 1e-3),
-                   "hbm_bytes_per_launch": nbytes, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
-                   "note": "same ensemble with dense output at m log-spaced points written to HBM "
-                           "(y and yp, [m][n][N] SoA); lean kernel twin with t_eval output"}
-        del y_eval, yp_eval
+            ts = []
+            for _ in range(2):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream); launch_te(); b.record(stream)
+                torch.cuda.synchronize(dev)
+                ts.append(a.elapsed_time(b))
+            assert bool((nev == m).all())
+            ms = float(np.mean(ts))
+            nbytes = Nper * (compulsory_bytes(n, npar) + 16 * n * m)
+            te_modes.append({"t_eval_points": m, "ms_per_launch": ms, "solves_per_s": Nper / (ms * 1e-3),
+                             "hbm_bytes_per_launch": nbytes, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
+                             "note": "same ensemble with dense output at m log-spaced points in [1e-6, 1e7] written to "
+                                     "HBM (y and yp, [m][n][N] SoA); lean kernel twin with t_eval output"})
+            del y_eval, yp_eval, nev
+            torch.cuda.empty_cache()
+    te_mode = te_modes[0] if te_modes else None
 
     # ---- max over ranks ----------------------------------------------------------------------------------
     t_all = torch.tensor([total_ms, e2e_total_ms], dtype=torch.float64, device=dev)
@@ -485,7 +576,58 @@ def main():
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     total_ms, e2e_total_ms = float(t_all[0]), float(t_all[1])
 
-    # one gather of the results (rank 0 receives every rank's final states), timed separately
+    # ---- strong scaling: BASELINE configs[1] literally -- ONE ensemble of --strong-total instances (2^20)
+    # sharded over the N GPUs through the product API (distributed.solve_dae_sharded), host inputs to
+    # host results, with the single gather INSIDE the timed region: every rank's host pipeline DMA-
+    # writes its shard into the node-wide shared, page-locked result arrays (distributed.SharedHostResult;
+    # no collective, no NCCL channel set-up), one barrier, done.  Max over ranks.
+    strong = None
+    if not args.no_strong:
+        from scipy_dae_b200.distributed import SharedHostResult, solve_dae_sharded, shard_bounds
+        Nt = int(args.strong_total)
+        lo, hi, per = shard_bounds(Nt, world, rank)
+        # the seed-0 ensemble (rank 0's weak-scaling ensemble when Nt == Nper) in pinned host memory;
+        # solve_dae_sharded slices a rank's block out of it (a rank never touches the other blocks)
+        p_all = params if (rank == 0 and Nt == Nper) else perturbed_params("robertson", Nt, WORKLOAD["sigma"], seed=0)
+        y_all, yp_all = initial_conditions("robertson", p_all)
+        hs_p, hs_y0, hs_yp0 = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (p_all, y_all, yp_all))
+        shared = SharedHostResult(f"b200dae_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}", Nt, n)
+        chunks = max(2, args.e2e_chunks // max(1, min(world, 4)))
+
+        def strong_step():
+            return solve_dae_sharded("robertson", WORKLOAD["t_span"], hs_y0, hs_yp0, hs_p, method="Radau",
+                                     rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], gather="host", host_result=shared,
+                                     device=dev, chunks=chunks, n_streams=args.e2e_streams, use_graph=True,
+                                     jac="analytic" if args.jac == "analytic" else None)
+        for _ in range(3):
+            strong_step()
+        barrier()
+        s_ms = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            barrier()
+            t0 = time.perf_counter()
+            res_s = strong_step()                      # ends with the barrier that closes the gather
+            s_ms.append(1e3 * (time.perf_counter() - t0))
+        t_s = torch.tensor(s_ms, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        s_ms = [float(x) for x in t_s]
+        if rank == 0:
+            ok_all = bool((res_s["status"] == 0).all())
+            same = bool(torch.equal(res_s["y_final"], host_out.y_final)) if Nt == Nper else None
+            strong = {"scaling": "strong", "instances_total": Nt, "n_gpus": world, "instances_per_gpu": per,
+                      "value": Nt * len(s_ms) / (sum(s_ms) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(s_ms)),
+                      "ms_each": [round(x, 3) for x in s_ms], "all_finished": ok_all,
+                      "matches_single_gpu_results": same,
+                      "api": f"distributed.solve_dae_sharded(gather='host', chunks={chunks}, use_graph=True): host inputs -> "
+                             "per-rank host pipeline -> shards DMA-written into shared pinned host arrays -> barrier",
+                      "h2d_bytes_per_step": 8 * Nt * (npar + 2 * n), "d2h_bytes_per_step": int(shared.nbytes),
+                      "gather": "inside the timed region (no collective)"}
+        shared.close()
+        del hs_p, hs_y0, hs_yp0
+
+    # the collective gather for comparison (rank 0 receives every rank's final states), timed apart
     gather_ms = gather_first_ms = None
     if world > 1:
         parts = [torch.empty_like(y_final) for _ in range(world)] if rank == 0 else None
@@ -513,8 +655,9 @@ def main():
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        if te_mode is not None:
-            te_mode["hbm_frac"] = te_mode["hbm_gbs"] / hbm_peak
+        for tm in te_modes:
+            if "hbm_gbs" in tm:
+                tm["hbm_frac"] = tm["hbm_gbs"] / hbm_peak
         ach_tflops = flops_per_launch / kernel_s / 1e12
         ach_gbs = bytes_per_launch / kernel_s / 1e9
         line = {
@@ -546,9 +689,12 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             },
             "work_per_solve": {k: float(v) / Nper for k, v in cnt.items()},
-            "t_eval_mode": te_mode,
+            "t_eval_mode": te_mode, "t_eval_modes": te_modes,
+            "strong": strong,
             "gather_ms": gather_ms, "gather_first_ms": gather_first_ms,
         }
+        if world == 1 and not args.no_configs:
+            line["configs"] = run_configs(dev, fp64_peak_tflops, os.cpu_count() or 1)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample, os.cpu_count() or 1)
             line["cpu_baseline_port"] = cpu_baseline_port(os.cpu_count() or 1)

@@ -47,6 +47,7 @@ class Problem:
     solution: Callable = None        # optional exact solution(t, *params) -> (y[n, ...], yp[n, ...])
     t0_default: float = None         # start of t_span (for problems whose ICs depend on it)
     events: tuple = ()               # NumPy twins g(t, y, yp, *params) of the functor's event functions
+    flops: int = 0                   # flops of one residual as written (the functor's kFlops; roofline model)
 
     def event_callable(self, index, spec=None):
         """Event function `index` as the callable the reference's `events=` takes (dae.py:226-247),
@@ -506,28 +507,28 @@ def _register(p: Problem):
 
 
 ROBERTSON = _register(Problem(
-    name="robertson", n=3, n_params=3, residual=robertson_residual,
+    name="robertson", flops=15, n=3, n_params=3, residual=robertson_residual,
     default_params=(0.04, 1e4, 3e7), initial=robertson_initial, t_span=(0.0, 1e7),
     initial_batch=robertson_initial_batch, jacobian=robertson_jacobian,
     param_names=("k1", "k2", "k3"), events=ROBERTSON_EVENTS,
     doc="Robertson chemical kinetics as an index-1 DAE"))
 
 AKZO_NOBEL = _register(Problem(
-    name="akzo_nobel", n=6, n_params=7, residual=akzo_residual,
+    name="akzo_nobel", flops=52, n=6, n_params=7, residual=akzo_residual,
     default_params=(18.7, 0.58, 0.09, 0.42, 34.4, 3.3, 115.83),
     initial=akzo_initial, t_span=(0.0, 180.0), jacobian=akzo_jacobian,
     param_names=("k1", "k2", "k3", "k4", "kbig", "kla", "ks"), events=AKZO_EVENTS,
     doc="Akzo Nobel chemical reaction, index 1"))
 
 TRANSAMP = _register(Problem(
-    name="transamp", n=8, n_params=3, residual=transamp_residual,
+    name="transamp", flops=75, n=8, n_params=3, residual=transamp_residual,
     default_params=(6.0, 1000.0, 1e-6), initial=transamp_initial, t_span=(0.0, 0.2),
     jacobian=transamp_jacobian,
     param_names=("Ub", "R0", "beta"),
     doc="Two-transistor amplifier (IVP test set 'transamp'), index 1"))
 
 ANDREWS = _register(Problem(
-    name="andrews", n=26, n_params=2, residual=andrews_residual,
+    name="andrews", flops=520, n=26, n_params=2, residual=andrews_residual,
     default_params=(0.033, 4530.0), initial=andrews_initial, t_span=(0.0, 0.03),
     param_names=("mom", "c0"),
     doc="Andrews' squeezer mechanism, stabilised index-1 formulation (n = 26)"))
@@ -564,13 +565,13 @@ BRENAN = _register(Problem(
 
 
 TRANSAMP1 = _register(Problem(
-    name="transamp1", n=5, n_params=3, residual=transamp1_residual,
+    name="transamp1", flops=40, n=5, n_params=3, residual=transamp1_residual,
     default_params=(6.0, 1000.0, 1e-6), initial=transamp1_initial, t_span=(0.0, 0.2),
     param_names=("Ub", "R0", "beta"),
     doc="One-transistor amplifier of the reference's examples/daes/stiff_transistor_amplifier.py (n = 5)"))
 
 BLOWUP = _register(Problem(
-    name="blowup", n=1, n_params=1, residual=blowup_residual, default_params=(1.0,),
+    name="blowup", flops=3, n=1, n_params=1, residual=blowup_residual, default_params=(1.0,),
     initial=_ic_from_solution(blowup_solution, 0.0), t_span=(0.0, 2.0),
     solution=blowup_solution, t0_default=0.0, param_names=("p",),
     doc="y' = p y^2, y(0) = 1: blows up at t = 1 / p (failure-path test problem)"))

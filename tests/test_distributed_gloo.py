@@ -31,6 +31,40 @@ def _oracle_solve(problem, t_span, y0, yp0, params, method="Radau", t_eval=None,
     return out
 
 
+def _oracle_solve_host(problem, t_span, y0, yp0, params, method="Radau", rtol=1e-3, atol=1e-6, out=None, **opts):
+    """Stand-in for solve_dae_batched_host: fills the rank's slice of the shared result arrays."""
+    opts.pop("device", None)
+    r = _oracle_solve(problem, t_span, np.asarray(y0), np.asarray(yp0), np.asarray(params), method=method, rtol=rtol, atol=atol, **opts)
+    out.t_final.copy_(r["t_final"]); out.y_final.copy_(r["y_final"]); out.yp_final.copy_(r["yp_final"])
+    out.status.copy_(r["status"])
+    for i, k in enumerate(("nfev", "njev", "nlu", "nsolve", "n_accepted", "n_err_rejected", "n_newton_fail", "n_newton_iter")):
+        out.counters[:, i] = r[k]
+
+
+def _worker_host(rank, world, port, N, q):
+    """gather="host": every rank writes its shard into the node-wide shared-memory result arrays."""
+    import sys
+    sys.path.insert(0, REPO)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scipy_dae_b200.distributed import solve_dae_sharded, SharedHostResult
+    from scipy_dae_b200.problems import perturbed_params, initial_conditions
+    params = perturbed_params("robertson", N, 0.1, seed=3)
+    y0, yp0 = initial_conditions("robertson", params)
+    shared = SharedHostResult(f"b200dae_test_{port}", N, 3)
+    for rep in range(2):                      # the shared arrays are reusable
+        res = solve_dae_sharded("robertson", (0.0, 1e3), torch.from_numpy(y0), torch.from_numpy(yp0), torch.from_numpy(params),
+                                method="Radau", rtol=1e-6, atol=1e-6, gather="host", host_result=shared,
+                                _solve_host=_oracle_solve_host)
+    if rank == 0:
+        q.put({k: v.numpy().copy() for k, v in res.items()})
+    else:
+        assert res is None
+    shared.close()
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, N, q):
     import sys
     sys.path.insert(0, REPO)
@@ -51,12 +85,12 @@ def _worker(rank, world, port, N, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("N", [10, 7, 1])
-def test_sharded_solve_matches_single_process(N):
+@pytest.mark.parametrize("N,worker", [(10, _worker), (7, _worker), (1, _worker), (9, _worker_host), (1, _worker_host)])
+def test_sharded_solve_matches_single_process(N, worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, N, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, port, N, q)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get(timeout=120)
