@@ -184,7 +184,7 @@ def ncu_traffic(n_per_gpu: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
     `ncu --set full` capture (profiles/), per launch, if it was taken at this batch size."""
     try:
-        d = json.load(open(os.path.join(REPO, "profiles", "r01_headline_traffic.json")))
+        d = json.load(open(os.path.join(REPO, "profiles", "r02_headline_traffic.json")))
     except (OSError, ValueError):
         return None
     if int(d.get("instances", -1)) != int(n_per_gpu):

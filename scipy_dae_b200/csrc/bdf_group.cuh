@@ -258,7 +258,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
                 double rate = 0.0;
                 if (has_old) rate = dy_norm * inv_norm_old;
                 const double cc = dy_norm * fast_rcp(1.0 - rate);
-                if (has_old && (rate >= 1.0 || powi(rate, kBdfNewtonMaxIter - k) * cc > L.newton_tol))
+                if (has_old && (rate >= 1.0 || powi<3>(rate, kBdfNewtonMaxIter - k) * cc > L.newton_tol))
                     break;                                        // BEFORE the update (bdf.py:52-53)
                 y_new += f;
                 d += f;

@@ -39,21 +39,27 @@ struct Regime {
 // ---------------------------------------------------------------------------------------------
 // real
 // ---------------------------------------------------------------------------------------------
-template <int N>
+// kFirstDone: the rows already stand in the order LAPACK's first interchange produces and piv[0]
+// is set (pivoted assembly, see first_pivot_order): the search and the swap of step 0 are skipped.
+template <int N, bool kFirstDone = false>
 __device__ __forceinline__ void lu_factor(double* __restrict__ a, int* __restrict__ piv) {
     constexpr bool REG = Regime<N>::kReg;
     constexpr int U = Regime<N>::kUnroll;
 #pragma unroll U
     for (int k = 0; k < N; ++k) {
         int p = k;
-        double best = fabs(a[k * N + k]);
+        if (!(kFirstDone && k == 0)) {
+            double best = fabs(a[k * N + k]);
 #pragma unroll U
-        for (int i = k + 1; i < N; ++i) {
-            const double v = fabs(a[i * N + k]);
-            if (v > best) { best = v; p = i; }
+            for (int i = k + 1; i < N; ++i) {
+                const double v = fabs(a[i * N + k]);
+                if (v > best) { best = v; p = i; }
+            }
+            piv[k] = p;
         }
-        piv[k] = p;
-        if (REG) {
+        if (kFirstDone && k == 0) {
+            // nothing to move
+        } else if (REG) {
 #pragma unroll U
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = (p == i);
@@ -89,36 +95,69 @@ template <int N>
 __device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const int* __restrict__ piv,
                                          double* __restrict__ b) {
     constexpr bool REG = Regime<N>::kReg;
-    constexpr int U = Regime<N>::kUnroll;
-#pragma unroll U
-    for (int k = 0; k < N; ++k) {
-        const int p = piv[k];
-        if (REG) {
-#pragma unroll U
+    if constexpr (REG) {
+        // (`#pragma unroll` without a count: with the count form ptxas once kept the inner loop of the
+        // complex twin rolled, which put its right-hand side into local memory)
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int p = piv[k];
+#pragma unroll
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = (p == i);
                 const double x = b[k], z = b[i];
                 b[k] = sw ? z : x;
                 b[i] = sw ? x : z;
             }
-        } else if (p != k) {
-            const double x = b[k]; b[k] = b[p]; b[p] = x;
+        }
+#pragma unroll
+        for (int i = 1; i < N; ++i) {
+            double acc = b[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) acc = fma(-lu[i * N + j], b[j], acc);
+            b[i] = acc;
+        }
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            double acc = b[i];
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) acc = fma(-lu[i * N + j], b[j], acc);
+            b[i] = acc * lu[i * N + i];
+        }
+    } else {
+        for (int k = 0; k < N; ++k) {
+            const int p = piv[k];
+            if (p != k) { const double x = b[k]; b[k] = b[p]; b[p] = x; }
+        }
+        for (int i = 1; i < N; ++i) {
+            double acc = b[i];
+            for (int j = 0; j < i; ++j) acc = fma(-lu[i * N + j], b[j], acc);
+            b[i] = acc;
+        }
+        for (int i = N - 1; i >= 0; --i) {
+            double acc = b[i];
+            for (int j = i + 1; j < N; ++j) acc = fma(-lu[i * N + j], b[j], acc);
+            b[i] = acc * lu[i * N + i];
         }
     }
-#pragma unroll U
-    for (int i = 1; i < N; ++i) {
-        double acc = b[i];
-#pragma unroll U
-        for (int j = 0; j < i; ++j) acc = fma(-lu[i * N + j], b[j], acc);
-        b[i] = acc;
-    }
-#pragma unroll U
-    for (int i = N - 1; i >= 0; --i) {
-        double acc = b[i];
-#pragma unroll U
-        for (int j = i + 1; j < N; ++j) acc = fma(-lu[i * N + j], b[j], acc);
-        b[i] = acc * lu[i * N + i];
-    }
+}
+
+// Pivoted assembly.  The first pivot of getrf depends only on column 0 of the matrix, which is known
+// before the matrix is assembled: p0 = first maximal |a[i][0]|.  LAPACK then interchanges rows 0 and
+// p0, i.e. the rows stand in the order  r[0] = p0,  r[p0] = 0,  r[i] = i otherwise.  Jy and Jyp live
+// in shared memory, where a run-time row index costs an address, not a select: the matrix is assembled
+// with its rows already in that order and the N^2 (real) / 2 N^2 (complex) selects of the first row
+// interchange disappear (they were 10 % of the select instructions of the Robertson kernel).
+template <int N>
+__device__ __forceinline__ void first_pivot_order(const double* __restrict__ mag, int* __restrict__ r, int& p0) {
+    int p = 0;
+    double best = mag[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i)
+        if (mag[i] > best) { best = mag[i]; p = i; }
+    p0 = p;
+    r[0] = p;
+#pragma unroll
+    for (int i = 1; i < N; ++i) r[i] = (i == p) ? 0 : i;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -136,21 +175,25 @@ __device__ __forceinline__ void crecip(double pr, double pi, double& rr, double&
     rr = a * r; ri = -b * r;
 }
 
-template <int N, class MR, class MI>
+template <int N, class MR, class MI, bool kFirstDone = false>
 __device__ __forceinline__ void zlu_factor(MR ar, MI ai, int* __restrict__ piv) {
     constexpr bool REG = Regime<N>::kReg;
     constexpr int U = Regime<N>::kUnroll;
 #pragma unroll U
     for (int k = 0; k < N; ++k) {
         int p = k;
-        double best = fabs(ar[k * N + k]) + fabs(ai[k * N + k]);
+        if (!(kFirstDone && k == 0)) {
+            double best = fabs(ar[k * N + k]) + fabs(ai[k * N + k]);
 #pragma unroll U
-        for (int i = k + 1; i < N; ++i) {
-            const double v = fabs(ar[i * N + k]) + fabs(ai[i * N + k]);
-            if (v > best) { best = v; p = i; }
+            for (int i = k + 1; i < N; ++i) {
+                const double v = fabs(ar[i * N + k]) + fabs(ai[i * N + k]);
+                if (v > best) { best = v; p = i; }
+            }
+            piv[k] = p;
         }
-        piv[k] = p;
-        if (REG) {
+        if (kFirstDone && k == 0) {
+            // nothing to move
+        } else if (REG) {
 #pragma unroll U
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = (p == i);
@@ -197,12 +240,11 @@ template <int N, class MR, class MI>
 __device__ __forceinline__ void zlu_solve(MR ar, MI ai, const int* __restrict__ piv,
                                           double* __restrict__ br, double* __restrict__ bi) {
     constexpr bool REG = Regime<N>::kReg;
-    constexpr int U = Regime<N>::kUnroll;
-#pragma unroll U
-    for (int k = 0; k < N; ++k) {
-        const int p = piv[k];
-        if (REG) {
-#pragma unroll U
+    if constexpr (REG) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int p = piv[k];
+#pragma unroll
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = (p == i);
                 double x = br[k], z = br[i];
@@ -210,34 +252,59 @@ __device__ __forceinline__ void zlu_solve(MR ar, MI ai, const int* __restrict__ 
                 x = bi[k]; z = bi[i];
                 bi[k] = sw ? z : x; bi[i] = sw ? x : z;
             }
-        } else if (p != k) {
-            double x = br[k]; br[k] = br[p]; br[p] = x;
-            x = bi[k]; bi[k] = bi[p]; bi[p] = x;
         }
-    }
-#pragma unroll U
-    for (int i = 1; i < N; ++i) {
-        double sr = br[i], si = bi[i];
-#pragma unroll U
-        for (int j = 0; j < i; ++j) {
-            const double lr = ar[i * N + j], li = ai[i * N + j];
-            sr = fma(li, bi[j], fma(-lr, br[j], sr));
-            si = fma(-li, br[j], fma(-lr, bi[j], si));
+#pragma unroll
+        for (int i = 1; i < N; ++i) {
+            double sr = br[i], si = bi[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) {
+                const double lr = ar[i * N + j], li = ai[i * N + j];
+                sr = fma(li, bi[j], fma(-lr, br[j], sr));
+                si = fma(-li, br[j], fma(-lr, bi[j], si));
+            }
+            br[i] = sr; bi[i] = si;
         }
-        br[i] = sr; bi[i] = si;
-    }
-#pragma unroll U
-    for (int i = N - 1; i >= 0; --i) {
-        double sr = br[i], si = bi[i];
-#pragma unroll U
-        for (int j = i + 1; j < N; ++j) {
-            const double ur = ar[i * N + j], ui = ai[i * N + j];
-            sr = fma(ui, bi[j], fma(-ur, br[j], sr));
-            si = fma(-ui, br[j], fma(-ur, bi[j], si));
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            double sr = br[i], si = bi[i];
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) {
+                const double ur = ar[i * N + j], ui = ai[i * N + j];
+                sr = fma(ui, bi[j], fma(-ur, br[j], sr));
+                si = fma(-ui, br[j], fma(-ur, bi[j], si));
+            }
+            const double dr = ar[i * N + i], di = ai[i * N + i];   // reciprocal pivot
+            br[i] = fma(sr, dr, -si * di);
+            bi[i] = fma(sr, di, si * dr);
         }
-        const double dr = ar[i * N + i], di = ai[i * N + i];   // reciprocal pivot
-        br[i] = fma(sr, dr, -si * di);
-        bi[i] = fma(sr, di, si * dr);
+    } else {
+        for (int k = 0; k < N; ++k) {
+            const int p = piv[k];
+            if (p != k) {
+                double x = br[k]; br[k] = br[p]; br[p] = x;
+                x = bi[k]; bi[k] = bi[p]; bi[p] = x;
+            }
+        }
+        for (int i = 1; i < N; ++i) {
+            double sr = br[i], si = bi[i];
+            for (int j = 0; j < i; ++j) {
+                const double lr = ar[i * N + j], li = ai[i * N + j];
+                sr = fma(li, bi[j], fma(-lr, br[j], sr));
+                si = fma(-li, br[j], fma(-lr, bi[j], si));
+            }
+            br[i] = sr; bi[i] = si;
+        }
+        for (int i = N - 1; i >= 0; --i) {
+            double sr = br[i], si = bi[i];
+            for (int j = i + 1; j < N; ++j) {
+                const double ur = ar[i * N + j], ui = ai[i * N + j];
+                sr = fma(ui, bi[j], fma(-ur, br[j], sr));
+                si = fma(-ui, br[j], fma(-ur, bi[j], si));
+            }
+            const double dr = ar[i * N + i], di = ai[i * N + i];
+            br[i] = fma(sr, dr, -si * di);
+            bi[i] = fma(sr, di, si * dr);
+        }
     }
 }
 

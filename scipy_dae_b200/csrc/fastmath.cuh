@@ -55,6 +55,10 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 #ifndef B200DAE_FASTMATH_LITE
 #define B200DAE_FASTMATH_LITE 1
 #endif
+#ifndef B200DAE_RCP_IGUARD
+#define B200DAE_RCP_IGUARD 0
+#endif
+
 
 // 1 / x.  x = 0 or denormal -> +-inf, x = +-inf -> +-0, NaN -> NaN.
 // The seed is good to 2^-20 or better, so r1 = r0 (1 + e + e^2) already carries a relative error of
@@ -66,7 +70,13 @@ __device__ __forceinline__ double fast_rcp(double x) {
     const double e1 = fma(e0, e0, e0);          // e + e^2
     const double r1 = fma(r0, e1, r0);          // r0 (1 + e + e^2): error e^3
 #if B200DAE_FASTMATH_LITE
+#if B200DAE_RCP_IGUARD
+    // |e0| < 0.25 on the integer pipe: 0.25 = 0x3fd0000000000000 has a zero low word, so the high word
+    // of |e0| decides (NaN / inf compare above it); keeps ~1500 DSETPs per Robertson solve off the FP64 pipe
+    return ((unsigned)(__double2hiint(e0) & 0x7fffffff) < 0x3fd00000u) ? r1 : r0;
+#else
     return (fabs(e0) < 0.25) ? r1 : r0;         // seed already exact for 0 / inf / NaN
+#endif
 #else
     const double e2 = fma(-x, r1, 1.0);
     const double r2 = fma(r1, e2, r1);
@@ -170,16 +180,18 @@ __device__ __forceinline__ double next_toward(double t, double dir) {
 #endif
 }
 
-// x ** k for 0 <= k < 32 without a loop
-__device__ __forceinline__ double powi32(double x, int k) {
-    const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8;
-    double r = (k & 1) ? x : 1.0;
-    r *= (k & 2) ? x2 : 1.0;
-    r *= (k & 4) ? x4 : 1.0;
-    r *= (k & 8) ? x8 : 1.0;
-    r *= (k & 16) ? x16 : 1.0;
+// x ** k for 0 <= k < 2^kBits without a loop
+template <int kBits>
+__device__ __forceinline__ double powi_bits(double x, int k) {
+    double sq = x, r = (k & 1) ? x : 1.0;
+#pragma unroll
+    for (int b = 1; b < kBits; ++b) {
+        sq *= sq;
+        r *= (k & (1 << b)) ? sq : 1.0;
+    }
     return r;
 }
+__device__ __forceinline__ double powi32(double x, int k) { return powi_bits<5>(x, k); }
 
 // all-finite test on the integer pipe: accumulates min over (~hi & 0x7ff00000); 0 <=> some value
 // has an all-ones exponent (inf or NaN).  Keeps 9..35 DSETPs per Newton iteration off the FP64 pipe.

@@ -152,6 +152,13 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
             done = true;
         }
     }
+    if constexpr (Regime<P::N>::kReg && S == 3) {
+        // the headline kernel with a 3-bit exponent in the Newton rate test (newton_max_iter <= 8: the default 7)
+        if (!done && lean && L.newton_max_iter <= 8) {
+            radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, false, 3><<<(unsigned)blocks, T, 0, st>>>(L);
+            done = true;
+        }
+    }
     if (!done) {
         if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true><<<(unsigned)blocks, T, 0, st>>>(L);
         else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false><<<(unsigned)blocks, T, 0, st>>>(L);

@@ -45,7 +45,8 @@ struct RadauLaunch {
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-__device__ __forceinline__ double powi(double x, int k) { return powi32(x, k); }   // 0 <= k < 32
+template <int kBits = 5>
+__device__ __forceinline__ double powi(double x, int k) { return powi_bits<kBits>(x, k); }   // 0 <= k < 2^kBits
 
 // predict_factor, radau.py:198-240 (KAPPA = 1).  inv_sp1 = 1 / (s + 1).
 template <int S>
@@ -68,6 +69,16 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
 
 #ifndef B200DAE_PF_ROOTS
 #define B200DAE_PF_ROOTS 1
+#endif
+#ifndef B200DAE_PIVOT_ASM
+#define B200DAE_PIVOT_ASM 1
+#endif
+#ifndef B200DAE_FIN_LATE
+#define B200DAE_FIN_LATE 1
+#endif
+
+#ifndef B200DAE_EVAL_ALIGNED
+#define B200DAE_EVAL_ALIGNED 1
 #endif
 // B200DAE_PF_ROOTS = 1 (s = 3): err ** (1/4) and err ** (-1/4) from one sqrt and one coupled
 // sqrt / rsqrt, and (err_old / err) ** (1/4) as err_old ** (1/4) * err ** (-1/4) with the first
@@ -101,8 +112,10 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
 #endif
 // kEval: t_eval output compiled in (always in the full-options kernel; the lean kernel comes with
 // and without it, so that dense output at t_eval does not pull in the other option paths).
+// kPowBits: bits of the exponent newton_max_iter - k in the rate test (3 when newton_max_iter <= 8,
+// the launcher's choice for the default 7: two squarings and two select-multiplies less per iteration).
 template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold, bool kLean, bool kJac = false,
-          bool kEval = !kLean>
+          bool kEval = !kLean, int kPowBits = 5>
 __global__ void B200DAE_RADAU_BOUNDS(kThreads, kMinBlocks)
 radau_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
@@ -136,6 +149,9 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     // accesses became 128-bit, 32 instructions less, and the launch got slower, 12.49 ms instead of
     // 12.30 ms per 2^20 solves -- a 128-bit access takes four wavefronts and holds its
     // short-scoreboard slot longer.)
+    // (Tried on B200, round 2: the real factors in shared memory as well, to free 18 registers for
+    // the scheduler: 11.03 instead of 10.87 ms per 2^20 solves; with 7 blocks of 144 registers 14.8 ms;
+    // 128-thread blocks x 3: 13.8 ms.)
     double LUr[N * N];
     int pivr[N], pivc[NCS > 0 ? NCS : 1][N];
     double Y[S][N], Yp[S][N], W[S][N], G[S][N];
@@ -256,6 +272,53 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         if (!lu_valid) {
             FiniteAcc fin;
             const double cr = h * tb.mu_real;
+            if constexpr (kSharedCold && B200DAE_PIVOT_ASM) {
+                // pivoted assembly (dense_lu.cuh: first_pivot_order): column 0 first, then the rows in
+                // the order of LAPACK's first interchange, read through run-time row offsets
+                double mag[N];
+                int r[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) mag[i] = fabs(fma(cr, Jy[i * N], Jyp[i * N]));
+                first_pivot_order<N>(mag, r, pivr[0]);
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const V jy = Jy + r[k] * N, jyp = Jyp + r[k] * N;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const double v = fma(cr, jy[j], jyp[j]);
+                        fin.add(v);
+                        LUr[k * N + j] = v;
+                    }
+                }
+                if (!fin.all_finite()) { status = B200DAE_ST_NONFINITE; break; }
+                lu_factor<N, true>(LUr, pivr);
+#pragma unroll
+                for (int c = 0; c < NCS; ++c) {
+                    const double mr = h * tb.mu_re[c], mi = h * tb.mu_im[c];
+                    double Ar[N * N], Ai[N * N];
+                    int rc[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) mag[i] = fabs(fma(mr, Jy[i * N], Jyp[i * N])) + fabs(mi * Jy[i * N]);
+                    first_pivot_order<N>(mag, rc, pivc[c][0]);
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const V jy = Jy + rc[k] * N, jyp = Jyp + rc[k] * N;
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            const double a = jy[j];
+                            Ar[k * N + j] = fma(mr, a, jyp[j]);
+                            Ai[k * N + j] = mi * a;
+                        }
+                    }
+                    zlu_factor<N, double*, double*, true>(Ar, Ai, pivc[c]);
+#pragma unroll
+                    for (int k = 0; k < N * N; ++k) {
+                        (LUcr0 + c * N * N)[k] = Ar[k];
+                        (LUci0 + c * N * N)[k] = Ai[k];
+                    }
+                }
+            } else {
+#pragma unroll U
 #pragma unroll U
             for (int k = 0; k < N * N; ++k) {
                 const double v = fma(cr, Jy[k], Jyp[k]);
@@ -278,6 +341,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
             lu_factor<N>(LUr, pivr);
 #pragma unroll
             for (int c = 0; c < NCS; ++c) zlu_factor<N>(LUcr0 + c * N * N, LUci0 + c * N * N, pivc[c]);
+            }
             nlu += 1 + NCS;
             lu_valid = true;
         }
@@ -320,16 +384,21 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 // "if not np.all(np.isfinite(F)): break" (radau.py:157-158), tested on G[0] = -TI[0] @ F:
                 // every entry of TI[0] is non-zero (checked by the launcher), so a non-finite F[l][j]
                 // makes G[0][j] non-finite: n values to test instead of s * n
-                {
-                    FiniteAcc fin;
+                FiniteAcc finG;
 #pragma unroll U
-                    for (int j = 0; j < N; ++j) fin.add(G[0][j]);
-                    if (!fin.all_finite()) break;
-                }
+                for (int j = 0; j < N; ++j) finG.add(G[0][j]);
+#if !B200DAE_FIN_LATE
+                if (!finG.all_finite()) break;
+#endif
                 lu_solve<N>(LUr, pivr, G[0]);
 #pragma unroll
                 for (int c = 0; c < NCS; ++c)
                     zlu_solve<N>(LUcr0 + c * N * N, LUci0 + c * N * N, pivc[c], G[2 * c + 1], G[2 * c + 2]);
+#if B200DAE_FIN_LATE
+                // the solves of a non-finite right-hand side are harmless (the iterate is dropped): testing
+                // after them keeps residuals, transformation and solves in one basic block
+                if (!finG.all_finite()) break;
+#endif
                 nsolve += 1 + NCS;
                 // dYp = T @ dW; Yp += dYp   (radau.py:176,179)
 #pragma unroll
@@ -377,12 +446,14 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     rate = dY_norm * inv_norm_old;
                     have_rate = true;
                     const double c = dY_norm * fast_rcp_nz(1.0 - rate);   // only used when rate < 1
-                    if (rate >= 1.0 || powi(rate, newton_max_iter - k) * c > L.newton_tol) break;
+                    if (rate >= 1.0 || powi<kPowBits>(rate, newton_max_iter - k) * c > L.newton_tol) break;
                     if (dY_norm == 0.0 || rate * c < L.newton_tol) { converged = true; break; }
                 } else if (dY_norm == 0.0) {
                     converged = true;
                     break;
                 }
+                // (Tried on B200, round 2: both tests as predicates with ONE exit branch, 11.16 instead of
+                // 10.87 ms per 2^20 solves; the loop unrolled by two, 14.1 ms: spills.)
                 inv_norm_old = inv_norm;
                 has_old = true;
             }
@@ -586,19 +657,37 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 dense_all(ts, y_stop, yp_stop);
             }
         }
-        // t_eval points passed by this step (dae.py:496-515; RadauDenseOutput radau.py:681-699)
+        // t_eval points passed by this step (dae.py:496-515; RadauDenseOutput radau.py:681-699).
+        // The lanes of a warp hold neighbouring instances, so row `r` of y_eval is 32 consecutive doubles
+        // for them -- if they store it in the SAME instruction.  Their next-row indices `ie` differ by a
+        // row or two (their step ends differ), so a lane-local loop pairs row ie_a of lane a with row
+        // ie_b of lane b and every store instruction scatters over several rows.  The loop therefore runs
+        // over the warp's common row range and a lane takes part in the rows of its own range
+        // [ie, ie_end): lanes that emit row r in this step emit it together, as one 256-byte segment.
         if (kEval && L.out.t_eval != nullptr) {
             const double rho = fast_rcp_nz(h);
-            while (ie < L.out.m) {
-                const double te = __ldg(L.out.t_eval + ie);
+            int ie_end = (int)ie;
+            while (ie_end < (int)L.out.m) {
+                const double te = __ldg(L.out.t_eval + ie_end);
                 if (!(dir > 0.0 ? te <= t_lim : te >= t_lim)) break;
+                ++ie_end;
+            }
+#if B200DAE_EVAL_ALIGNED
+            const unsigned amask = __activemask();
+            const int r_lo = __reduce_min_sync(amask, (int)ie), r_hi = __reduce_max_sync(amask, ie_end);
+            for (int r = r_lo; r < r_hi; ++r) {
+                if (r < (int)ie || r >= ie_end) continue;
+#else
+            for (int r = (int)ie; r < ie_end; ++r) {
+#endif
+                const double te = __ldg(L.out.t_eval + r);
                 const double x = (te - t) * rho;
                 double pw[S], dpw[S];
                 double xk = 1.0;
 #pragma unroll
                 for (int k = 0; k < S; ++k) { dpw[k] = (k + 1) * rho * xk; xk *= x; pw[k] = xk; }
-                double* ye = L.out.y_eval + ie * N * ld + inst;
-                double* ype = L.out.yp_eval ? L.out.yp_eval + ie * N * ld + inst : nullptr;
+                double* ye = L.out.y_eval + (int64_t)r * N * ld + inst;
+                double* ype = L.out.yp_eval ? L.out.yp_eval + (int64_t)r * N * ld + inst : nullptr;
 #pragma unroll U
                 for (int j = 0; j < N; ++j) {
                     double a = 0.0, b = 0.0;
@@ -607,8 +696,8 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                     ye[j * ld] = a + y[j];
                     if (ype) ype[j * ld] = b;
                 }
-                ++ie;
             }
+            ie = ie_end;
         }
         // commit
         t = t_lim;
