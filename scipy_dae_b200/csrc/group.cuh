@@ -24,7 +24,9 @@
 // All sync primitives take the group's lane mask, so the 32 / G groups of a warp run
 // independent systems with independent control flow.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #include "dense_lu.cuh"
 
 // Unroll factor of the substitution loops.  Swept on B200 (solves/s, amplifier Radau s=3 / Andrews

@@ -59,7 +59,10 @@ class SharedHostResult:
     by every rank of the node and page-locked where a CUDA device is present, so that
     ``solve_dae_batched_host(out=...)`` of rank r DMA-writes its shard ``[lo:hi]`` into them.
 
-    Rank 0 creates the file, the others map it after a barrier; ``close()`` unpins / unlinks."""
+    Rank 0 creates the file, the others map it after a barrier; ``close()`` unpins / unlinks.
+    The tail of the allocation holds one arrival counter per rank: ``arrive()`` / ``wait_all()`` are
+    the barrier that closes a gather, in host shared memory (microseconds; an NCCL barrier is a
+    device all-reduce plus a synchronisation, 0.1-0.2 ms of a 1.5 ms job at 8 GPUs)."""
 
     FIELDS = (("t_final", torch.float64, ()), ("y_final", torch.float64, ("n",)), ("yp_final", torch.float64, ("n",)),
               ("status", torch.int32, ()), ("counters", torch.int32, (8,)))
@@ -68,6 +71,8 @@ class SharedHostResult:
         import os
         self.N, self.n, self.group = int(N), int(n), group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.epoch = 0
         self.path = os.path.join("/dev/shm", name)
         shapes, off = [], 0
         for key, dt, tail in self.FIELDS:
@@ -75,6 +80,8 @@ class SharedHostResult:
             nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
             shapes.append((key, dt, shape, off, nbytes))
             off += (nbytes + 255) // 256 * 256
+        flags_off = off
+        off += (8 * self.world + 255) // 256 * 256
         self.nbytes = max(off, 256)
         if self.rank == 0:
             with open(self.path, "wb") as fh:
@@ -90,6 +97,21 @@ class SharedHostResult:
             self._pinned = True
         for key, dt, shape, o, nbytes in shapes:
             setattr(self, key, self._raw[o:o + nbytes].view(dt).view(shape))
+        self._flags = self._raw[flags_off:flags_off + 8 * self.world].view(torch.int64)
+        self._flags_np = self._flags.numpy()            # plain loads / stores on the shared mapping
+
+    def arrive(self):
+        """This rank's shard of the current gather has landed in the shared arrays."""
+        self.epoch += 1
+        self._flags_np[self.rank] = self.epoch
+
+    def wait_all(self, timeout_s: float = 120.0):
+        """Rank 0: spin until every rank has arrived at the current epoch."""
+        import time
+        t0 = time.perf_counter()
+        while int(self._flags_np.min()) < self.epoch:
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError("a rank did not deliver its shard")
 
     def shard(self, lo: int, hi: int):
         """The slice [lo:hi] as the result buffers the host pipeline writes into."""
@@ -151,8 +173,11 @@ def solve_dae_sharded(problem, t_span, y0, yp0, params, method="Radau", t_eval=N
                 options.setdefault("device", device)
             _solve_host(problem, t_span, y0[lo:hi], yp0[lo:hi], params[lo:hi], method=method, rtol=rtol, atol=atol,
                         out=host_result.shard(lo, hi), **options)
-        if dist.is_initialized():
-            dist.barrier(group)
+        # the barrier that closes the gather lives in the same shared memory: every rank marks its
+        # arrival (its stream is synchronised: the shard is in host memory), rank 0 waits for all
+        host_result.arrive()
+        if rank == 0:
+            host_result.wait_all()
         return host_result.as_dict() if rank == 0 else None
     to_np = lambda a: a.numpy() if isinstance(a, torch.Tensor) else a        # noqa: E731
     params, y0, yp0 = to_np(params), to_np(y0), to_np(yp0)
