@@ -24,13 +24,18 @@
 #ifndef B200DAE_H
 #define B200DAE_H
 
+#ifdef __CUDACC_RTC__            /* run-time compiled kernels: NVRTC has no <stdint.h> */
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define B200DAE_VERSION 103
+#define B200DAE_VERSION 104
 #define B200DAE_MAX_STAGES 7
 #define B200DAE_MAX_ORDER 6
 #define B200DAE_MAX_N 32
@@ -41,6 +46,7 @@ extern "C" {
 #define B200DAE_EINVAL (-1)      /* bad argument (message says which) */
 #define B200DAE_ENOPROBLEM (-2)  /* unknown problem id / (problem, stages) not compiled */
 #define B200DAE_ECUDA (-3)       /* CUDA runtime error at launch */
+#define B200DAE_ERTC (-4)        /* run-time compilation of a registered problem failed (message = NVRTC log) */
 
 /* per-instance status[] values */
 #define B200DAE_ST_FINISHED 0         /* reached t_bound           (solve_dae status 0)  */
@@ -206,6 +212,27 @@ int b200dae_num_problems(void);
 int b200dae_problem_lookup(const char *name, int32_t *n, int32_t *n_params);
 int b200dae_problem_num_events(int problem_id);   /* event functions g(t, y, y'; p) of the functor */
 const char *b200dae_problem_name(int problem_id);
+
+/* Register a residual at RUN time: the reference takes any Python callable fun(t, y, yp, *args)
+ * (base.py:44-45, dae.py:365-383); here `cuda_src` is CUDA C++ source text that defines
+ *
+ *     struct Problem {
+ *         static constexpr int N = <n>, NP = <n_params>;
+ *         static constexpr bool kHasJac = false;            // true: also provide jac(), see problems.cuh
+ *         __device__ static void eval(double t, const double* y, const double* yp,
+ *                                     const double* p, double* out);       // out[N] = F(t, y, y'; p)
+ *         // optional: kNumEvents + static __device__ double event(int which, t, y, yp, p)
+ *     };
+ *
+ * It is compiled with NVRTC against the library's own kernel templates (csrc/ next to the
+ * library), one kernel variant at a time on first use, cubins cached under B200DAE_RT_CACHE
+ * (default ~/.cache/scipy_dae_b200/rt).  Returns the problem id (usable with every entry point
+ * below), B200DAE_ERTC with the compiler's message in b200dae_last_error(), or B200DAE_EINVAL.
+ * Registering the same name with the same source again returns the same id. */
+int b200dae_register_problem(const char *name, const char *cuda_src, int32_t n, int32_t n_params);
+/* Compile (no device needed) the kernel a solve with these settings would launch:
+ * method 0 = Radau (stages), 1 = BDF; with_t_eval / analytic_jac select the variant. */
+int b200dae_precompile(int problem_id, int32_t method, int32_t stages, int32_t with_t_eval, int32_t analytic_jac);
 
 /* Evaluate the registered residual on the device for N instances (SoA, ld): out[n][ld].
  * Lets the host side verify that a device functor matches its NumPy twin. */

@@ -22,7 +22,7 @@ EXPORTS = ("b200dae_version", "b200dae_last_error", "b200dae_num_problems",
            "b200dae_problem_lookup", "b200dae_problem_name", "b200dae_residual",
            "b200dae_solve_radau", "b200dae_solve_bdf", "b200dae_launch_count",
            "b200dae_fp64_peak_kernel", "b200dae_selftest_fastmath", "b200dae_consistent_ic",
-           "b200dae_problem_num_events")
+           "b200dae_problem_num_events", "b200dae_register_problem", "b200dae_precompile")
 
 
 class B200DaeLibraryError(ImportError):
@@ -115,6 +115,10 @@ def load():
     L.b200dae_problem_num_events.restype = ctypes.c_int
     L.b200dae_problem_num_events.argtypes = [ctypes.c_int]
     L.b200dae_launch_count.restype = i64
+    L.b200dae_register_problem.restype = ctypes.c_int
+    L.b200dae_register_problem.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32]
+    L.b200dae_precompile.restype = ctypes.c_int
+    L.b200dae_precompile.argtypes = [ctypes.c_int] + [ctypes.c_int32] * 4
     L.b200dae_residual.restype = ctypes.c_int
     L.b200dae_residual.argtypes = [ctypes.c_int, i64, i64, dbl, vp, vp, vp, vp, vp]
     L.b200dae_solve_radau.restype = ctypes.c_int
@@ -131,8 +135,8 @@ def load():
     L.b200dae_fp64_peak_kernel.argtypes = [ctypes.c_int, ctypes.c_int, i64, vp, vp]
     L.b200dae_selftest_fastmath.restype = ctypes.c_int
     L.b200dae_selftest_fastmath.argtypes = [i64, vp, vp, vp, vp]
-    if L.b200dae_version() != 103:
-        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 103")
+    if L.b200dae_version() != 104:
+        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 104")
     _lib = L
     return L
 
@@ -142,6 +146,8 @@ def check(rc: int):
         msg = load().b200dae_last_error().decode(errors="replace")
         if rc in (-1, -2):
             raise ValueError(msg)
+        if rc == -4:
+            raise B200DaeError(f"run-time compilation failed:\n{msg}")
         raise B200DaeError(f"libb200dae error {rc}: {msg}")
 
 

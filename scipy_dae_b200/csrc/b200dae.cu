@@ -10,6 +10,7 @@
 
 #include "../../include/b200dae.h"
 #include "launchers.cuh"
+#include "rt_registry.h"
 
 namespace b200dae {
 
@@ -29,10 +30,33 @@ static const ProblemEntry* registry(int* count) {
     return table;
 }
 
-static const ProblemEntry* find_problem(int id) {
+// Problems registered at run time (rt_registry.cu) follow the built-in table: id = count + index.
+// Their entries carry no launchers (rt >= 0 routes the call through NVRTC-compiled kernels).
+static const ProblemEntry* find_problem(int id, int* rt = nullptr) {
     int cnt;
     const ProblemEntry* t = registry(&cnt);
-    return (id >= 0 && id < cnt) ? &t[id] : nullptr;
+    if (rt) *rt = -1;
+    if (id >= 0 && id < cnt) return &t[id];
+    static thread_local ProblemEntry dyn;
+    const char* name;
+    int n, np, nev;
+    if (id >= cnt && rt_info(id - cnt, &name, &n, &np, &nev, nullptr)) {
+        memset(&dyn, 0, sizeof(dyn));
+        dyn.name = name;
+        dyn.n = n;
+        dyn.n_params = np;
+        dyn.n_events = nev;
+        if (rt) *rt = id - cnt;
+        return &dyn;
+    }
+    return nullptr;
+}
+
+static int rt_result(int rc, const std::string& err, const ProblemEntry* e) {
+    if (rc == 0) return 0;
+    if (rc == kRtErrNoJac) return fail(B200DAE_ENOPROBLEM, "problem '%s' provides no analytic Jacobian (kHasJac)", e->name);
+    snprintf(g_err, sizeof(g_err), "%s", err.c_str());
+    return rc;
 }
 
 static int check_common(const ProblemEntry* e, int64_t N, int64_t ld, const double* y0,
@@ -132,7 +156,7 @@ const char* b200dae_last_error(void) { return g_err; }
 int b200dae_num_problems(void) {
     int cnt;
     registry(&cnt);
-    return cnt;
+    return cnt + rt_count();
 }
 
 int b200dae_problem_num_events(int problem_id) {
@@ -150,6 +174,16 @@ int b200dae_problem_lookup(const char* name, int32_t* n, int32_t* n_params) {
                 if (n_params) *n_params = t[i].n_params;
                 return i;
             }
+    if (name)
+        for (int i = 0; i < rt_count(); ++i) {
+            const char* nm;
+            int rn, rnp;
+            if (rt_info(i, &nm, &rn, &rnp, nullptr, nullptr) && strcmp(nm, name) == 0) {
+                if (n) *n = rn;
+                if (n_params) *n_params = rnp;
+                return cnt + i;
+            }
+        }
     return fail(B200DAE_ENOPROBLEM, "unknown problem '%s'", name ? name : "(null)");
 }
 
@@ -160,12 +194,62 @@ const char* b200dae_problem_name(int problem_id) {
 
 int64_t b200dae_launch_count(void) { return g_launches.load(); }
 
+int b200dae_register_problem(const char* name, const char* cuda_src, int32_t n, int32_t n_params) {
+    if (!name || !*name || !cuda_src) return fail(B200DAE_EINVAL, "register_problem needs a name and a source%s", "");
+    for (const char* c = name; *c; ++c)
+        if (!((*c >= 'a' && *c <= 'z') || (*c >= 'A' && *c <= 'Z') || (*c >= '0' && *c <= '9') || *c == '_'))
+            return fail(B200DAE_EINVAL, "problem name '%s' must be an identifier", name);
+    if (n < 1 || n > B200DAE_MAX_N || n_params < 0 || n_params > 64)
+        return fail(B200DAE_EINVAL, "need 1 <= n <= 32 and 0 <= n_params <= 64%s (n=%lld)", "", (long long)n);
+    int cnt;
+    const ProblemEntry* t = registry(&cnt);
+    for (int i = 0; i < cnt; ++i)
+        if (strcmp(t[i].name, name) == 0) return fail(B200DAE_EINVAL, "'%s' is a built-in problem", name);
+    std::string err;
+    const int idx = rt_register(name, cuda_src, n, n_params, err);
+    if (idx < 0) {
+        snprintf(g_err, sizeof(g_err), "%s", err.c_str());
+        return idx;
+    }
+    return cnt + idx;
+}
+
+int b200dae_precompile(int problem_id, int32_t method, int32_t stages, int32_t with_t_eval, int32_t analytic_jac) {
+    int rt;
+    const ProblemEntry* e = find_problem(problem_id, &rt);
+    if (!e) return fail(B200DAE_ENOPROBLEM, "unknown problem id%s (%lld)", "", problem_id);
+    if (rt < 0) return 0;                                 // built-in: compiled by nvcc
+    static const double dummy = 0.0;
+    std::string err;
+    if (method == 0) {
+        if (stages < 1 || stages > B200DAE_MAX_STAGES || stages % 2 != 1) return fail(B200DAE_EINVAL, "bad number of stages%s", "");
+        RadauLaunch L;
+        memset(&L, 0, sizeof(L));
+        L.tb.s = stages;
+        L.newton_iter_embedded = 1;
+        L.newton_max_iter = 7 + (int)((stages - 3) * 2.5);
+        L.analytic_jac = analytic_jac;
+        if (with_t_eval) { L.out.t_eval = &dummy; L.out.m = 1; }
+        return rt_result(rt_launch_radau(rt, L, nullptr, false, err), err, e);
+    }
+    BdfLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.analytic_jac = analytic_jac;
+    if (with_t_eval) { L.out.t_eval = &dummy; L.out.m = 1; }
+    return rt_result(rt_launch_bdf(rt, L, nullptr, false, err), err, e);
+}
+
 int b200dae_residual(int problem_id, int64_t N, int64_t ld, double t, const double* y,
                      const double* yp, const double* params, double* out, void* stream) {
-    const ProblemEntry* e = find_problem(problem_id);
+    int rt;
+    const ProblemEntry* e = find_problem(problem_id, &rt);
     if (!e) return fail(B200DAE_ENOPROBLEM, "unknown problem id%s (%lld)", "", problem_id);
     if (N < 0 || ld < N || !y || !yp || !out) return fail(B200DAE_EINVAL, "bad residual arguments%s", "");
     if (N == 0) return 0;
+    if (rt >= 0) {
+        std::string err;
+        return rt_result(rt_launch_residual(rt, N, ld, t, y, yp, params, out, (cudaStream_t)stream, err), err, e);
+    }
     const int rc = e->residual(N, ld, t, y, yp, params, out, (cudaStream_t)stream);
     if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
     return 0;
@@ -175,12 +259,13 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
                         const double* params, double t0, double t_bound, const double* atol,
                         const b200dae_radau_opts* opts, const b200dae_radau_tables* tb,
                         const b200dae_outputs* out, void* stream) {
-    const ProblemEntry* e = find_problem(problem_id);
+    int rt;
+    const ProblemEntry* e = find_problem(problem_id, &rt);
     int rc = check_common(e, N, ld, y0, yp0, params, atol, out);
     if (rc) return rc;
     if (!opts || !tb) return fail(B200DAE_EINVAL, "opts / tables must not be NULL%s", "");
     const int s = tb->s;
-    if (s < 1 || s > B200DAE_MAX_STAGES || s % 2 != 1 || !e->radau[s])
+    if (s < 1 || s > B200DAE_MAX_STAGES || s % 2 != 1 || (rt < 0 && !e->radau[s]))
         return fail(B200DAE_ENOPROBLEM, "Radau stages not compiled for problem '%s' (stages=%lld)", e->name, s);
     if (!(opts->max_step > 0)) return fail(B200DAE_EINVAL, "`max_step` must be positive.%s", "");
     if (opts->first_step > fabs(t_bound - t0)) return fail(B200DAE_EINVAL, "`first_step` exceeds bounds.%s", "");
@@ -236,6 +321,10 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
     L.out = normalise(out);
     rc = check_events(e, out, &L.ev);
     if (rc) return rc;
+    if (rt >= 0) {
+        std::string err;
+        return rt_result(rt_launch_radau(rt, L, (cudaStream_t)stream, true, err), err, e);
+    }
     rc = e->radau[s](L, (cudaStream_t)stream);
     if (rc == kErrNoJac)
         return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s' (stages=%lld)", e->name, s);
@@ -246,7 +335,8 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
 int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, const double* yp0,
                       const double* params, double t0, double t_bound, const double* atol,
                       const b200dae_bdf_opts* opts, const b200dae_outputs* out, void* stream) {
-    const ProblemEntry* e = find_problem(problem_id);
+    int rt;
+    const ProblemEntry* e = find_problem(problem_id, &rt);
     int rc = check_common(e, N, ld, y0, yp0, params, atol, out);
     if (rc) return rc;
     if (!opts) return fail(B200DAE_EINVAL, "opts must not be NULL%s", "");
@@ -293,9 +383,13 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
     L.out = normalise(out);
     rc = check_events(e, out, &L.ev);
     if (rc) return rc;
+    if (rt >= 0) {
+        std::string err;
+        return rt_result(rt_launch_bdf(rt, L, (cudaStream_t)stream, true, err), err, e);
+    }
     rc = e->bdf(L, (cudaStream_t)stream);
     if (rc == kErrNoJac)
-        return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s'%s", e->name);
+        return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s'", e->name);
     if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
     return 0;
 }
@@ -304,7 +398,8 @@ int b200dae_consistent_ic(int problem_id, int64_t N, int64_t ld, double t0, doub
                           const double* params, const double* atol, const int32_t* fixed_y,
                           const int32_t* fixed_yp, const b200dae_cic_opts* opts, double* f_out,
                           int32_t* status, int32_t* n_iter, void* stream) {
-    const ProblemEntry* e = find_problem(problem_id);
+    int rt;
+    const ProblemEntry* e = find_problem(problem_id, &rt);
     if (!e) return fail(B200DAE_ENOPROBLEM, "unknown problem id%s (%lld)", "", problem_id);
     if (N < 0 || ld < N) return fail(B200DAE_EINVAL, "need 0 <= N <= ld%s (N=%lld)", "", (long long)N);
     if (N > 0 && (!y0 || !yp0 || !status || (e->n_params > 0 && !params)))
@@ -336,9 +431,13 @@ int b200dae_consistent_ic(int problem_id, int64_t N, int64_t ld, double t0, doub
     L.f_out = f_out;
     L.status = status;
     L.n_iter = n_iter;
+    if (rt >= 0) {
+        std::string err;
+        return rt_result(rt_launch_cic(rt, L, (cudaStream_t)stream, true, err), err, e);
+    }
     const int rc = e->cic(L, (cudaStream_t)stream);
     if (rc == kErrNoJac)
-        return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s'%s", e->name);
+        return fail(B200DAE_ENOPROBLEM, "analytic Jacobian not compiled for problem '%s'", e->name);
     if (rc) return fail(B200DAE_ECUDA, "CUDA: %s", cudaGetErrorString((cudaError_t)rc));
     return 0;
 }

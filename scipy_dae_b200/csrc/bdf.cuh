@@ -9,7 +9,7 @@
 // The quasi-constant-step difference array D[(max_order+3)][n] is indexed by the run-time order,
 // so it lives in per-thread local memory (L1-resident: 9*n doubles per instance).
 #pragma once
-#include <stdint.h>
+#include "rt_compat.cuh"
 #include "../../include/b200dae.h"
 #include "events.cuh"
 #include "fd_jacobian.cuh"

@@ -8,7 +8,7 @@
 // are the row-per-lane routines of group.cuh, the FD Jacobian runs its columns on n lanes at
 // once (radau_group.cuh: fd_jacobian_group).
 #pragma once
-#include <stdint.h>
+#include "rt_compat.cuh"
 #include "../../include/b200dae.h"
 #include "bdf.cuh"
 #include "radau_group.cuh"

@@ -13,7 +13,7 @@
 // This runs once per instance before the integration, so it is written for clarity: rolled
 // loops over run-time sizes, matrices in per-thread local memory (5 n^2 doubles).
 #pragma once
-#include <stdint.h>
+#include "rt_compat.cuh"
 #include "../../include/b200dae.h"
 #include "fd_jacobian.cuh"
 

@@ -15,7 +15,7 @@
 //                  dynamically.
 // The diagonal of U is stored as its reciprocal so the solves multiply instead of divide.
 #pragma once
-#include <math.h>
+#include "rt_compat.cuh"
 #include "fastmath.cuh"
 
 namespace b200dae {

@@ -9,8 +9,7 @@
 // (kind 2, problems.cuh: EventOf), with the reference's `direction` and `terminal` attributes
 // (terminal = k stops at the k-th occurrence).  The kind is spec.of_yp[k].
 #pragma once
-#include <math.h>
-#include <stdint.h>
+#include "rt_compat.cuh"
 #include "../../include/b200dae.h"
 #include "problems.cuh"
 

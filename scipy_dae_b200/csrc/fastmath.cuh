@@ -10,7 +10,7 @@
 // Accuracy: <= 1 ulp (tests/test_gpu_fastmath.py); the IEEE results are reproduced for
 // 0, inf, NaN and denormal arguments where the integrator relies on them (zero pivot -> inf).
 #pragma once
-#include <math.h>
+#include "rt_compat.cuh"
 
 namespace b200dae {
 

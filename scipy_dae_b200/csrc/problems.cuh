@@ -24,7 +24,7 @@
 // call site and, up to the libm functions (exp, sin, cos; sqrt and division are IEEE), to the C
 // oracle twin (built with -ffp-contract=off) and the NumPy twin the reference integrates.
 #pragma once
-#include <math.h>
+#include "rt_compat.cuh"
 
 namespace b200dae {
 

@@ -16,7 +16,7 @@
 // different call sites; only the trip counts differ.  Every quirk of the reference that moves
 // step sequences is kept and marked "quirk".
 #pragma once
-#include <stdint.h>
+#include "rt_compat.cuh"
 #include "../../include/b200dae.h"
 #include "fastmath.cuh"
 #include "events.cuh"

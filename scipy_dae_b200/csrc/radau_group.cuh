@@ -20,7 +20,7 @@
 // (aliased with the FD scratch: the Jacobian is only ever refreshed when the factors are stale),
 // S staged stage vectors, the pivot-row buffer.
 #pragma once
-#include <stdint.h>
+#include "rt_compat.cuh"
 #include "../../include/b200dae.h"
 #include "group.cuh"
 #include "radau.cuh"
