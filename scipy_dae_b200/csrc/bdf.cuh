@@ -47,6 +47,48 @@ __device__ __forceinline__ double norm_root(double norm, double e) {
     return (norm == INFINITY) ? 0.0 : pow_ctrl(norm, e);
 }
 
+// log2(x) to ~1e-13 for the ORDER SELECTION (bdf.py:398-404: factors = error_norms ** (-1 / k),
+// np.argmax(factors), np.max(factors)).  The three candidate factors are compared through
+// key_i = (-1 / k_i) log2(norm_i) (factor_i = 2 ** key_i, same order) and only the winner goes
+// through pow: one libdevice pow (~200 instructions, a call) instead of three per selection.  The
+// argmax can differ from the reference's only when two factors agree to ~1e-13 relative.
+// 0 -> -inf (and subnormals with it: the factor is beyond any bound either way), inf -> inf, NaN -> NaN.
+__device__ __forceinline__ double log2_key(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                    // mantissa in [1, 2)
+    double m = __hiloint2double(hi, lo);
+    if (m > 1.4142135623730951) { m *= 0.5; ++e; }         // [sqrt(1/2), sqrt(2))
+    const double s = (m - 1.0) * fast_rcp_nz(m + 1.0);     // log m = 2 atanh(s), |s| < 0.1716
+    const double z = s * s;
+    double q = 1.0 / 15.0;
+    q = fma(q, z, 1.0 / 13.0);
+    q = fma(q, z, 1.0 / 11.0);
+    q = fma(q, z, 1.0 / 9.0);
+    q = fma(q, z, 1.0 / 7.0);
+    q = fma(q, z, 1.0 / 5.0);
+    q = fma(q, z, 1.0 / 3.0);
+    q = fma(q, z, 1.0);
+    const double r = fma(2.0 * 1.4426950408889634 * s, q, (double)e);
+    const bool normal = (x >= 2.2250738585072014e-308) && (x < INFINITY);
+    return normal ? r : ((x < 2.2250738585072014e-308) ? -INFINITY : x);    // x < tiny is false for NaN: NaN stays
+}
+
+// argmax and max of norms[i] ** neg_inv_i over the three candidate orders, np.argmax semantics
+// (first maximum, a NaN wins): returns the index, `best` = the winning factor from ONE pow.
+__device__ __forceinline__ int select_order(const double (&norms)[3], double e0, double e1, double e2, double& best) {
+    const double k0 = e0 * log2_key(norms[0]), k1 = e1 * log2_key(norms[1]), k2 = e2 * log2_key(norms[2]);
+    int arg = 0;
+    double kb = k0;
+    if (kb == kb && (k1 > kb || k1 != k1)) { kb = k1; arg = 1; }
+    if (kb == kb && (k2 > kb || k2 != k2)) { kb = k2; arg = 2; }
+    const double nb = (arg == 0) ? norms[0] : ((arg == 1) ? norms[1] : norms[2]);
+    const double eb = (arg == 0) ? e0 : ((arg == 1) ? e1 : e2);
+    best = norm_root(nb, eb);
+    return arg;
+}
+
 // change_D (bdf.py:24-29): D[:order+1] = (R @ U).T @ D[:order+1], evaluated as U.T @ (R.T @ D)
 // with R = cumprod_i (i - 1 - factor*j) / i generated column by column (bdf.py:14-21).
 //
@@ -357,13 +399,8 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             } else {
                 norms[2] = INFINITY;
             }
-            double best = 0.0;
-            int arg = 0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double fc = norm_root(norms[i], L.neg_inv[order + i]);
-                if (i == 0 || (best == best && (fc > best || fc != fc))) { best = fc; arg = i; }
-            }
+            double best;
+            const int arg = select_order(norms, L.neg_inv[order], L.neg_inv[order + 1], L.neg_inv[order + 2], best);
             order += arg - 1;
             const double factor = fmin(10.0, safety * best);
             h_abs *= factor;

@@ -352,13 +352,8 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             } else {
                 norms[2] = INFINITY;
             }
-            double best = 0.0;
-            int arg = 0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double fc = norm_root(norms[i], L.neg_inv[order + i]);
-                if (i == 0 || (best == best && (fc > best || fc != fc))) { best = fc; arg = i; }
-            }
+            double best;
+            const int arg = select_order(norms, L.neg_inv[order], L.neg_inv[order + 1], L.neg_inv[order + 2], best);
             order += arg - 1;
             const double factor = fmin(10.0, safety * best);
             h_abs *= factor;

@@ -50,15 +50,20 @@ template <int N> struct GroupSize { static constexpr int value = N <= 8 ? 8 : (N
 // capped at 8 (128 registers, 16 warps); measured on B200 for Akzo Nobel Radau s = 3: 4 blocks 3.64 M,
 // 6 blocks 4.8 M, 8 blocks 5.26 M solves/s.  The amplifier's shared memory admits 6, so it stays at
 // 168 registers.
-template <class P, int S>
+template <class P, int S, bool GJ = false>
 struct RadauGroupShape {
     static constexpr int G = GroupSize<P::N>::value;
     static constexpr int T = (G == 32) ? 32 : 64;
-    using Lay = RadauGroupLayout<P::N, S, G>;
+    // one warp per system (G = 32): the variant with the Jacobians in global memory (radau_group.cuh)
+    // is worth its scratch block; the plain solve (lean kernel, FD Jacobian) uses it
+    static constexpr bool kCanGJ = (G == 32);
+    using Lay = RadauGroupLayout<P::N, S, G, GJ>;
     static constexpr size_t smem = (size_t)(T / G) * Lay::doubles(P::NP) * sizeof(double);
+    static constexpr size_t scratch = (size_t)Lay::kScratch * sizeof(double);    // global bytes per instance
     static_assert(smem <= 227 * 1024, "per-block shared memory");
-    static constexpr int kFit = (int)((227 * 1024) / (smem + 1024));
-    static constexpr int MB = (G == 32) ? 1 : (kFit >= 8 ? 8 : (kFit >= B200DAE_GROUP_MINBLOCKS(G) ? B200DAE_GROUP_MINBLOCKS(G) : (kFit > 0 ? kFit : 1)));
+    static constexpr int kFit = (int)((228 * 1024) / (smem + 1024));            // 1 KB per block is reserved
+    static constexpr int MB = (G == 32) ? (GJ ? (kFit > 8 ? 8 : kFit) : 1)
+                                        : (kFit >= 8 ? 8 : (kFit >= B200DAE_GROUP_MINBLOCKS(G) ? B200DAE_GROUP_MINBLOCKS(G) : (kFit > 0 ? kFit : 1)));
 };
 
 template <class P>

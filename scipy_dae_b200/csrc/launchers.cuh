@@ -50,12 +50,12 @@ static bool force_thread_regime() {
 
 constexpr int kErrNoJac = -77;    // analytic Jacobian requested but not compiled for (problem, stages)
 
-template <class P, int S, bool J = false, bool LEAN = false>
-static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
-    using Sh = RadauGroupShape<P, S>;
+template <class P, int S, bool J, bool LEAN, bool GJ>
+static int launch_radau_group_shape(const RadauLaunch& L, cudaStream_t st) {
+    using Sh = RadauGroupShape<P, S, GJ>;
     constexpr int G = Sh::G, T = Sh::T, MB = Sh::MB;
     constexpr size_t smem = Sh::smem;
-    auto kern = radau_group_kernel<P, S, G, T, MB, J, LEAN>;
+    auto kern = radau_group_kernel<P, S, G, T, MB, J, LEAN, GJ>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -66,6 +66,31 @@ static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
     kern<<<(unsigned)blocks, T, smem, st>>>(L);
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
+}
+
+// B200DAE_GLOBAL_J=0 keeps the Jacobians of the one-warp-per-system kernels in shared memory (A/B)
+static bool global_j_enabled() {
+    static const bool v = !(getenv("B200DAE_GLOBAL_J") && strcmp(getenv("B200DAE_GLOBAL_J"), "0") == 0);
+    return v;
+}
+
+template <class P, int S, bool J = false, bool LEAN = false>
+static int launch_radau_group(const RadauLaunch& L, cudaStream_t st) {
+    if constexpr (LEAN && !J && RadauGroupShape<P, S>::kCanGJ) {
+        // Jacobians in a stream-ordered global scratch block (2 n (n|1) doubles per instance, L2-resident
+        // for the resident systems); beyond 8 GB, or if the pool cannot serve it, the shared-memory variant runs
+        const size_t bytes = (size_t)L.N * RadauGroupShape<P, S, true>::scratch;
+        void* scr = nullptr;
+        if (global_j_enabled() && bytes <= ((size_t)8 << 30) && cudaMallocAsync(&scr, bytes, st) == cudaSuccess) {
+            RadauLaunch Lg = L;
+            Lg.jscratch = (double*)scr;
+            const int rc = launch_radau_group_shape<P, S, J, LEAN, true>(Lg, st);
+            cudaFreeAsync(scr, st);
+            return rc;
+        }
+        (void)cudaGetLastError();
+    }
+    return launch_radau_group_shape<P, S, J, LEAN, false>(L, st);
 }
 
 template <class P, int S>

@@ -41,6 +41,7 @@ struct RadauLaunch {
     const double *y0, *yp0, *params;
     b200dae_outputs out;
     EventLaunch ev;             // ev.spec.n_events == 0: no events
+    double* jscratch;           // group kernels with the Jacobians in global memory (RadauGroupLayout: kGJ): N blocks, else NULL
 };
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }

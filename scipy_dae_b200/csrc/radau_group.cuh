@@ -27,23 +27,34 @@
 
 namespace b200dae {
 
-template <int N, int S, int G>
+// kGJ: the Jacobians Jy, Jyp live in GLOBAL memory (a per-instance scratch block that stays in L2:
+// written once per Jacobian refresh, read once per factorisation) instead of shared memory.  For
+// Andrews' squeezer (n = 26, s = 5) that and two trims (the pivot index buffer aliases the staged
+// residuals, which are dead during a factorisation; the real factors need no read-ahead pad because
+// the work area follows them) take a system from 43.7 KB to 32.2 KB: 7 resident systems per SM
+// instead of 5 (the kernel runs ONE warp per system and is latency-bound at ~1.1 warps per scheduler).
+template <int N, int S, int G, bool kGJ = false>
 struct RadauGroupLayout {   // offsets in doubles inside one group's shared-memory block
     static constexpr int NCS = S / 2;
     static constexpr int LD = N | 1;                       // odd leading dimension: conflict-free rows
     static constexpr int LDC = N | 1;                      // in double2 units
     static constexpr int kJ = N * LD;                      // doubles per Jacobian
-    static constexpr int kLUr = N * LD + N + ((N * LD + N) & 1);      // real factors (+ N read-ahead pad)
+    static constexpr int kJs = kGJ ? 0 : kJ;               // ... of which in shared memory
+    static constexpr int kLUr0 = N * LD + (kGJ ? 0 : N);   // real factors (+ N read-ahead pad, see above)
+    static constexpr int kLUr = kLUr0 + (kLUr0 & 1);
     static constexpr int kLUc = (N * LDC + N) * 2;         // one complex factor matrix, in doubles
     static constexpr int kCplx = NCS * kLUc;
     static constexpr int kFd = 3 * G * LD;                 // FD scratch: x copy, f(attempt 0), f(attempt 1) per lane
     static constexpr int kWork = (kCplx > kFd ? kCplx : kFd) + ((kCplx > kFd ? kCplx : kFd) & 1);
     static constexpr int kVec = S * LD;                    // one staged S x n block
-    static constexpr int oJy = 0, oJyp = oJy + kJ, oLUr = oJyp + kJ + ((2 * kJ) & 1);
+    static constexpr int oJy = 0, oJyp = oJy + kJs, oLUr = oJyp + kJs + ((2 * kJs) & 1);
     static constexpr int oWork = oLUr + kLUr;
     static constexpr int oY = oWork + kWork, oYp = oY + kVec, oF = oYp + kVec;
-    static constexpr int oIdx = oF + kVec + ((3 * kVec) & 1);        // G ints
-    static constexpr int oPar = oIdx + (G + 1) / 2;                  // NP parameters (appended by the kernel)
+    static constexpr int kIdx = (G + 1) / 2;               // G ints
+    static_assert(!kGJ || kVec >= kIdx, "pivot index buffer aliases the staged residuals");
+    static constexpr int oIdx = kGJ ? oF : oF + kVec + ((3 * kVec) & 1);
+    static constexpr int oPar = kGJ ? oF + kVec + ((3 * kVec) & 1) : oIdx + kIdx;   // NP parameters (appended by the kernel)
+    static constexpr int kScratch = kGJ ? 2 * kJ : 0;      // doubles of global scratch per instance
     __host__ __device__ static constexpr int doubles(int np) { return oPar + np + ((oPar + np) & 1); }   // keep groups 16 B aligned
 };
 
@@ -179,11 +190,11 @@ __device__ __forceinline__ void analytic_jacobian_group(const Grp& g, double t, 
 
 // kLean: default error estimator, no t_eval / step trace / events (compiled out: these kernels
 // are bound by instruction fetch, every KB of cold code costs throughput).
-template <class P, int S, int G, int kThreads, int kMinBlocks, bool kJac = false, bool kLean = false>
+template <class P, int S, int G, int kThreads, int kMinBlocks, bool kJac = false, bool kLean = false, bool kGJ = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
-    using Lay = RadauGroupLayout<N, S, G>;
+    using Lay = RadauGroupLayout<N, S, G, kGJ>;
     constexpr int LD = Lay::LD, LDC = Lay::LDC;
     static_assert(G >= N && G >= S, "group must cover the components and the stages");
     extern __shared__ __align__(16) double smem[];
@@ -197,8 +208,8 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     const b200dae_radau_tables& tb = L.tb;
 
     double* sm = smem + (size_t)(threadIdx.x / G) * Lay::doubles(NP);
-    double* sJy = sm + Lay::oJy;
-    double* sJyp = sm + Lay::oJyp;
+    double* sJy = kGJ ? L.jscratch + inst * Lay::kScratch : sm + Lay::oJy;
+    double* sJyp = kGJ ? sJy + Lay::kJ : sm + Lay::oJyp;
     double* sWork = sm + Lay::oWork;
     double* sY = sm + Lay::oY;
     double* sYp = sm + Lay::oYp;
