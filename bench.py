@@ -169,7 +169,7 @@ def run_configs(dev, fp64_peak_tflops, nthreads):
         ratio = (np.abs(rn.y_final[:n_par] - ref["y_final"]) / np.maximum(10 * rtol * np.abs(ref["y_final"]), atol)).max(axis=1)[both]
         dacc = np.abs(rn.n_accepted[:n_par] - ref["n_accepted"])[both] / ref["n_accepted"][both]
         rows.append({"config": label, "problem": problem, "method": method, "options": opts, "instances": N,
-                     "kernel": ("radau_group" if method == "Radau" else "bdf_group") + f"_kernel<{problem}>",
+                     "kernel": (("radau" if method == "Radau" else "bdf") + ("" if pr.n <= 6 else "_group") + f"_kernel<{problem}>"),
                      "ms": ms, "value": N / (ms * 1e-3), "unit": UNIT, "n_unfinished": int((~ok).sum()),
                      "work_per_solve": {k: v / max(int(ok.sum()), 1) for k, v in cnt.items()},
                      "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak_tflops, "unit": "TFLOP/s",

@@ -30,9 +30,12 @@ struct Vec {
     __device__ __forceinline__ Vec operator+(int off) const { return Vec{p + (SH ? off * STRIDE : off)}; }
 };
 
+#ifndef B200DAE_REG_MAXN
+#define B200DAE_REG_MAXN 6
+#endif
 template <int N>
 struct Regime {
-    static constexpr bool kReg = (N <= 4);
+    static constexpr bool kReg = (N <= B200DAE_REG_MAXN);
     static constexpr int kUnroll = kReg ? 64 : 1;   // "#pragma unroll kUnroll": full vs none
 };
 

@@ -37,10 +37,12 @@ template <class P, int S>
 struct RadauTune {
     static constexpr int N = P::N, NCS = S / 2;
     static constexpr bool kReg = Regime<N>::kReg;
-    static constexpr int kThreads = kReg ? B200DAE_REG_THREADS : 64;
+    static constexpr bool kBig = kReg && N > 4;         // unrolled thread regime beyond n = 4 (B200DAE_REG_MAXN)
+    static constexpr int kThreads = kReg ? (kBig ? 32 : B200DAE_REG_THREADS) : 64;
     static constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
-    static constexpr bool kSharedCold = kReg && (kCold * kThreads * 8 <= 48 * 1024);
-    static constexpr int kMinBlocks = (kSharedCold && S <= 3) ? B200DAE_REG_MINBLOCKS : 1;
+    static constexpr bool kSharedCold = kReg && (kBig || kCold * kThreads * 8 <= 48 * 1024);
+    static constexpr size_t kDynSmem = (kSharedCold && (size_t)kCold * kThreads * 8 > 48 * 1024) ? (size_t)kCold * kThreads * 8 : 0;
+    static constexpr int kMinBlocks = kBig ? 1 : ((kSharedCold && S <= 3) ? B200DAE_REG_MINBLOCKS : 1);
 };
 
 // Group size of the cooperative kernels (group.cuh): the smallest power of two >= n (>= 8).

@@ -118,29 +118,42 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
                            L.ev.spec.n_events == 0;
     const bool lean = lean_opts && L.out.t_eval == nullptr;
     bool done = false;
+    if (Tn::kDynSmem > 0) {
+        // cold state of the unrolled thread regime beyond n = 4: dynamic shared memory above 48 KB
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+            cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+            if constexpr (Regime<P::N>::kReg && S == 3) {
+                cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+                cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+            }
+            attr_set = true;
+        }
+    }
     if constexpr (kJacOk && Regime<P::N>::kReg) {
         if (L.analytic_jac) {
-            if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, true><<<(unsigned)blocks, T, 0, st>>>(L);
-            else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false, true><<<(unsigned)blocks, T, 0, st>>>(L);
+            if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, true><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
+            else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false, true><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
             done = true;
         }
     }
     if constexpr (Regime<P::N>::kReg && S == 3) {
         if (!done && lean_opts && !lean) {
-            radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, true><<<(unsigned)blocks, T, 0, st>>>(L);
+            radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, true><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
             done = true;
         }
     }
     if constexpr (Regime<P::N>::kReg && S == 3) {
         // the headline kernel with a 3-bit exponent in the Newton rate test (newton_max_iter <= 8: the default 7)
         if (!done && lean && L.newton_max_iter <= 8) {
-            radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, false, 3><<<(unsigned)blocks, T, 0, st>>>(L);
+            radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, false, 3><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
             done = true;
         }
     }
     if (!done) {
-        if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true><<<(unsigned)blocks, T, 0, st>>>(L);
-        else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false><<<(unsigned)blocks, T, 0, st>>>(L);
+        if (lean) radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
+        else radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
     }
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();

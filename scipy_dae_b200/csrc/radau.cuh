@@ -138,7 +138,12 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     // kSharedCold they live in shared memory [element][thread], which frees ~100 registers and
     // lets a third warp per scheduler hide the 8.7-cycle DFMA latency.
     constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
-    __shared__ double s_cold[kSharedCold ? kCold * kThreads : 1];
+    // up to 48 KB the block's cold state is a static array; beyond that (4 < n <= B200DAE_REG_MAXN:
+    // 32-thread blocks) it is the launch's dynamic shared memory
+    constexpr bool kDynCold = kSharedCold && ((size_t)kCold * kThreads * sizeof(double) > 48 * 1024);
+    extern __shared__ __align__(16) double s_cold_dyn[];
+    __shared__ double s_cold_static[(kSharedCold && !kDynCold) ? kCold * kThreads : 1];
+    double* const s_cold = kDynCold ? s_cold_dyn : s_cold_static;
     double r_cold[kSharedCold ? 1 : kCold];
     using V = Vec<kSharedCold, kThreads>;
     const V Jy{kSharedCold ? (s_cold + threadIdx.x) : r_cold};

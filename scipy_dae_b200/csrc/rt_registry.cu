@@ -432,7 +432,7 @@ int rt_launch_radau(int idx, const RadauLaunch& L, cudaStream_t st, bool do_laun
     const bool jac_ok = p.has_jac && S == 3;
     if (L.analytic_jac && !jac_ok) return kRtErrNoJac;
     char key[128], kern[512], shape[256];
-    if (p.n > 4) {                                         // group regime (launch_radau_group)
+    if (p.n > B200DAE_REG_MAXN) {                          // group regime (launch_radau_group)
         const bool glean = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_eval == nullptr &&
                            L.out.t_steps == nullptr && L.ev.spec.n_events == 0;
         const bool J = L.analytic_jac != 0, lean = !J && glean;
@@ -470,7 +470,7 @@ int rt_launch_bdf(int idx, const BdfLaunch& L, cudaStream_t st, bool do_launch, 
     char key[128], kern[512], shape[256];
     const bool ev = L.ev.spec.n_events > 0;
     const bool plain = !ev && L.out.t_eval == nullptr && L.out.t_steps == nullptr;
-    if (p.n > 4) {
+    if (p.n > B200DAE_REG_MAXN) {
         const bool J = L.analytic_jac != 0;
         const bool E = ev, O = J ? true : !plain;
         snprintf(key, sizeof(key), "bdf_group j%d e%d o%d", J, E, O);
