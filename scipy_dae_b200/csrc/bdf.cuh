@@ -141,7 +141,9 @@ __device__ __noinline__ void change_D(double* __restrict__ D, int order, double 
 
 // kLean: no t_eval output, no step trace, no events -- those paths are compiled out (the kernel is
 // instruction-fetch bound: ncu stall_no_inst 38 % with all options in, 7200 instructions).
-template <class P, int kThreads, bool kJac = false, bool kLean = false>
+// kSharedCold: Jy, Jyp and the FD step factors (touched once per Jacobian refresh / factorisation)
+// live in shared memory [element][thread] instead of registers / local memory (as in radau.cuh).
+template <class P, int kThreads, bool kJac = false, bool kLean = false, bool kSharedCold = false>
 __global__ void __launch_bounds__(kThreads)
 bdf_kernel(const __grid_constant__ BdfLaunch L) {
     constexpr int N = P::N, NP = P::NP;
@@ -156,7 +158,15 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
 #pragma unroll U
     for (int j = 0; j < N; ++j) { y[j] = L.y0[j * ld + inst]; yp[j] = L.yp0[j * ld + inst]; }
 
-    double Jy[N * N], Jyp[N * N], factor_y[N], factor_yp[N], LU[N * N];
+    constexpr int kCold = 2 * N * N + 2 * N;
+    constexpr bool kDynCold = kSharedCold && ((size_t)kCold * kThreads * sizeof(double) > 48 * 1024);
+    extern __shared__ __align__(16) double s_cold_dyn[];
+    __shared__ double s_cold_static[(kSharedCold && !kDynCold) ? kCold * kThreads : 1];
+    double r_cold[kSharedCold ? 1 : kCold];
+    using V = Vec<kSharedCold, kThreads>;
+    const V Jy{kSharedCold ? ((kDynCold ? s_cold_dyn : s_cold_static) + threadIdx.x) : r_cold};
+    const V Jyp = Jy + N * N, factor_y = Jyp + N * N, factor_yp = factor_y + N;
+    double LU[N * N];
     int piv[N];
     double D[kBdfRows * N];
     double y_predict[N], psi[N], inv_scale[N], y_new[N], yp_new[N], d[N], f[N];
@@ -211,8 +221,8 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
     while (status == B200DAE_ST_RUNNING) {
         // ---- phase J: FD Jacobian at the committed (t, y, yp) (base.py:297, bdf.py:330) ------
         if (need_jac) {
-            if constexpr (kJac) analytic_jacobian<P, N>(t, y, yp, p, (double*)Jy, (double*)Jyp);
-            else fd_jacobian<P, double*>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
+            if constexpr (kJac) analytic_jacobian<P, N>(t, y, yp, p, Jy, Jyp);
+            else fd_jacobian<P, V>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
             ++njev;
             need_jac = false;
         }

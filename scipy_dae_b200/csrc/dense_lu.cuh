@@ -81,7 +81,7 @@ __device__ __forceinline__ void lu_factor(double* __restrict__ a, int* __restric
             }
         }
         const double pv = a[k * N + k];
-        const double r = fast_rcp(pv);
+        const double r = fast_rcp_scale(pv);
         a[k * N + k] = r;                              // reciprocal pivot
         const double rs = (pv != 0.0) ? r : 1.0;       // LAPACK skips the scaling for a zero pivot
 #pragma unroll U

@@ -99,6 +99,24 @@ __device__ __forceinline__ double fast_rcp_nz(double x) {
 
 __device__ __forceinline__ double fast_div(double a, double b) { return a * fast_rcp(b); }
 
+// 1 / x where the IEEE limits for x = 0 / inf do not change what happens next (B200DAE_RCP_LIMITS=0):
+//   * the Newton scale atol + rtol |y| (zero only for atol = 0 and y = 0, where the reference divides
+//     by zero too: the increment norm is non-finite either way and the Newton iteration fails; the
+//     error-estimate scale keeps the IEEE limits, because inf rejects a step where NaN would accept it),
+//   * LU pivots: a zero pivot leaves inf in the reference's factors and NaN here; both make the next
+//     triangular solve non-finite, which the non-finite test after the solves catches (the multipliers
+//     use the separate "LAPACK skips the scaling" select, not this value).
+#ifndef B200DAE_RCP_LIMITS
+#define B200DAE_RCP_LIMITS 0
+#endif
+__device__ __forceinline__ double fast_rcp_scale(double x) {
+#if B200DAE_RCP_LIMITS
+    return fast_rcp(x);
+#else
+    return fast_rcp_nz(x);
+#endif
+}
+
 // sqrt(x), correct for 0, inf, NaN, negative and denormal arguments.
 // Arguments below 1e-200 (denormals would flush in the seed) are rescaled first, by selects.
 // (Tried on B200: a never-taken branch for that case instead of the selects, 6 instructions

@@ -45,6 +45,22 @@ struct RadauTune {
     static constexpr int kMinBlocks = kBig ? 1 : ((kSharedCold && S <= 3) ? B200DAE_REG_MINBLOCKS : 1);
 };
 
+// Launch shape of the thread-per-system BDF kernel.  kSharedCold (Jacobians and FD step factors in
+// shared memory [element][thread], as in the Radau kernel) is compiled but OFF: measured on B200 it
+// costs the L1 capacity the spilled difference array D lives in (Akzo Nobel: 86 KB per 128-thread
+// block, 5.95 M -> 5.01 M solves/s; Robertson: 16.0 M -> 15.8 M).  -DB200DAE_BDF_SHARED_COLD=1 enables it.
+#ifndef B200DAE_BDF_SHARED_COLD
+#define B200DAE_BDF_SHARED_COLD 0
+#endif
+template <class P>
+struct BdfTune {
+    static constexpr int N = P::N;
+    static constexpr int kThreads = BlockSize<P>::value;
+    static constexpr bool kSharedCold = Regime<N>::kReg && (B200DAE_BDF_SHARED_COLD != 0);
+    static constexpr size_t kColdBytes = (size_t)(2 * N * N + 2 * N) * kThreads * sizeof(double);
+    static constexpr size_t kDynSmem = (kSharedCold && kColdBytes > 48 * 1024) ? kColdBytes : 0;
+};
+
 // Group size of the cooperative kernels (group.cuh): the smallest power of two >= n (>= 8).
 template <int N> struct GroupSize { static constexpr int value = N <= 8 ? 8 : (N <= 16 ? 16 : 32); };
 

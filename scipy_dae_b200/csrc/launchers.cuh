@@ -192,17 +192,31 @@ static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
         }
         if (L.analytic_jac) return kErrNoJac;
     }
-    constexpr int T = BlockSize<P>::value;
+    using Tn = BdfTune<P>;
+    constexpr int T = Tn::kThreads;
+    constexpr bool SC = Tn::kSharedCold;
     const int64_t blocks = (L.N + T - 1) / T;
     const bool lean = L.out.t_eval == nullptr && L.out.t_steps == nullptr && L.ev.spec.n_events == 0;
+    if (Tn::kDynSmem > 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(bdf_kernel<P, T, false, false, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+            if constexpr (Regime<P::N>::kReg) {
+                cudaFuncSetAttribute(bdf_kernel<P, T, false, true, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+                if constexpr (P::kHasJac)
+                    cudaFuncSetAttribute(bdf_kernel<P, T, true, false, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+            }
+            attr_set = true;
+        }
+    }
     bool done = false;
     if constexpr (P::kHasJac && Regime<P::N>::kReg) {
-        if (L.analytic_jac) { bdf_kernel<P, T, true><<<(unsigned)blocks, T, 0, st>>>(L); done = true; }
+        if (L.analytic_jac) { bdf_kernel<P, T, true, false, SC><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L); done = true; }
     }
     if constexpr (Regime<P::N>::kReg) {
-        if (!done && lean) { bdf_kernel<P, T, false, true><<<(unsigned)blocks, T, 0, st>>>(L); done = true; }
+        if (!done && lean) { bdf_kernel<P, T, false, true, SC><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L); done = true; }
     }
-    if (!done) bdf_kernel<P, T><<<(unsigned)blocks, T, 0, st>>>(L);
+    if (!done) bdf_kernel<P, T, false, false, SC><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
     g_launches.fetch_add(1);
     return (int)cudaGetLastError();
 }

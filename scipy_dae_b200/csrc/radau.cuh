@@ -270,7 +270,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 }
             }
 #pragma unroll U
-            for (int j = 0; j < N; ++j) h_inv_scale[j] = h * fast_rcp(fma(fabs(y[j]), rtol, L.atol[j]));
+            for (int j = 0; j < N; ++j) h_inv_scale[j] = h * fast_rcp_scale(fma(fabs(y[j]), rtol, L.atol[j]));
         }
         retry = false;
 

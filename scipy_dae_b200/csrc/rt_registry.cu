@@ -453,7 +453,7 @@ int rt_launch_radau(int idx, const RadauLaunch& L, cudaStream_t st, bool do_laun
         snprintf(key, sizeof(key), "radau s%d l%d j%d e%d b%d", S, kl, kj, ke, bits);
         snprintf(kern, sizeof(kern), "b200dae::radau_kernel<P, %d, RadauTune<P, %d>::kThreads, RadauTune<P, %d>::kMinBlocks, "
                  "RadauTune<P, %d>::kSharedCold, %s, %s, %s, %d>", S, S, S, S, tf(kl), tf(kj), tf(ke), bits);
-        snprintf(shape, sizeof(shape), "1, RadauTune<P, %d>::kThreads, RadauTune<P, %d>::kMinBlocks, 0", S, S);
+        snprintf(shape, sizeof(shape), "1, RadauTune<P, %d>::kThreads, RadauTune<P, %d>::kMinBlocks, (long long)RadauTune<P, %d>::kDynSmem", S, S, S);
     }
     RtKernel* k = nullptr;
     int rc = get_kernel(p, key, kern, shape, &k, err);
@@ -480,8 +480,8 @@ int rt_launch_bdf(int idx, const BdfLaunch& L, cudaStream_t st, bool do_launch, 
     } else {
         const bool J = L.analytic_jac != 0, lean = !J && plain;
         snprintf(key, sizeof(key), "bdf j%d l%d", J, lean);
-        snprintf(kern, sizeof(kern), "b200dae::bdf_kernel<P, BlockSize<P>::value, %s, %s>", tf(J), tf(lean));
-        snprintf(shape, sizeof(shape), "1, BlockSize<P>::value, 1, 0");
+        snprintf(kern, sizeof(kern), "b200dae::bdf_kernel<P, BdfTune<P>::kThreads, %s, %s, BdfTune<P>::kSharedCold>", tf(J), tf(lean));
+        snprintf(shape, sizeof(shape), "1, BdfTune<P>::kThreads, 1, (long long)BdfTune<P>::kDynSmem");
     }
     RtKernel* k = nullptr;
     int rc = get_kernel(p, key, kern, shape, &k, err);

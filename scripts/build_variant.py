@@ -49,7 +49,7 @@ def main():
     abi = os.path.join(out_dir, f"b200dae_{name}.o")
     subprocess.run([B.find_nvcc(), *B.NVCC_FLAGS, *flags, "-c", "-o", abi,
                     os.path.join(B.CSRC, "b200dae.cu")], check=True)
-    objs = [abi, stubs, obj]
+    objs = [abi, stubs, obj, os.path.join(B.OBJ_DIR, "rt_registry.o")]   # run-time registry: from the product build
     if with_stages:
         st = os.path.join(out_dir, f"problem_robertson_stages_{name}.o")
         subprocess.run([B.find_nvcc(), *B.NVCC_FLAGS, *flags, "-c", "-o", st,
