@@ -534,11 +534,11 @@ def main():
     # ---- secondary: the same ensemble WITH t_eval output (the HBM-heavier mode) --------
     te_modes = []
     if rank == 0:
-        for m in [int(x) for x in (args.t_eval_points or []) if int(x) > 0]:
+        for m, layout in [(int(x), lay) for x in (args.t_eval_points or []) if int(x) > 0 for lay in ("soa", "instance")]:
             te = torch.from_numpy(np.logspace(-6, 7, m)).to(dev)
             try:
-                y_eval = torch.empty((m, n, Nper), **f64)
-                yp_eval = torch.empty((m, n, Nper), **f64)
+                y_eval = torch.empty((m, n, Nper) if layout == "soa" else (Nper, m, n), **f64)
+                yp_eval = torch.empty_like(y_eval)
             except RuntimeError as exc:          # not enough free HBM for 2 x 8 m n N bytes
                 te_modes.append({"t_eval_points": m, "skipped": f"{type(exc).__name__}"})
                 continue
@@ -548,6 +548,8 @@ def main():
             out2.status, out2.counters = status.data_ptr(), counters.data_ptr()
             out2.t_eval, out2.m = te.data_ptr(), m
             out2.y_eval, out2.yp_eval, out2.n_eval_valid = y_eval.data_ptr(), yp_eval.data_ptr(), nev.data_ptr()
+            if layout == "instance":          # [N][m][n]: every instance's rows one contiguous stream
+                out2.eval_stride_row, out2.eval_stride_comp, out2.eval_stride_inst = n, 1, m * n
 
             def launch_te():
                 _lib.check(L.b200dae_solve_radau(pid, Nper, Nper, d_y0.data_ptr(), d_yp0.data_ptr(), d_p.data_ptr(),
@@ -565,10 +567,11 @@ def main():
             assert bool((nev == m).all())
             ms = float(np.mean(ts))
             nbytes = Nper * (compulsory_bytes(n, npar) + 16 * n * m)
-            te_modes.append({"t_eval_points": m, "ms_per_launch": ms, "solves_per_s": Nper / (ms * 1e-3),
+            te_modes.append({"t_eval_points": m, "layout": "[N][m][n]" if layout == "instance" else "[m][n][N]",
+                             "ms_per_launch": ms, "solves_per_s": Nper / (ms * 1e-3),
                              "hbm_bytes_per_launch": nbytes, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
                              "note": "same ensemble with dense output at m log-spaced points in [1e-6, 1e7] written to "
-                                     "HBM (y and yp, [m][n][N] SoA); lean kernel twin with t_eval output"})
+                                     "HBM (y and yp); lean kernel twin with t_eval output"})
             del y_eval, yp_eval, nev
             torch.cuda.empty_cache()
     te_mode = te_modes[0] if te_modes else None

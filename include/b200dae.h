@@ -35,7 +35,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define B200DAE_VERSION 104
+#define B200DAE_VERSION 105
 #define B200DAE_MAX_STAGES 7
 #define B200DAE_MAX_ORDER 6
 #define B200DAE_MAX_N 32
@@ -162,7 +162,13 @@ typedef struct b200dae_events {
  *   counters          [8][ld]   see enum above
  *   t_eval            [m]       DEVICE, sorted in the direction of integration (dae.py:384-403)
  *   y_eval, yp_eval   [m][n][ld] dense output at t_eval (dae.py:496-515; Radau: radau.py:681-699,
- *                                BDF: bdf.py:525-548); rows >= n_eval_valid[i] are left untouched
+ *                                BDF: bdf.py:525-548); rows >= n_eval_valid[i] are left untouched.
+ *                                Entry (row r, component j, instance i) lives at
+ *                                r * eval_stride_row + j * eval_stride_comp + i * eval_stride_inst
+ *                                (in doubles); all three 0 = the default [m][n][ld] (n * ld, ld, 1).
+ *                                The instance-major form [ld][m][n] is (n, 1, m * n): every
+ *                                instance's (m, n) block contiguous; the default is the faster
+ *                                one on the device (a warp writes a row as 256-byte segments)
  *   n_eval_valid      [ld]      number of t_eval points produced (all m unless the instance failed:
  *                               solve_dae breaks before recording a failed step, dae.py:451-453)
  *   t_steps           [steps_cap][ld]     accepted step ends incl. t0 (what solve_dae returns as
@@ -200,6 +206,7 @@ typedef struct b200dae_outputs {
     double *dense_coef;
     int64_t coef_rows;
     const b200dae_events *events;   /* HOST pointer, NULL = no events */
+    int64_t eval_stride_row, eval_stride_comp, eval_stride_inst;   /* layout of y_eval / yp_eval, see above */
 } b200dae_outputs;
 
 int b200dae_version(void);

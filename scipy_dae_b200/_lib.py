@@ -66,7 +66,9 @@ class Outputs(ctypes.Structure):
                 ("yp_steps", ctypes.c_void_p), ("n_steps", ctypes.c_void_p),
                 ("h_steps", ctypes.c_void_p), ("order_steps", ctypes.c_void_p),
                 ("dense_coef", ctypes.c_void_p), ("coef_rows", ctypes.c_int64),
-                ("events", ctypes.c_void_p)]
+                ("events", ctypes.c_void_p),
+                ("eval_stride_row", ctypes.c_int64), ("eval_stride_comp", ctypes.c_int64),
+                ("eval_stride_inst", ctypes.c_int64)]
 
 
 MAX_EVENTS = 4
@@ -135,8 +137,8 @@ def load():
     L.b200dae_fp64_peak_kernel.argtypes = [ctypes.c_int, ctypes.c_int, i64, vp, vp]
     L.b200dae_selftest_fastmath.restype = ctypes.c_int
     L.b200dae_selftest_fastmath.argtypes = [i64, vp, vp, vp, vp]
-    if L.b200dae_version() != 104:
-        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 104")
+    if L.b200dae_version() != 105:
+        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 105")
     _lib = L
     return L
 

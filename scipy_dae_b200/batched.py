@@ -224,7 +224,7 @@ def _warn_extraneous(extraneous):
 def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="Radau",
                       t_eval=None, rtol=1e-3, atol=1e-6, *, device=None, stream=None,
                       record_steps: int = 0, record_dense: bool = False, max_steps: int = 0,
-                      check_finite: bool = True,
+                      check_finite: bool = True, eval_layout: str = "soa",
                       events=None, event_cap: int = 16, **options) -> BatchedDaeResult:
     """Integrate ``N`` instances of a registered problem from ``t_span[0]`` to ``t_span[1]``.
 
@@ -240,12 +240,19 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
                                BdfDenseOutput objects); ``result.solution(i)`` is then instance i's
                                ``DaeSolution`` without any re-integration
     max_steps : int            > 0: stop every instance after that many accepted steps (status -3)
+    eval_layout : str          device layout of the ``t_eval`` states behind ``result.y`` / ``result.yp``
+                               (both are ``[N, n, m]`` views either way): ``"soa"`` = ``[m][n][N]`` (default:
+                               the lanes of a warp write a row together, measured 34.5 ms against 55.0 ms
+                               for 2^20 Robertson instances at m = 1000), ``"instance"`` = ``[N][m][n]``
+                               (every instance's ``(m, n)`` block contiguous, e.g. for per-instance D2H)
     events : list of ThresholdEvent / FunctorEvent   located on the dense output with Brent's method as in the
                                reference (dae.py:30-109, 466-490); a terminal event ends the instance
                                with status 1; up to ``event_cap`` occurrences per event are stored
 
     Returns a ``BatchedDaeResult`` of device tensors (call ``.numpy()`` for host arrays).
     """
+    if eval_layout not in ("instance", "soa"):
+        raise ValueError("eval_layout must be 'instance' or 'soa'")
     L = _lib.load()
     prob = get_problem(problem)
     pid, n, npar = _lib.problem_lookup(prob.name)
@@ -313,8 +320,14 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
             te = _validate_t_eval(t_eval, t0, t_bound)
             m = te.shape[0]
             te_d = torch.from_numpy(te).to(device)
-            y_eval = torch.full((m, n, ld), float("nan"), **f64)
-            yp_eval = torch.full((m, n, ld), float("nan"), **f64)
+            # "soa" = [m][n][ld] (default); "instance" = [ld][m][n] through the strides of b200dae_outputs
+            if eval_layout == "instance":
+                y_eval = torch.full((ld, m, n), float("nan"), **f64)
+                yp_eval = torch.full((ld, m, n), float("nan"), **f64)
+                out.eval_stride_row, out.eval_stride_comp, out.eval_stride_inst = n, 1, m * n
+            else:
+                y_eval = torch.full((m, n, ld), float("nan"), **f64)
+                yp_eval = torch.full((m, n, ld), float("nan"), **f64)
             n_eval_valid = torch.empty((ld,), **i32)
             out.t_eval, out.m = te_d.data_ptr(), m
             out.y_eval, out.yp_eval = y_eval.data_ptr(), yp_eval.data_ptr()
@@ -428,8 +441,12 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
         n_newton_iter=counters[7], method=method, problem=prob.name)
     if t_eval is not None:
         res.t = te_d
-        res.y = y_eval.permute(2, 1, 0)      # [N, n, m]
-        res.yp = yp_eval.permute(2, 1, 0)
+        if eval_layout == "instance":
+            res.y = y_eval.permute(0, 2, 1)      # [N, n, m]
+            res.yp = yp_eval.permute(0, 2, 1)
+        else:
+            res.y = y_eval.permute(2, 1, 0)      # [N, n, m]
+            res.yp = yp_eval.permute(2, 1, 0)
         res.n_eval_valid = n_eval_valid
     if t_steps is not None:
         res.t_steps = t_steps.t()            # [N, K]

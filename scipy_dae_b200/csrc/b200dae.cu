@@ -73,6 +73,8 @@ static int check_common(const ProblemEntry* e, int64_t N, int64_t ld, const doub
         return fail(B200DAE_EINVAL, "out->y_final / t_final / status must not be NULL%s", "");
     if (out->m < 0 || (out->m > 0 && (!out->t_eval || !out->y_eval)))
         return fail(B200DAE_EINVAL, "m > 0 needs t_eval and y_eval%s", "");
+    if (out->eval_stride_row < 0 || out->eval_stride_comp < 0 || out->eval_stride_inst < 0)
+        return fail(B200DAE_EINVAL, "y_eval strides must not be negative%s", "");
     if (out->steps_cap < 0 || (out->steps_cap > 0 && !out->t_steps))
         return fail(B200DAE_EINVAL, "steps_cap > 0 needs t_steps%s", "");
     if (out->dense_coef && (out->steps_cap <= 0 || !out->h_steps || !out->y_steps))
@@ -103,10 +105,15 @@ static int check_events(const ProblemEntry* e, const b200dae_outputs* out, Event
     return 0;
 }
 
-static b200dae_outputs normalise(const b200dae_outputs* out) {
+static b200dae_outputs normalise(const b200dae_outputs* out, int n, int64_t ld) {
     b200dae_outputs o = *out;
     o.events = nullptr;
     if (o.m == 0) { o.t_eval = nullptr; o.y_eval = nullptr; o.yp_eval = nullptr; }
+    if (o.eval_stride_row == 0 && o.eval_stride_comp == 0 && o.eval_stride_inst == 0) {
+        o.eval_stride_row = (int64_t)n * ld;              // the default [m][n][ld]
+        o.eval_stride_comp = ld;
+        o.eval_stride_inst = 1;
+    }
     if (o.steps_cap == 0) { o.t_steps = nullptr; o.y_steps = nullptr; o.yp_steps = nullptr; o.dense_coef = nullptr; }
     if (o.dense_coef == nullptr) { o.h_steps = nullptr; o.order_steps = nullptr; }
     return o;
@@ -318,7 +325,7 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
     L.y0 = y0;
     L.yp0 = yp0;
     L.params = params;
-    L.out = normalise(out);
+    L.out = normalise(out, e->n, ld);
     rc = check_events(e, out, &L.ev);
     if (rc) return rc;
     if (rt >= 0) {
@@ -380,7 +387,7 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
     L.y0 = y0;
     L.yp0 = yp0;
     L.params = params;
-    L.out = normalise(out);
+    L.out = normalise(out, e->n, ld);
     rc = check_events(e, out, &L.ev);
     if (rc) return rc;
     if (rt >= 0) {

@@ -481,13 +481,13 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
             while (ie < L.out.m) {
                 const double te = __ldg(L.out.t_eval + ie);
                 if (!(dir > 0.0 ? te <= t : te >= t)) break;
-                double* ye = L.out.y_eval + ie * N * ld + inst;
-                double* ype = L.out.yp_eval ? L.out.yp_eval + ie * N * ld + inst : nullptr;
+                double* ye = L.out.y_eval + ie * L.out.eval_stride_row + inst * L.out.eval_stride_inst;
+                double* ype = L.out.yp_eval ? L.out.yp_eval + ie * L.out.eval_stride_row + inst * L.out.eval_stride_inst : nullptr;
                 double ya[N], ypa[N];
                 dense_all(te, ya, ypa);
                 for (int j = 0; j < N; ++j) {
-                    ye[j * ld] = ya[j];
-                    if (ype) ype[j * ld] = ypa[j];
+                    ye[j * L.out.eval_stride_comp] = ya[j];
+                    if (ype) ype[j * L.out.eval_stride_comp] = ypa[j];
                 }
                 ++ie;
             }

@@ -436,8 +436,8 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
                 double ya, ypa;
                 dense_lane(te, ya, ypa);
                 if (act) {
-                    L.out.y_eval[(ie * N + lane) * ld + inst] = ya;
-                    if (L.out.yp_eval) L.out.yp_eval[(ie * N + lane) * ld + inst] = ypa;
+                    L.out.y_eval[ie * L.out.eval_stride_row + lane * L.out.eval_stride_comp + inst * L.out.eval_stride_inst] = ya;
+                    if (L.out.yp_eval) L.out.yp_eval[ie * L.out.eval_stride_row + lane * L.out.eval_stride_comp + inst * L.out.eval_stride_inst] = ypa;
                 }
                 ++ie;
             }

@@ -678,29 +678,33 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
                 if (!(dir > 0.0 ? te <= t_lim : te >= t_lim)) break;
                 ++ie_end;
             }
+            // (instance-major layouts, eval_stride_inst != 1: every lane streams its own rows, nothing to align)
+            const int64_t e_sr = L.out.eval_stride_row, e_sc = L.out.eval_stride_comp, e_si = L.out.eval_stride_inst;
+            int r_lo = (int)ie, r_hi = ie_end;
 #if B200DAE_EVAL_ALIGNED
-            const unsigned amask = __activemask();
-            const int r_lo = __reduce_min_sync(amask, (int)ie), r_hi = __reduce_max_sync(amask, ie_end);
+            if (e_si == 1) {
+                const unsigned amask = __activemask();
+                r_lo = __reduce_min_sync(amask, (int)ie);
+                r_hi = __reduce_max_sync(amask, ie_end);
+            }
+#endif
             for (int r = r_lo; r < r_hi; ++r) {
                 if (r < (int)ie || r >= ie_end) continue;
-#else
-            for (int r = (int)ie; r < ie_end; ++r) {
-#endif
                 const double te = __ldg(L.out.t_eval + r);
                 const double x = (te - t) * rho;
                 double pw[S], dpw[S];
                 double xk = 1.0;
 #pragma unroll
                 for (int k = 0; k < S; ++k) { dpw[k] = (k + 1) * rho * xk; xk *= x; pw[k] = xk; }
-                double* ye = L.out.y_eval + (int64_t)r * N * ld + inst;
-                double* ype = L.out.yp_eval ? L.out.yp_eval + (int64_t)r * N * ld + inst : nullptr;
+                double* ye = L.out.y_eval + (int64_t)r * e_sr + inst * e_si;
+                double* ype = L.out.yp_eval ? L.out.yp_eval + (int64_t)r * e_sr + inst * e_si : nullptr;
 #pragma unroll U
                 for (int j = 0; j < N; ++j) {
                     double a = 0.0, b = 0.0;
 #pragma unroll
                     for (int k = 0; k < S; ++k) { a = fma(ZP[j * S + k], pw[k], a); b = fma(ZP[j * S + k], dpw[k], b); }
-                    ye[j * ld] = a + y[j];
-                    if (ype) ype[j * ld] = b;
+                    ye[j * e_sc] = a + y[j];
+                    if (ype) ype[j * e_sc] = b;
                 }
             }
             ie = ie_end;

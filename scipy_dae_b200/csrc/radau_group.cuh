@@ -625,8 +625,8 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                 double av, bv;
                 dense_lane(te, av, bv);
                 if (act) {
-                    L.out.y_eval[(ie * N + lane) * ld + inst] = av;
-                    if (L.out.yp_eval) L.out.yp_eval[(ie * N + lane) * ld + inst] = bv;
+                    L.out.y_eval[ie * L.out.eval_stride_row + lane * L.out.eval_stride_comp + inst * L.out.eval_stride_inst] = av;
+                    if (L.out.yp_eval) L.out.yp_eval[ie * L.out.eval_stride_row + lane * L.out.eval_stride_comp + inst * L.out.eval_stride_inst] = bv;
                 }
                 ++ie;
             }
