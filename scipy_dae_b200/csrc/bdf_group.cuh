@@ -218,6 +218,19 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         // ---- phase F: LU of Jy + c*Jyp (bdf.py:320-321) ------------------------------------------
         if (!lu_valid) {
             bool fin = true;
+#if B200DAE_LU_INPLACE
+            if (act) {
+#pragma unroll 2
+                for (int k = 0; k < N; ++k) {
+                    const double v = fma(c, sJyp[jc * LD + k], sJy[jc * LD + k]);
+                    fin = fin && finite_d(v);
+                    sLU[jc * LD + k] = v;
+                }
+            }
+            if (!g.all(fin)) { status = B200DAE_ST_NONFINITE; break; }
+            g.sync();
+            group_lu_factor_inplace<N, LD>(g, perm, sLU);
+#else
             double a[N];
 #pragma unroll
             for (int k = 0; k < N; ++k) {
@@ -227,6 +240,7 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
             }
             if (!g.all(fin)) { status = B200DAE_ST_NONFINITE; break; }
             group_lu_factor<N, LD>(g, a, perm, sLU, sIdx);
+#endif
             ++nlu;
             lu_valid = true;
         }

@@ -31,6 +31,13 @@
 
 // Unroll factor of the substitution loops.  Swept on B200 (solves/s, amplifier Radau s=3 / Andrews
 // Radau s=5): 1 -> 60.8 k / 91.6 k, 2 -> 63.4 k / 93.7 k, 4 (Andrews) -> 90.8 k, full for n <= 8 -> 56.7 k.
+// 0 (default): the rotated-register LU below; 1: the in-place shared-memory variants (measured slower, see there)
+#ifndef B200DAE_LU_INPLACE
+#define B200DAE_LU_INPLACE 0
+#endif
+#ifndef B200DAE_LU_INPLACE_UNROLL
+#define B200DAE_LU_INPLACE_UNROLL 2
+#endif
 #ifndef B200DAE_SOLVE_UNROLL
 #define B200DAE_SOLVE_UNROLL(N) 2
 #endif
@@ -210,6 +217,112 @@ __device__ __forceinline__ void group_zlu_factor(const Grp& g, double (&ar)[N], 
     g.sync();
     perm = act ? sidx[lane] : lane;
     g.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-place variants (-DB200DAE_LU_INPLACE=1; compiled out by default): the matrix is assembled straight
+// into the shared-memory factor storage and eliminated there.  Lane r owns the row at POSITION r for
+// the whole factorisation: an interchange swaps the two rows physically (every lane moves one
+// column), the elimination of step k touches columns k+1 .. N-1 only.  Against the rotated-register
+// form above this halves the multiply-adds (sum (N-k-1) instead of N (N-1) per lane), drops the
+// pivot-row write (N predicated stores by ONE lane per step: 10.7 % of all instructions of the
+// Andrews kernel, ncu round 2) and the 2N..4N registers that held the rows; same operations on the
+// same values in the same order per entry, so the factors are bit-identical (verified: identical work
+// counters on every ensemble).  MEASURED SLOWER on B200 all the same: Andrews Radau s = 5 103.3 k
+// (rotated) against 94.8 / 94.4 / 97.5 / 96.8 k solves/s (in place, inner loop unrolled 1 / 2 / 4 / 8),
+// amplifier 80.8 -> 80.4 k (Radau), 58.6 -> 57.3 k (BDF).  These kernels are latency-bound: the in-place
+// update puts a shared-memory load AND store into every entry's dependency chain, the rotated form
+// only a broadcast load, and its extra multiply-adds issue into idle slots.
+template <int N, int LD, class Grp>
+__device__ __forceinline__ void group_lu_factor_inplace(const Grp& g, int& perm, double* __restrict__ mat) {
+    constexpr int kLuUnroll = B200DAE_LU_INPLACE_UNROLL;
+    const int lane = g.lane;
+    const bool act = lane < N;
+    int orig = lane;
+    double* myrow = mat + (act ? lane : 0) * LD;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        const bool cand = act && lane >= k;
+        double v = cand ? myrow[k] : 0.0;
+        int ppos;
+        pivot_search(g, cand, fabs(v), lane, ppos);
+        if (ppos != k) {                                 // same decision in every lane of the group
+            if (act) {                                   // LAPACK interchanges the full rows
+                const double x = mat[k * LD + lane], z = mat[ppos * LD + lane];
+                mat[k * LD + lane] = z;
+                mat[ppos * LD + lane] = x;
+            }
+            const int ok = g.bcast(orig, k), op = g.bcast(orig, ppos);
+            if (lane == k) orig = op;
+            else if (lane == ppos) orig = ok;
+            g.sync();
+            if (cand) v = myrow[k];
+        }
+        const double* prow = mat + k * LD;
+        const double pv = prow[k];
+        const double r = fast_rcp(pv);
+        const double rs = (pv != 0.0) ? r : 1.0;       // LAPACK skips the scaling for a zero pivot
+        if (act && lane > k) {
+            const double l = v * rs;
+            myrow[k] = l;
+#pragma unroll kLuUnroll
+            for (int j = k + 1; j < N; ++j) myrow[j] = fma(-l, prow[j], myrow[j]);
+        }
+        g.sync();
+        if (lane == k) myrow[k] = r;                    // reciprocal pivot (not read again before the solves)
+    }
+    g.sync();
+    perm = orig;
+}
+
+template <int N, int LDC, class Grp>
+__device__ __forceinline__ void group_zlu_factor_inplace(const Grp& g, int& perm, double2* __restrict__ cmat) {
+    constexpr int kLuUnroll = B200DAE_LU_INPLACE_UNROLL;
+    const int lane = g.lane;
+    const bool act = lane < N;
+    int orig = lane;
+    double2* myrow = cmat + (act ? lane : 0) * LDC;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        const bool cand = act && lane >= k;
+        double2 v = cand ? myrow[k] : make_double2(0.0, 0.0);
+        int ppos;
+        pivot_search(g, cand, fabs(v.x) + fabs(v.y), lane, ppos);   // izamax: |re| + |im|
+        if (ppos != k) {
+            if (act) {
+                const double2 x = cmat[k * LDC + lane], z = cmat[ppos * LDC + lane];
+                cmat[k * LDC + lane] = z;
+                cmat[ppos * LDC + lane] = x;
+            }
+            const int ok = g.bcast(orig, k), op = g.bcast(orig, ppos);
+            if (lane == k) orig = op;
+            else if (lane == ppos) orig = ok;
+            g.sync();
+            if (cand) v = myrow[k];
+        }
+        const double2* prow = cmat + k * LDC;
+        const double2 pv = prow[k];
+        double rr, ri;
+        crecip(pv.x, pv.y, rr, ri);
+        const bool nz = (pv.x != 0.0) || (pv.y != 0.0);
+        const double sr = nz ? rr : 1.0, si = nz ? ri : 0.0;
+        if (act && lane > k) {
+            const double lr = fma(v.x, sr, -v.y * si), li = fma(v.x, si, v.y * sr);
+            myrow[k] = make_double2(lr, li);
+#pragma unroll kLuUnroll
+            for (int j = k + 1; j < N; ++j) {
+                const double2 u = prow[j];
+                double2 a = myrow[j];
+                a.x = fma(li, u.y, fma(-lr, u.x, a.x));
+                a.y = fma(-li, u.x, fma(-lr, u.y, a.y));
+                myrow[j] = a;
+            }
+        }
+        g.sync();
+        if (lane == k) myrow[k] = make_double2(rr, ri);
+    }
+    g.sync();
+    perm = orig;
 }
 
 // Solves LU x = b for one real system and NC complex systems at once (same step index k, so

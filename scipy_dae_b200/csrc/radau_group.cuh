@@ -333,6 +333,42 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         // ---- phase F (radau.py:536-538) -----------------------------------------------------
         if (!lu_valid) {
             bool fin = true;
+#if B200DAE_LU_INPLACE
+            // rows assembled straight into the factor storage (group.cuh: in-place variants)
+#pragma unroll 1
+            for (int c = 0; c < NCS; ++c) {
+                const double mr = h * tb.mu_re[c], mi = h * tb.mu_im[c];
+                double2* cm = sCplx + c * (Lay::kLUc / 2);
+                if (act) {
+#pragma unroll 2
+                    for (int k = 0; k < N; ++k) {
+                        const double jy = sJy[jc * LD + k], jyp = sJyp[jc * LD + k];
+                        const double re = fma(mr, jy, jyp), im = mi * jy;
+                        fin = fin && finite_d(re) && finite_d(im);
+                        cm[jc * LDC + k] = make_double2(re, im);
+                    }
+                }
+                g.sync();
+                int pm;
+                group_zlu_factor_inplace<N, LDC>(g, pm, cm);
+#pragma unroll
+                for (int cc = 0; cc < NCS; ++cc)
+                    if (cc == c) cperm[cc] = pm;
+            }
+            {
+                const double cr = h * tb.mu_real;
+                if (act) {
+#pragma unroll 2
+                    for (int k = 0; k < N; ++k) {
+                        const double v = fma(cr, sJy[jc * LD + k], sJyp[jc * LD + k]);
+                        fin = fin && finite_d(v);
+                        sLUr[jc * LD + k] = v;
+                    }
+                }
+                g.sync();
+                group_lu_factor_inplace<N, LD>(g, perm, sLUr);
+            }
+#else
 #pragma unroll 1
             for (int c = 0; c < NCS; ++c) {
                 const double mr = h * tb.mu_re[c], mi = h * tb.mu_im[c];
@@ -361,6 +397,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
                 }
                 group_lu_factor<N, LD>(g, a, perm, sLUr, sIdx);
             }
+#endif
             // lu_factor(check_finite=True) raises before factoring; the factors of a non-finite
             // matrix are never used because the instance stops here
             if (!g.all(fin)) { status = B200DAE_ST_NONFINITE; break; }
