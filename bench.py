@@ -576,6 +576,49 @@ def main():
             torch.cuda.empty_cache()
     te_mode = te_modes[0] if te_modes else None
 
+    # ---- secondary: smaller ensembles (2^16, 2^18 for the size curve) and the
+    # divergence stress sigma = 0.5 (rate constants spread over e^-0.5 .. e^0.5), same kernel ----------------
+    variants = []
+    if rank == 0 and world == 1:
+        def timed(fn, reps=3):
+            ts = []
+            for _ in range(reps):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream); fn(); b.record(stream)
+                torch.cuda.synchronize(dev)
+                ts.append(a.elapsed_time(b))
+            return float(min(ts))
+        for Ns in (1 << 16, 1 << 18):
+            if Ns >= Nper:
+                continue
+            def launch_ns(Ns=Ns):                   # the first Ns instances of the resident SoA arrays (ld = Nper)
+                _lib.check(L.b200dae_solve_radau(pid, Ns, Nper, d_y0.data_ptr(), d_yp0.data_ptr(), d_p.data_ptr(),
+                                                 WORKLOAD["t_span"][0], WORKLOAD["t_span"][1], atol, ctypes.byref(ro),
+                                                 ctypes.byref(tb), ctypes.byref(out), ctypes.c_void_p(stream.cuda_stream)))
+            launch_ns()
+            ms = timed(launch_ns)
+            variants.append({"instances": Ns, "sigma": WORKLOAD["sigma"], "ms_per_launch": ms, "solves_per_s": Ns / (ms * 1e-3)})
+        p5 = perturbed_params("robertson", Nper, 0.5, seed=0)
+        y5, yp5 = initial_conditions("robertson", p5)
+        d5 = [torch.from_numpy(np.ascontiguousarray(a)).to(dev).t().contiguous() for a in (y5, yp5, p5)]
+
+        def launch_s5():
+            _lib.check(L.b200dae_solve_radau(pid, Nper, Nper, d5[0].data_ptr(), d5[1].data_ptr(), d5[2].data_ptr(),
+                                             WORKLOAD["t_span"][0], WORKLOAD["t_span"][1], atol, ctypes.byref(ro),
+                                             ctypes.byref(tb), ctypes.byref(out), ctypes.c_void_p(stream.cuda_stream)))
+        launch_s5()
+        ms = timed(launch_s5)
+        torch.cuda.synchronize(dev)
+        variants.append({"instances": Nper, "sigma": 0.5, "ms_per_launch": ms, "solves_per_s": Nper / (ms * 1e-3),
+                         "n_unfinished": int((status != 0).sum()),
+                         "accepted_steps_mean": float(counters[4].double().mean()),
+                         "accepted_steps_min_max": [int(counters[4].min()), int(counters[4].max())],
+                         "note": "divergence stress: lanes of a warp integrate systems whose rate constants differ by up to e"})
+        del d5
+        launch()                                    # leave the sigma = 0.1 results in the output buffers
+        torch.cuda.synchronize(dev)
+
     # ---- max over ranks ----------------------------------------------------------------------------------
     t_all = torch.tensor([total_ms, e2e_total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -696,6 +739,7 @@ def main():
             },
             "work_per_solve": {k: float(v) / Nper for k, v in cnt.items()},
             "t_eval_mode": te_mode, "t_eval_modes": te_modes,
+            "ensemble_variants": variants,
             "strong": strong,
             "gather_ms": gather_ms, "gather_first_ms": gather_first_ms,
         }
