@@ -64,6 +64,9 @@ def parse_args():
                     help="instances of the strong-scaling job (BASELINE configs[1]: 1M instances sharded over the GPUs)")
     ap.add_argument("--e2e-no-graph", action="store_true",
                     help="queue the host pipeline eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--e2e-mode", default="zero_copy", choices=["zero_copy", "pipeline"],
+                    help="host-facing call timed as e2e: ONE launch working on the pinned host arrays in place over "
+                         "PCIe (default), or the chunked H2D / kernel / D2H pipeline (also timed, as e2e_pipeline)")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="pipeline chunks of the host-facing call")
     ap.add_argument("--e2e-no-taper", action="store_true", help="equal chunk sizes in the host pipeline")
     ap.add_argument("--e2e-streams", type=int, default=3, help="compute streams of the host pipeline")
@@ -478,15 +481,20 @@ def main():
 
     e2e_graph = not args.e2e_no_graph
 
-    def e2e_step():
+    def e2e_pipeline_step():
         return solve_dae_batched_host("robertson", WORKLOAD["t_span"], h_y0, h_yp0, h_params, method="Radau",
                                       rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], device=dev,
                                       chunks=args.e2e_chunks, n_streams=args.e2e_streams,
                                       taper=not args.e2e_no_taper, out=host_out, use_graph=e2e_graph,
                                       jac="analytic" if args.jac == "analytic" else None)
 
+    def e2e_zero_copy_step():
+        return solve_dae_batched_host("robertson", WORKLOAD["t_span"], h_y0, h_yp0, h_params, method="Radau",
+                                      rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], device=dev, out=host_out,
+                                      zero_copy=True, jac="analytic" if args.jac == "analytic" else None)
+
     try:
-        e2e_step()
+        e2e_pipeline_step()
     except Exception as exc:          # noqa: BLE001 - graph capture is an optimisation, not a requirement
         if not e2e_graph:
             raise
@@ -494,18 +502,25 @@ def main():
               "timing the eagerly queued pipeline instead", file=sys.stderr)
         e2e_graph = False
         torch.cuda.synchronize(dev)
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e2e_ms = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        e2e_step()
-        torch.cuda.synchronize(dev)
-        e2e_ms.append(1e3 * (time.perf_counter() - t0))
-    barrier()
+
+    def time_e2e(step):
+        for _ in range(2):
+            step()
+        barrier()
+        ms = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            step()
+            torch.cuda.synchronize(dev)
+            ms.append(1e3 * (time.perf_counter() - t0))
+        barrier()
+        return ms
+
+    pipe_ms = time_e2e(e2e_pipeline_step)
+    zc_ms = time_e2e(e2e_zero_copy_step)
+    e2e_ms = zc_ms if args.e2e_mode == "zero_copy" else pipe_ms
     e2e_total_ms = float(sum(e2e_ms))
     clocks = sampler.stop() if rank == 0 else None
     h2d = 8 * Nper * (npar + 2 * n)
@@ -620,10 +635,10 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- max over ranks ----------------------------------------------------------------------------------
-    t_all = torch.tensor([total_ms, e2e_total_ms], dtype=torch.float64, device=dev)
+    t_all = torch.tensor([total_ms, e2e_total_ms, float(sum(pipe_ms)), float(sum(zc_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total_ms = float(t_all[0]), float(t_all[1])
+    total_ms, e2e_total_ms, pipe_all_ms, zc_all_ms = (float(x) for x in t_all)
 
     # ---- strong scaling: BASELINE configs[1] literally -- ONE ensemble of --strong-total instances (2^20)
     # sharded over the N GPUs through the product API (distributed.solve_dae_sharded), host inputs to
@@ -643,7 +658,13 @@ def main():
         shared = SharedHostResult(f"b200dae_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}", Nt, n)
         chunks = max(2, args.e2e_chunks // max(1, min(world, 4)))
 
+        strong_zc = args.e2e_mode == "zero_copy"
+
         def strong_step():
+            if strong_zc:       # every rank's launch writes its shard straight into the shared pinned arrays
+                return solve_dae_sharded("robertson", WORKLOAD["t_span"], hs_y0, hs_yp0, hs_p, method="Radau",
+                                         rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], gather="host", host_result=shared,
+                                         device=dev, zero_copy=True, jac="analytic" if args.jac == "analytic" else None)
             return solve_dae_sharded("robertson", WORKLOAD["t_span"], hs_y0, hs_yp0, hs_p, method="Radau",
                                      rtol=WORKLOAD["rtol"], atol=WORKLOAD["atol"], gather="host", host_result=shared,
                                      device=dev, chunks=chunks, n_streams=args.e2e_streams, use_graph=True,
@@ -669,8 +690,11 @@ def main():
                       "value": Nt * len(s_ms) / (sum(s_ms) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(s_ms)),
                       "ms_each": [round(x, 3) for x in s_ms], "all_finished": ok_all,
                       "matches_single_gpu_results": same,
-                      "api": f"distributed.solve_dae_sharded(gather='host', chunks={chunks}, use_graph=True): host inputs -> "
-                             "per-rank host pipeline -> shards DMA-written into shared pinned host arrays -> barrier",
+                      "api": ("distributed.solve_dae_sharded(gather='host', zero_copy=True): every rank's ONE launch reads its "
+                              "block of the pinned host inputs and writes its shard of the shared pinned host result arrays "
+                              "in place over PCIe -> arrival counters" if strong_zc else
+                              f"distributed.solve_dae_sharded(gather='host', chunks={chunks}, use_graph=True): host inputs -> "
+                              "per-rank host pipeline -> shards DMA-written into shared pinned host arrays -> barrier"),
                       "h2d_bytes_per_step": 8 * Nt * (npar + 2 * n), "d2h_bytes_per_step": int(shared.nbytes),
                       "gather": "inside the timed region (no collective)"}
         shared.close()
@@ -717,10 +741,18 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
                     "timer": "host perf_counter bracketed by cuda synchronize",
-                    "api": f"solve_dae_batched_host(chunks={args.e2e_chunks}, n_streams={args.e2e_streams}, "
-                           f"taper={not args.e2e_no_taper}, use_graph={e2e_graph}), "
-                           "pinned host inputs and outputs",
+                    "api": ("solve_dae_batched_host(zero_copy=True): ONE launch that reads the pinned (N, n) host inputs "
+                            "and writes the pinned host results in place over PCIe (io_layout = 1), check_finite on"
+                            if args.e2e_mode == "zero_copy" else
+                            f"solve_dae_batched_host(chunks={args.e2e_chunks}, n_streams={args.e2e_streams}, "
+                            f"taper={not args.e2e_no_taper}, use_graph={e2e_graph}), pinned host inputs and outputs"),
                     "ms_each": [round(x, 3) for x in e2e_ms], "cpu_affinity": affinity},
+            "e2e_pipeline": {"value": Nper * world * args.steps / (pipe_all_ms * 1e-3), "unit": UNIT,
+                             "ms_per_step": pipe_all_ms / args.steps,
+                             "api": f"solve_dae_batched_host(chunks={args.e2e_chunks}, n_streams={args.e2e_streams}, "
+                                    f"taper={not args.e2e_no_taper}, use_graph={e2e_graph}): chunked H2D / relayout / kernel / D2H pipeline"},
+            "e2e_zero_copy": {"value": Nper * world * args.steps / (zc_all_ms * 1e-3), "unit": UNIT,
+                              "ms_per_step": zc_all_ms / args.steps},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": {

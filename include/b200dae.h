@@ -35,7 +35,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define B200DAE_VERSION 105
+#define B200DAE_VERSION 106
 #define B200DAE_MAX_STAGES 7
 #define B200DAE_MAX_ORDER 6
 #define B200DAE_MAX_N 32
@@ -112,7 +112,14 @@ typedef struct b200dae_radau_opts {
     int32_t analytic_jac;            /* 0: jac=None, finite differences (base.py:250-297);
                                         1: the functor's analytic Jacobians = a `jac` callable
                                         (base.py:299-331); compiled for stages = 3 */
-    int32_t reserved;
+    int32_t io_layout;               /* 0: y0 / yp0 [n][ld], params [p][ld], y_final / yp_final [n][ld],
+                                        counters [8][ld] (instance index innermost);
+                                        1: instance-major, the reference's own array shapes: y0 / yp0 /
+                                        y_final / yp_final [ld][n], params [ld][p], counters [ld][8].
+                                        With 1 the pointers may be page-locked HOST arrays (cudaHostAlloc /
+                                        cudaHostRegister, see b200dae_host_device_pointer): the launch then
+                                        reads its inputs and writes its results over PCIe in place, no
+                                        staging copies.  t_final, status, t_eval rows and traces are unaffected */
 } b200dae_radau_opts;
 
 /* keyword arguments of BDFDAE.__init__ (bdf.py:224-227) */
@@ -124,7 +131,7 @@ typedef struct b200dae_bdf_opts {
     int32_t ndf_strategy;            /* 0 "stability", 1 "efficiency", 2 plain BDF (bdf.py:242-247) */
     int64_t max_steps;
     int32_t analytic_jac;            /* as in b200dae_radau_opts */
-    int32_t reserved;
+    int32_t io_layout;               /* as in b200dae_radau_opts */
 } b200dae_bdf_opts;
 
 /* Events of solve_dae (dae.py:30-109, 426-490).  A Python event callable cannot run inside the
@@ -291,6 +298,10 @@ int b200dae_consistent_ic(int problem_id, int64_t N, int64_t ld, double t0,
                           const int32_t *fixed_y, const int32_t *fixed_yp,
                           const b200dae_cic_opts *opts,
                           double *f_out, int32_t *status, int32_t *n_iter, void *stream);
+
+/* Device address of a page-locked host allocation (cudaHostGetDevicePointer), for io_layout = 1 launches
+ * that work on host arrays in place.  On x86-64 Linux it equals the host address. */
+int b200dae_host_device_pointer(void *host_ptr, void **device_ptr);
 
 /* Number of kernels launched by this library since load (bench.py's "gpu_launches" claim). */
 int64_t b200dae_launch_count(void);

@@ -1,5 +1,5 @@
 """Freeze the reference's Radau IIA tables (radau_constants, radau.py:51-134) for s = 1, 3, 5, 7
-into tests/golden/radau_constants_ref.npz — TEST INFRASTRUCTURE, run in the build container where
+into tests/golden/constants/radau_constants_ref.npz — TEST INFRASTRUCTURE, run in the build container where
 the unmodified reference is importable:
 
     python oracle/gen_golden_constants.py
@@ -26,7 +26,7 @@ def main():
     for s in (1, 3, 5, 7):
         for name, val in zip(NAMES, radau_constants(s)):
             out[f"s{s}_{name}"] = np.asarray(val)
-    path = os.path.join(REPO, "tests", "golden", "radau_constants_ref.npz")
+    path = os.path.join(REPO, "tests", "golden", "constants", "radau_constants_ref.npz")
     np.savez(path, **out)
     print(path, len(out), "arrays")
 

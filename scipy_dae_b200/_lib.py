@@ -22,7 +22,7 @@ EXPORTS = ("b200dae_version", "b200dae_last_error", "b200dae_num_problems",
            "b200dae_problem_lookup", "b200dae_problem_name", "b200dae_residual",
            "b200dae_solve_radau", "b200dae_solve_bdf", "b200dae_launch_count",
            "b200dae_fp64_peak_kernel", "b200dae_selftest_fastmath", "b200dae_consistent_ic",
-           "b200dae_problem_num_events", "b200dae_register_problem", "b200dae_precompile")
+           "b200dae_problem_num_events", "b200dae_register_problem", "b200dae_precompile", "b200dae_host_device_pointer")
 
 
 class B200DaeLibraryError(ImportError):
@@ -40,14 +40,14 @@ class RadauOpts(ctypes.Structure):
                 ("deadband_lo", ctypes.c_double), ("deadband_hi", ctypes.c_double),
                 ("newton_max_iter", ctypes.c_int32), ("newton_iter_embedded", ctypes.c_int32),
                 ("max_steps", ctypes.c_int64), ("analytic_jac", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("io_layout", ctypes.c_int32)]
 
 
 class BdfOpts(ctypes.Structure):
     _fields_ = [("rtol", ctypes.c_double), ("max_step", ctypes.c_double),
                 ("first_step", ctypes.c_double), ("max_order", ctypes.c_int32),
                 ("ndf_strategy", ctypes.c_int32), ("max_steps", ctypes.c_int64),
-                ("analytic_jac", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("analytic_jac", ctypes.c_int32), ("io_layout", ctypes.c_int32)]
 
 
 class CicOpts(ctypes.Structure):
@@ -119,6 +119,8 @@ def load():
     L.b200dae_launch_count.restype = i64
     L.b200dae_register_problem.restype = ctypes.c_int
     L.b200dae_register_problem.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32]
+    L.b200dae_host_device_pointer.restype = ctypes.c_int
+    L.b200dae_host_device_pointer.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
     L.b200dae_precompile.restype = ctypes.c_int
     L.b200dae_precompile.argtypes = [ctypes.c_int] + [ctypes.c_int32] * 4
     L.b200dae_residual.restype = ctypes.c_int
@@ -137,8 +139,8 @@ def load():
     L.b200dae_fp64_peak_kernel.argtypes = [ctypes.c_int, ctypes.c_int, i64, vp, vp]
     L.b200dae_selftest_fastmath.restype = ctypes.c_int
     L.b200dae_selftest_fastmath.argtypes = [i64, vp, vp, vp, vp]
-    if L.b200dae_version() != 105:
-        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 105")
+    if L.b200dae_version() != 106:
+        raise B200DaeLibraryError(f"{LIB_PATH}: ABI version {L.b200dae_version()} != 106")
     _lib = L
     return L
 

@@ -221,6 +221,13 @@ def _warn_extraneous(extraneous):
                       f"{', '.join(f'`{x}`' for x in extraneous)}.", stacklevel=3)
 
 
+def _host_device_ptr(L, t):
+    """Device address of a page-locked host tensor (cudaHostGetDevicePointer through the C-ABI)."""
+    dp = ctypes.c_void_p()
+    _lib.check(L.b200dae_host_device_pointer(ctypes.c_void_p(t.data_ptr()), ctypes.byref(dp)))
+    return dp.value
+
+
 def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="Radau",
                       t_eval=None, rtol=1e-3, atol=1e-6, *, device=None, stream=None,
                       record_steps: int = 0, record_dense: bool = False, max_steps: int = 0,
@@ -253,6 +260,7 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
     """
     if eval_layout not in ("instance", "soa"):
         raise ValueError("eval_layout must be 'instance' or 'soa'")
+    host_io = options.pop("_host_io", None)      # host_pipeline.py: zero-copy launch on pinned host arrays
     L = _lib.load()
     prob = get_problem(problem)
     pid, n, npar = _lib.problem_lookup(prob.name)
@@ -299,22 +307,37 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
     else:
         stream_ctx = contextlib.nullcontext()
     with torch.cuda.device(device), stream_ctx:
-        y0_d = _as_device_soa(y0, N, n, "y0", device, check_finite)
-        yp0_d = _as_device_soa(yp0, N, n, "yp0", device, check_finite)
-        p_d = _as_device_soa(params, N, npar, "params", device, False) if npar > 0 else None
         ld = N
-
-        # ---- outputs -----------------------------------------------------------------------
         f64 = dict(dtype=torch.float64, device=device)
         i32 = dict(dtype=torch.int32, device=device)
-        y_final = torch.empty((n, ld), **f64)
-        yp_final = torch.empty((n, ld), **f64)
-        t_final = torch.empty((ld,), **f64)
-        status = torch.empty((ld,), **i32)
-        counters = torch.empty((_lib.NUM_COUNTERS, ld), **i32)
         out = _lib.Outputs()
-        out.y_final, out.yp_final, out.t_final = y_final.data_ptr(), yp_final.data_ptr(), t_final.data_ptr()
-        out.status, out.counters = status.data_ptr(), counters.data_ptr()
+        if host_io is None:
+            y0_d = _as_device_soa(y0, N, n, "y0", device, check_finite)
+            yp0_d = _as_device_soa(yp0, N, n, "yp0", device, check_finite)
+            p_d = _as_device_soa(params, N, npar, "params", device, False) if npar > 0 else None
+            y0_ptr, yp0_ptr = y0_d.data_ptr(), yp0_d.data_ptr()
+            p_ptr = p_d.data_ptr() if p_d is not None else None
+            # ---- outputs -------------------------------------------------------------------
+            y_final = torch.empty((n, ld), **f64)
+            yp_final = torch.empty((n, ld), **f64)
+            t_final = torch.empty((ld,), **f64)
+            status = torch.empty((ld,), **i32)
+            counters = torch.empty((_lib.NUM_COUNTERS, ld), **i32)
+            out.y_final, out.yp_final, out.t_final = y_final.data_ptr(), yp_final.data_ptr(), t_final.data_ptr()
+            out.status, out.counters = status.data_ptr(), counters.data_ptr()
+        else:
+            # in place on page-locked HOST arrays of the reference's own shapes (io_layout = 1): the
+            # launch reads (N, n) / (N, p) inputs and writes (N, n) / (N, 8) results over PCIe
+            if t_eval is not None or record_steps or events:
+                raise NotImplementedError("t_eval / record_steps / events are not available in place on host arrays")
+            hb = host_io["out"]
+            y0_d, yp0_d, p_d = host_io["y0"], host_io["yp0"], host_io["params"]
+            y0_ptr, yp0_ptr = _host_device_ptr(L, y0_d), _host_device_ptr(L, yp0_d)
+            p_ptr = _host_device_ptr(L, p_d) if npar > 0 else None
+            y_final, yp_final, t_final, status, counters = hb.y_final, hb.yp_final, hb.t_final, hb.status, hb.counters
+            out.y_final, out.yp_final = _host_device_ptr(L, y_final), _host_device_ptr(L, yp_final)
+            out.t_final, out.status = _host_device_ptr(L, t_final), _host_device_ptr(L, status)
+            out.counters = _host_device_ptr(L, counters)
         te_d = y_eval = yp_eval = n_eval_valid = None
         if t_eval is not None:
             te = _validate_t_eval(t_eval, t0, t_bound)
@@ -394,7 +417,7 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
                 raise ValueError("`first_step` exceeds bounds.")
         cu_stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         atol_p = atol_v.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-        p_ptr = p_d.data_ptr() if p_d is not None else None
+        io_layout = 0 if host_io is None else 1
         if method == "Radau":
             stages = int(opts.pop("stages", 3))
             if stages % 2 != 1:
@@ -412,10 +435,10 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
                 deadband_lo=float(db[0]), deadband_hi=float(db[1]),
                 newton_max_iter=int(nmi) if nmi is not None else 0,
                 newton_iter_embedded=int(opts.pop("newton_iter_embedded", 1)),
-                max_steps=int(max_steps), analytic_jac=analytic_jac)
+                max_steps=int(max_steps), analytic_jac=analytic_jac, io_layout=io_layout)
             _warn_extraneous(opts)
             tb = radau_tables_c(stages)
-            rc = L.b200dae_solve_radau(pid, N, ld, y0_d.data_ptr(), yp0_d.data_ptr(), p_ptr,
+            rc = L.b200dae_solve_radau(pid, N, ld, y0_ptr, yp0_ptr, p_ptr,
                                        t0, t_bound, atol_p, ctypes.byref(ro), ctypes.byref(tb),
                                        ctypes.byref(out), cu_stream)
         else:
@@ -423,17 +446,24 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
             bo = _lib.BdfOpts(rtol=rtol, max_step=max_step, first_step=first_step or 0.0,
                               max_order=int(opts.pop("max_order", 5)),
                               ndf_strategy=NDF_STRATEGIES.get(ndf, 2), max_steps=int(max_steps),
-                              analytic_jac=analytic_jac)
+                              analytic_jac=analytic_jac, io_layout=io_layout)
             if bo.max_order == 6:
                 warnings.warn("Choosing `max_order = 6` is not recomended due to its poor "
                               "stability properties.", stacklevel=2)
             _warn_extraneous(opts)
-            rc = L.b200dae_solve_bdf(pid, N, ld, y0_d.data_ptr(), yp0_d.data_ptr(), p_ptr,
+            rc = L.b200dae_solve_bdf(pid, N, ld, y0_ptr, yp0_ptr, p_ptr,
                                      t0, t_bound, atol_p, ctypes.byref(bo), ctypes.byref(out),
                                      cu_stream)
         _lib.check(rc)
         if ev_struct is not None:  # device code 2 -> solve_dae's status 1 ("A termination event occurred.")
             status = torch.where(status == _lib.ST_EVENT, torch.ones_like(status), status)
+    if host_io is not None:
+        cn = counters
+        return BatchedDaeResult(
+            t_final=t_final, y_final=y_final, yp_final=yp_final, status=status,
+            nfev=cn[:, 0], njev=cn[:, 1], nlu=cn[:, 2], nsolve=cn[:, 3], n_accepted=cn[:, 4],
+            n_err_rejected=cn[:, 5], n_newton_fail=cn[:, 6], n_newton_iter=cn[:, 7],
+            method=method, problem=prob.name, extra={"_keepalive": (y0_d, yp0_d, p_d)})
     res = BatchedDaeResult(
         t_final=t_final, y_final=y_final.t(), yp_final=yp_final.t(), status=status,
         nfev=counters[0], njev=counters[1], nlu=counters[2], nsolve=counters[3],

@@ -201,6 +201,16 @@ const char* b200dae_problem_name(int problem_id) {
 
 int64_t b200dae_launch_count(void) { return g_launches.load(); }
 
+int b200dae_host_device_pointer(void* host_ptr, void** device_ptr) {
+    if (!host_ptr || !device_ptr) return fail(B200DAE_EINVAL, "host_device_pointer needs two pointers%s", "");
+    const cudaError_t rc = cudaHostGetDevicePointer(device_ptr, host_ptr, 0);
+    if (rc != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(B200DAE_ECUDA, "CUDA: %s (is the host allocation page-locked?)", cudaGetErrorString(rc));
+    }
+    return 0;
+}
+
 int b200dae_register_problem(const char* name, const char* cuda_src, int32_t n, int32_t n_params) {
     if (!name || !*name || !cuda_src) return fail(B200DAE_EINVAL, "register_problem needs a name and a source%s", "");
     for (const char* c = name; *c; ++c)
@@ -283,6 +293,7 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
     if (!(opts->deadband_lo > 0 && opts->deadband_lo <= opts->deadband_hi))
         return fail(B200DAE_EINVAL, "need 0 < controller_deadband[0] <= controller_deadband[1]%s", "");
     if (opts->newton_iter_embedded < 0) return fail(B200DAE_EINVAL, "need newton_iter_embedded >= 0%s", "");
+    if (opts->io_layout != 0 && opts->io_layout != 1) return fail(B200DAE_EINVAL, "io_layout must be 0 or 1%s", "");
     // the kernels evaluate rate ** (newton_max_iter - k) (radau.py:186) with a 5-bit square-and-multiply
     if (opts->newton_max_iter > 32) return fail(B200DAE_EINVAL, "need newton_max_iter <= 32%s (got %lld)", "", (long long)opts->newton_max_iter);
     // The thread-per-system kernel relies on the normalisation of the reference's eigen-transformation
@@ -320,6 +331,7 @@ int b200dae_solve_radau(int problem_id, int64_t N, int64_t ld, const double* y0,
     L.newton_iter_embedded = opts->newton_iter_embedded;
     L.max_steps = opts->max_steps;
     L.analytic_jac = opts->analytic_jac;
+    L.io_aos = opts->io_layout == 1;
     L.N = N;
     L.ld = ld;
     L.y0 = y0;
@@ -351,6 +363,7 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
         return fail(B200DAE_EINVAL, "Ensure that 1 <= max_order <= 6.%s", "");
     if (!(opts->max_step > 0)) return fail(B200DAE_EINVAL, "`max_step` must be positive.%s", "");
     if (opts->first_step > fabs(t_bound - t0)) return fail(B200DAE_EINVAL, "`first_step` exceeds bounds.%s", "");
+    if (opts->io_layout != 0 && opts->io_layout != 1) return fail(B200DAE_EINVAL, "io_layout must be 0 or 1%s", "");
     if (out->dense_coef && (out->coef_rows != (int64_t)e->n * kBdfQ || !out->order_steps))
         return fail(B200DAE_EINVAL, "BDF dense_coef needs order_steps and coef_rows = 7 * n%s (got %lld)", "", (long long)out->coef_rows);
     if (N == 0) return 0;
@@ -382,6 +395,7 @@ int b200dae_solve_bdf(int problem_id, int64_t N, int64_t ld, const double* y0, c
     L.max_order = opts->max_order;
     L.max_steps = opts->max_steps;
     L.analytic_jac = opts->analytic_jac;
+    L.io_aos = opts->io_layout == 1;
     L.N = N;
     L.ld = ld;
     L.y0 = y0;

@@ -36,6 +36,7 @@ struct BdfLaunch {
     const double *y0, *yp0, *params;
     b200dae_outputs out;
     EventLaunch ev;             // ev.spec.n_events == 0: no events
+    int32_t io_aos;             // instance-major main inputs / outputs, see RadauLaunch
 };
 
 // norm ** (-1 / k) of the step-size / order controller (bdf.py:353,398-404), one shared copy of
@@ -154,9 +155,9 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
 
     double p[NP > 0 ? NP : 1], y[N], yp[N];
 #pragma unroll U
-    for (int j = 0; j < NP; ++j) p[j] = L.params[j * ld + inst];
+    for (int j = 0; j < NP; ++j) p[j] = L.params[io_index(L.io_aos, ld, NP, j, inst)];
 #pragma unroll U
-    for (int j = 0; j < N; ++j) { y[j] = L.y0[j * ld + inst]; yp[j] = L.yp0[j * ld + inst]; }
+    for (int j = 0; j < N; ++j) { y[j] = L.y0[io_index(L.io_aos, ld, N, j, inst)]; yp[j] = L.yp0[io_index(L.io_aos, ld, N, j, inst)]; }
 
     constexpr int kCold = 2 * N * N + 2 * N;
     constexpr bool kDynCold = kSharedCold && ((size_t)kCold * kThreads * sizeof(double) > 48 * 1024);
@@ -516,8 +517,8 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
 
 #pragma unroll U
     for (int j = 0; j < N; ++j) {
-        L.out.y_final[j * ld + inst] = y[j];
-        if (L.out.yp_final) L.out.yp_final[j * ld + inst] = yp[j];
+        L.out.y_final[io_index(L.io_aos, ld, N, j, inst)] = y[j];
+        if (L.out.yp_final) L.out.yp_final[io_index(L.io_aos, ld, N, j, inst)] = yp[j];
     }
     L.out.t_final[inst] = t;
     L.out.status[inst] = status;
@@ -525,15 +526,16 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
     if (L.out.n_steps) L.out.n_steps[inst] = nst;
     if (!kLean) for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
     if (L.out.counters) {
-        int32_t* cn = L.out.counters + inst;
-        cn[B200DAE_CNT_NFEV * ld] = nfev;
-        cn[B200DAE_CNT_NJEV * ld] = njev;
-        cn[B200DAE_CNT_NLU * ld] = nlu;
-        cn[B200DAE_CNT_NSOLVE * ld] = nsolve;
-        cn[B200DAE_CNT_ACCEPTED * ld] = nacc;
-        cn[B200DAE_CNT_ERR_REJECTED * ld] = nrej;
-        cn[B200DAE_CNT_NEWTON_FAIL * ld] = nfail;
-        cn[B200DAE_CNT_NEWTON_ITER * ld] = niter;
+        int32_t* cn = L.out.counters + (L.io_aos ? inst * 8 : inst);
+            const int64_t cs_ = L.io_aos ? 1 : ld;
+        cn[B200DAE_CNT_NFEV * cs_] = nfev;
+        cn[B200DAE_CNT_NJEV * cs_] = njev;
+        cn[B200DAE_CNT_NLU * cs_] = nlu;
+        cn[B200DAE_CNT_NSOLVE * cs_] = nsolve;
+        cn[B200DAE_CNT_ACCEPTED * cs_] = nacc;
+        cn[B200DAE_CNT_ERR_REJECTED * cs_] = nrej;
+        cn[B200DAE_CNT_NEWTON_FAIL * cs_] = nfail;
+        cn[B200DAE_CNT_NEWTON_ITER * cs_] = niter;
     }
 }
 

@@ -104,11 +104,11 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     int* sIdx = reinterpret_cast<int*>(sm + Lay::oIdx);
 
     double* p = sm + Lay::oPar;
-    for (int j = lane; j < NP; j += G) p[j] = L.params[j * ld + inst];
+    for (int j = lane; j < NP; j += G) p[j] = L.params[io_index(L.io_aos, ld, NP, j, inst)];
     g.sync();
     const int jc = act ? lane : 0;
-    double y = act ? L.y0[jc * ld + inst] : 0.0;
-    double yp = act ? L.yp0[jc * ld + inst] : 0.0;
+    double y = act ? L.y0[io_index(L.io_aos, ld, N, jc, inst)] : 0.0;
+    double yp = act ? L.yp0[io_index(L.io_aos, ld, N, jc, inst)] : 0.0;
     const double atol_j = L.atol[jc], thr_j = L.thr[jc];
     double fac_y = kNjInitFactor, fac_yp = kNjInitFactor;
 
@@ -483,8 +483,8 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
     }
 
     if (act) {
-        L.out.y_final[lane * ld + inst] = y;
-        if (L.out.yp_final) L.out.yp_final[lane * ld + inst] = yp;
+        L.out.y_final[io_index(L.io_aos, ld, N, lane, inst)] = y;
+        if (L.out.yp_final) L.out.yp_final[io_index(L.io_aos, ld, N, lane, inst)] = yp;
     }
     if (lane == 0) {
         L.out.t_final[inst] = t;
@@ -493,15 +493,16 @@ bdf_group_kernel(const __grid_constant__ BdfLaunch L) {
         if (L.out.n_steps) L.out.n_steps[inst] = nst;
         if (kEv) for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
         if (L.out.counters) {
-            int32_t* cn = L.out.counters + inst;
-            cn[B200DAE_CNT_NFEV * ld] = nfev;
-            cn[B200DAE_CNT_NJEV * ld] = njev;
-            cn[B200DAE_CNT_NLU * ld] = nlu;
-            cn[B200DAE_CNT_NSOLVE * ld] = nsolve;
-            cn[B200DAE_CNT_ACCEPTED * ld] = nacc;
-            cn[B200DAE_CNT_ERR_REJECTED * ld] = nrej;
-            cn[B200DAE_CNT_NEWTON_FAIL * ld] = nfail;
-            cn[B200DAE_CNT_NEWTON_ITER * ld] = niter;
+            int32_t* cn = L.out.counters + (L.io_aos ? inst * 8 : inst);
+            const int64_t cs_ = L.io_aos ? 1 : ld;
+            cn[B200DAE_CNT_NFEV * cs_] = nfev;
+            cn[B200DAE_CNT_NJEV * cs_] = njev;
+            cn[B200DAE_CNT_NLU * cs_] = nlu;
+            cn[B200DAE_CNT_NSOLVE * cs_] = nsolve;
+            cn[B200DAE_CNT_ACCEPTED * cs_] = nacc;
+            cn[B200DAE_CNT_ERR_REJECTED * cs_] = nrej;
+            cn[B200DAE_CNT_NEWTON_FAIL * cs_] = nfail;
+            cn[B200DAE_CNT_NEWTON_ITER * cs_] = niter;
         }
     }
 }

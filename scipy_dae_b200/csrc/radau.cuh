@@ -42,7 +42,15 @@ struct RadauLaunch {
     b200dae_outputs out;
     EventLaunch ev;             // ev.spec.n_events == 0: no events
     double* jscratch;           // group kernels with the Jacobians in global memory (RadauGroupLayout: kGJ): N blocks, else NULL
+    int32_t io_aos;             // 1: y0 / yp0 / params / y_final / yp_final / counters are instance-major ([ld][n], [ld][p], [ld][8])
 };
+
+// Index of (component j of instance i) in the main input / output arrays: [n][ld] (default) or, with
+// io_aos, [ld][n] -- the layout of the reference's own arrays, which lets a launch read and write
+// pinned HOST arrays of shape (N, n) in place (host_pipeline.py: zero_copy).  Prologue / epilogue only.
+__device__ __forceinline__ int64_t io_index(int aos, int64_t ld, int width, int j, int64_t inst) {
+    return aos ? inst * width + j : (int64_t)j * ld + inst;
+}
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
@@ -129,9 +137,9 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     // ---- per-instance state -------------------------------------------------------------
     double p[NP > 0 ? NP : 1], y[N], yp[N];
 #pragma unroll U
-    for (int j = 0; j < NP; ++j) p[j] = L.params[j * ld + inst];
+    for (int j = 0; j < NP; ++j) p[j] = L.params[io_index(L.io_aos, ld, NP, j, inst)];
 #pragma unroll U
-    for (int j = 0; j < N; ++j) { y[j] = L.y0[j * ld + inst]; yp[j] = L.yp0[j * ld + inst]; }
+    for (int j = 0; j < N; ++j) { y[j] = L.y0[io_index(L.io_aos, ld, N, j, inst)]; yp[j] = L.yp0[io_index(L.io_aos, ld, N, j, inst)]; }
 
     // "Cold" per-instance state (touched once per step or per LU, not per Newton iteration):
     // Jacobians, FD step factors, dense-output coefficients, complex LU factors.  With
@@ -745,8 +753,8 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     // ---- results ----------------------------------------------------------------------------
 #pragma unroll U
     for (int j = 0; j < N; ++j) {
-        L.out.y_final[j * ld + inst] = y[j];
-        if (L.out.yp_final) L.out.yp_final[j * ld + inst] = yp[j];
+        L.out.y_final[io_index(L.io_aos, ld, N, j, inst)] = y[j];
+        if (L.out.yp_final) L.out.yp_final[io_index(L.io_aos, ld, N, j, inst)] = yp[j];
     }
     L.out.t_final[inst] = t;
     L.out.status[inst] = status;
@@ -756,15 +764,16 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
         for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
     }
     if (L.out.counters) {
-        int32_t* c = L.out.counters + inst;
-        c[B200DAE_CNT_NFEV * ld] = nfev;
-        c[B200DAE_CNT_NJEV * ld] = njev;
-        c[B200DAE_CNT_NLU * ld] = nlu;
-        c[B200DAE_CNT_NSOLVE * ld] = nsolve;
-        c[B200DAE_CNT_ACCEPTED * ld] = nacc;
-        c[B200DAE_CNT_ERR_REJECTED * ld] = nrej;
-        c[B200DAE_CNT_NEWTON_FAIL * ld] = nfail;
-        c[B200DAE_CNT_NEWTON_ITER * ld] = niter;
+        int32_t* c = L.out.counters + (L.io_aos ? inst * 8 : inst);
+        const int64_t cs = L.io_aos ? 1 : ld;
+        c[B200DAE_CNT_NFEV * cs] = nfev;
+        c[B200DAE_CNT_NJEV * cs] = njev;
+        c[B200DAE_CNT_NLU * cs] = nlu;
+        c[B200DAE_CNT_NSOLVE * cs] = nsolve;
+        c[B200DAE_CNT_ACCEPTED * cs] = nacc;
+        c[B200DAE_CNT_ERR_REJECTED * cs] = nrej;
+        c[B200DAE_CNT_NEWTON_FAIL * cs] = nfail;
+        c[B200DAE_CNT_NEWTON_ITER * cs] = niter;
     }
 }
 

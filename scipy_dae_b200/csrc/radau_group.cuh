@@ -220,11 +220,11 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
 
     // ---- per-instance state: scalars replicated in every lane, vectors one component per lane --
     double* p = sm + Lay::oPar;                            // per-instance parameters, shared by the group
-    for (int j = lane; j < NP; j += G) p[j] = L.params[j * ld + inst];
+    for (int j = lane; j < NP; j += G) p[j] = L.params[io_index(L.io_aos, ld, NP, j, inst)];
     g.sync();
     const int jc = act ? lane : 0;                        // clamped component index for loads
-    double y = act ? L.y0[jc * ld + inst] : 0.0;
-    double yp = act ? L.yp0[jc * ld + inst] : 0.0;
+    double y = act ? L.y0[io_index(L.io_aos, ld, N, jc, inst)] : 0.0;
+    double yp = act ? L.yp0[io_index(L.io_aos, ld, N, jc, inst)] : 0.0;
     const double atol_j = L.atol[jc], thr_j = L.thr[jc];
     double fac_y = kNjInitFactor, fac_yp = kNjInitFactor;
 
@@ -701,8 +701,8 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
 
     // ---- results ----------------------------------------------------------------------------
     if (act) {
-        L.out.y_final[lane * ld + inst] = y;
-        if (L.out.yp_final) L.out.yp_final[lane * ld + inst] = yp;
+        L.out.y_final[io_index(L.io_aos, ld, N, lane, inst)] = y;
+        if (L.out.yp_final) L.out.yp_final[io_index(L.io_aos, ld, N, lane, inst)] = yp;
     }
     if (lane == 0) {
         L.out.t_final[inst] = t;
@@ -711,15 +711,16 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
         if (L.out.n_steps) L.out.n_steps[inst] = nst;
         if (!kLean) for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];
         if (L.out.counters) {
-            int32_t* c = L.out.counters + inst;
-            c[B200DAE_CNT_NFEV * ld] = nfev;
-            c[B200DAE_CNT_NJEV * ld] = njev;
-            c[B200DAE_CNT_NLU * ld] = nlu;
-            c[B200DAE_CNT_NSOLVE * ld] = nsolve;
-            c[B200DAE_CNT_ACCEPTED * ld] = nacc;
-            c[B200DAE_CNT_ERR_REJECTED * ld] = nrej;
-            c[B200DAE_CNT_NEWTON_FAIL * ld] = nfail;
-            c[B200DAE_CNT_NEWTON_ITER * ld] = niter;
+            int32_t* c = L.out.counters + (L.io_aos ? inst * 8 : inst);
+            const int64_t cs_ = L.io_aos ? 1 : ld;
+            c[B200DAE_CNT_NFEV * cs_] = nfev;
+            c[B200DAE_CNT_NJEV * cs_] = njev;
+            c[B200DAE_CNT_NLU * cs_] = nlu;
+            c[B200DAE_CNT_NSOLVE * cs_] = nsolve;
+            c[B200DAE_CNT_ACCEPTED * cs_] = nacc;
+            c[B200DAE_CNT_ERR_REJECTED * cs_] = nrej;
+            c[B200DAE_CNT_NEWTON_FAIL * cs_] = nfail;
+            c[B200DAE_CNT_NEWTON_ITER * cs_] = niter;
         }
     }
 }

@@ -30,7 +30,7 @@ def test_registry_without_gpu():
     from scipy_dae_b200 import _lib
     from scipy_dae_b200.problems import PROBLEMS
     L = _lib.load()
-    assert L.b200dae_version() == 105
+    assert L.b200dae_version() == 106
     assert L.b200dae_num_problems() == len(PROBLEMS)
     for name, pr in PROBLEMS.items():
         pid, n, npar = _lib.problem_lookup(name)

@@ -3,7 +3,7 @@
 The reference's tables carry ~1e-14 of eigen-solver noise that the step sequences are sensitive to
 (SURVEY.md App. E), so `scipy_dae_b200.constants.radau_tables` derives them with the same
 NumPy / SciPy primitives.  Pinned here against values frozen from the unmodified reference
-(oracle/gen_golden_constants.py -> tests/golden/radau_constants_ref.npz): bit for bit where this
+(oracle/gen_golden_constants.py -> tests/golden/constants/radau_constants_ref.npz): bit for bit where this
 machine's LAPACK reproduces the frozen eigen-decomposition (the build container and the GPU box share
 one image), to 1e-13 otherwise; and bit for bit against the LIVE reference wherever it is importable."""
 import os
@@ -20,7 +20,7 @@ FIELDS = {"A": "A", "c": "c", "T": "T", "TI": "TI", "P": "P", "P2": "P2", "b_hat
 @pytest.mark.parametrize("s", [1, 3, 5, 7])
 def test_radau_tables_match_the_frozen_reference_tables(s):
     from scipy_dae_b200.constants import radau_tables
-    ref = np.load(os.path.join(HERE, "golden", "radau_constants_ref.npz"))
+    ref = np.load(os.path.join(HERE, "golden", "constants", "radau_constants_ref.npz"))
     tb = radau_tables(s)
     exact = True
     for rname, ours in FIELDS.items():

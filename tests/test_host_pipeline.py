@@ -37,3 +37,47 @@ def test_radau_tables_have_the_normalisation_the_kernel_relies_on():
         T, TI = np.asarray(tb.T).reshape(s, s), np.asarray(tb.TI).reshape(s, s)
         assert np.array_equal(T[-1], np.array([1.0 if l % 2 == 0 else 0.0 for l in range(s)]))
         assert (TI[0] != 0.0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem,method,N,sigma,tol", [
+    ("robertson", "Radau", 5000, 0.1, 1e-6),      # radau_kernel (headline)
+    ("robertson", "BDF", 1500, 0.1, 1e-6),        # bdf_kernel
+    ("akzo_nobel", "BDF", 300, 0.05, 1e-8),       # unrolled thread regime
+    ("transamp", "Radau", 70, 0.02, 1e-8),        # radau_group_kernel
+    ("transamp", "BDF", 70, 0.02, 1e-8),          # bdf_group_kernel
+])
+def test_zero_copy_launch_is_bit_identical_to_the_device_path(problem, method, N, sigma, tol):
+    """io_layout = 1 (include/b200dae.h): ONE launch reads the pinned (N, n) / (N, p) host arrays and
+    writes the pinned result buffers in place.  Same kernels, same arithmetic: every output must equal
+    the device-resident solve bit for bit."""
+    import torch
+    from scipy_dae_b200 import (solve_dae_batched, solve_dae_batched_host, alloc_host_result, perturbed_params,
+                                initial_conditions, get_problem)
+    pr = get_problem(problem)
+    params = perturbed_params(problem, N, sigma, seed=11)
+    y0, yp0 = initial_conditions(problem, params)
+    hp, hy, hyp = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (params, y0, yp0))
+    out = alloc_host_result(N, pr.n)
+    r = solve_dae_batched_host(problem, pr.t_span, hy, hyp, hp, method=method, rtol=tol, atol=tol, out=out, zero_copy=True)
+    ref = solve_dae_batched(problem, pr.t_span, y0, yp0, params, method=method, rtol=tol, atol=tol)
+    torch.cuda.synchronize()
+    ref = ref.numpy()
+    assert r.extra["zero_copy"] and (ref.status == 0).all()
+    assert np.array_equal(r.status.numpy(), ref.status) and np.array_equal(r.t_final.numpy(), ref.t_final)
+    assert np.array_equal(r.y_final.numpy(), ref.y_final) and np.array_equal(r.yp_final.numpy(), ref.yp_final)
+    for key in ("nfev", "njev", "nlu", "nsolve", "n_accepted", "n_err_rejected", "n_newton_fail", "n_newton_iter"):
+        assert np.array_equal(getattr(r, key).numpy(), getattr(ref, key)), key
+
+
+@pytest.mark.gpu
+def test_zero_copy_reports_non_finite_initial_values_like_the_reference():
+    import torch
+    from scipy_dae_b200 import solve_dae_batched_host, alloc_host_result, perturbed_params, initial_conditions
+    params = perturbed_params("robertson", 64, 0.1, seed=0)
+    y0, yp0 = initial_conditions("robertson", params)
+    y0[17, 1] = np.nan
+    hp, hy, hyp = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (params, y0, yp0))
+    with pytest.raises(ValueError, match="must be finite"):          # base.py:33-37
+        solve_dae_batched_host("robertson", (0.0, 1e3), hy, hyp, hp, rtol=1e-6, atol=1e-6,
+                               out=alloc_host_result(64, 3), zero_copy=True)
