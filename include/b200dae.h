@@ -214,6 +214,11 @@ typedef struct b200dae_outputs {
     int64_t coef_rows;
     const b200dae_events *events;   /* HOST pointer, NULL = no events */
     int64_t eval_stride_row, eval_stride_comp, eval_stride_inst;   /* layout of y_eval / yp_eval, see above */
+    int32_t *bad_input;             /* optional, ONE int (device or page-locked host): set to 1 by the lean Radau
+                                       kernel in io_layout = 1 launches when an instance stops with NONFINITE before
+                                       its first accepted step (non-finite y0 / yp0 / parameters: what the reference
+                                       rejects in check_arguments, base.py:33-37); the host then looks at that one
+                                       word instead of scanning status[] */
 } b200dae_outputs;
 
 int b200dae_version(void);

@@ -68,7 +68,7 @@ class Outputs(ctypes.Structure):
                 ("dense_coef", ctypes.c_void_p), ("coef_rows", ctypes.c_int64),
                 ("events", ctypes.c_void_p),
                 ("eval_stride_row", ctypes.c_int64), ("eval_stride_comp", ctypes.c_int64),
-                ("eval_stride_inst", ctypes.c_int64)]
+                ("eval_stride_inst", ctypes.c_int64), ("bad_input", ctypes.c_void_p)]
 
 
 MAX_EVENTS = 4

@@ -338,6 +338,8 @@ def solve_dae_batched(problem, t_span, y0=None, yp0=None, params=None, method="R
             out.y_final, out.yp_final = _host_device_ptr(L, y_final), _host_device_ptr(L, yp_final)
             out.t_final, out.status = _host_device_ptr(L, t_final), _host_device_ptr(L, status)
             out.counters = _host_device_ptr(L, counters)
+            if host_io.get("flag") is not None:
+                out.bad_input = _host_device_ptr(L, host_io["flag"])
         te_d = y_eval = yp_eval = n_eval_valid = None
         if t_eval is not None:
             te = _validate_t_eval(t_eval, t0, t_bound)

@@ -515,6 +515,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
         else if (L.max_steps > 0 && nacc >= L.max_steps) status = B200DAE_ST_MAX_STEPS;
     }
 
+    if (L.out.bad_input != nullptr && status == B200DAE_ST_NONFINITE && nacc == 0) *L.out.bad_input = 1;
 #pragma unroll U
     for (int j = 0; j < N; ++j) {
         L.out.y_final[io_index(L.io_aos, ld, N, j, inst)] = y[j];

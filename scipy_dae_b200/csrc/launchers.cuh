@@ -144,6 +144,19 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
             done = true;
         }
     }
+    if constexpr (Regime<P::N>::kReg && S == 3 && Tn::kSharedCold) {
+        // instance-major I/O (io_layout = 1, zero-copy launches on pinned host arrays): the lean kernel with
+        // its inputs and results staged through shared memory, so that PCIe sees contiguous runs
+        if (!done && lean && L.io_aos && L.newton_max_iter <= 8) {
+            auto kern = radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, false, 3, true>;
+            if (Tn::kDynSmem > 0) {
+                static bool attr_io = false;
+                if (!attr_io) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem); attr_io = true; }
+            }
+            kern<<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
+            done = true;
+        }
+    }
     if constexpr (Regime<P::N>::kReg && S == 3) {
         // the headline kernel with a 3-bit exponent in the Newton rate test (newton_max_iter <= 8: the default 7)
         if (!done && lean && L.newton_max_iter <= 8) {

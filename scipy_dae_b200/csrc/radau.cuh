@@ -123,35 +123,72 @@ __device__ __forceinline__ double predict_factor(double h_abs, double h_abs_old,
 // and without it, so that dense output at t_eval does not pull in the other option paths).
 // kPowBits: bits of the exponent newton_max_iter - k in the rate test (3 when newton_max_iter <= 8,
 // the launcher's choice for the default 7: two squarings and two select-multiplies less per iteration).
+// kIoStage: the instance-major I/O of the lean kernel staged through shared memory (see below); its own
+// instantiation, so that the default launches carry none of it (the staging indices cost 0.045 ms of the
+// 10.7 ms headline launch when compiled into the same kernel).
 template <class P, int S, int kThreads, int kMinBlocks, bool kSharedCold, bool kLean, bool kJac = false,
-          bool kEval = !kLean, int kPowBits = 5>
+          bool kEval = !kLean, int kPowBits = 5, bool kIoStage = false>
 __global__ void B200DAE_RADAU_BOUNDS(kThreads, kMinBlocks)
 radau_kernel(const __grid_constant__ RadauLaunch L) {
     constexpr int N = P::N, NP = P::NP, NCS = S / 2;
     constexpr int U = Regime<N>::kUnroll;
-    const int64_t inst = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (inst >= L.N) return;
+    // Instance-major I/O (io_aos) of the lean kernel goes THROUGH SHARED MEMORY: the block's inputs are
+    // one contiguous run of kThreads * n doubles per array, loaded with consecutive lanes on consecutive
+    // words and picked up per thread from shared memory (results the other way round).  Per-thread
+    // accesses of 8 bytes at a 24-byte stride are fine in HBM but not over PCIe, which is where this
+    // layout matters (zero-copy launches on pinned host arrays): 11.48 ms per 2^20 Robertson instances
+    // with direct indexing, 10.7x ms staged (SoA host arrays: 10.74 ms).  Threads past the end of the
+    // ensemble stay alive for the warp barriers and store nothing.
+    constexpr bool kStage = kIoStage && kSharedCold && kLean && !kEval;
+    const int64_t inst0 = (int64_t)blockIdx.x * kThreads;
+    const bool staged = kStage && L.io_aos != 0;
+    if (!staged && inst0 + threadIdx.x >= L.N) return;
+    const bool valid = inst0 + threadIdx.x < L.N;
+    const int64_t inst = valid ? inst0 + threadIdx.x : L.N - 1;
     const int64_t ld = L.ld;
     const b200dae_radau_tables& tb = L.tb;
-
-    // ---- per-instance state -------------------------------------------------------------
-    double p[NP > 0 ? NP : 1], y[N], yp[N];
-#pragma unroll U
-    for (int j = 0; j < NP; ++j) p[j] = L.params[io_index(L.io_aos, ld, NP, j, inst)];
-#pragma unroll U
-    for (int j = 0; j < N; ++j) { y[j] = L.y0[io_index(L.io_aos, ld, N, j, inst)]; yp[j] = L.yp0[io_index(L.io_aos, ld, N, j, inst)]; }
 
     // "Cold" per-instance state (touched once per step or per LU, not per Newton iteration):
     // Jacobians, FD step factors, dense-output coefficients, complex LU factors.  With
     // kSharedCold they live in shared memory [element][thread], which frees ~100 registers and
     // lets a third warp per scheduler hide the 8.7-cycle DFMA latency.
     constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
+    static_assert(!kStage || kCold >= 2 * N + NP + 4, "the staging of instance-major I/O reuses the warp's cold-state slots");
     // up to 48 KB the block's cold state is a static array; beyond that (4 < n <= B200DAE_REG_MAXN:
     // 32-thread blocks) it is the launch's dynamic shared memory
     constexpr bool kDynCold = kSharedCold && ((size_t)kCold * kThreads * sizeof(double) > 48 * 1024);
     extern __shared__ __align__(16) double s_cold_dyn[];
     __shared__ double s_cold_static[(kSharedCold && !kDynCold) ? kCold * kThreads : 1];
     double* const s_cold = kDynCold ? s_cold_dyn : s_cold_static;
+
+    // ---- per-instance state -------------------------------------------------------------
+    double p[NP > 0 ? NP : 1], y[N], yp[N];
+    // staging area of a WARP: its own 32 slots of the first cold-state elements (the cold block is laid
+    // out [element][thread]), so that only the warp's own lanes ever touch it: __syncwarp() suffices and a
+    // warp retires without waiting for the other warp of its block
+    const int wbase = (int)(threadIdx.x & ~31u);
+    const int64_t winst0 = inst0 + wbase;                  // first instance of this warp
+    const int wn = (int)((L.N - winst0 < 32) ? ((L.N - winst0 > 0) ? (L.N - winst0) : 0) : 32);
+    auto stage = [&](int i) -> double& { return s_cold[(i >> 5) * kThreads + wbase + (i & 31)]; };
+    const int wl = (int)(threadIdx.x & 31u);
+    if (staged) {
+        constexpr int oP = 0, oY = 32 * NP, oYp = oY + 32 * N;
+        for (int e = wl; e < wn * NP; e += 32) stage(oP + e) = L.params[winst0 * NP + e];
+        for (int e = wl; e < wn * N; e += 32) { stage(oY + e) = L.y0[winst0 * N + e]; stage(oYp + e) = L.yp0[winst0 * N + e]; }
+        __syncwarp();
+        const int me = valid ? wl : 0;
+#pragma unroll U
+        for (int j = 0; j < NP; ++j) p[j] = stage(oP + me * NP + j);
+#pragma unroll U
+        for (int j = 0; j < N; ++j) { y[j] = stage(oY + me * N + j); yp[j] = stage(oYp + me * N + j); }
+        __syncwarp();                                      // the slots are the cold state from here on
+    } else {
+#pragma unroll U
+        for (int j = 0; j < NP; ++j) p[j] = L.params[io_index(L.io_aos, ld, NP, j, inst)];
+#pragma unroll U
+        for (int j = 0; j < N; ++j) { y[j] = L.y0[io_index(L.io_aos, ld, N, j, inst)]; yp[j] = L.yp0[io_index(L.io_aos, ld, N, j, inst)]; }
+    }
+
     double r_cold[kSharedCold ? 1 : kCold];
     using V = Vec<kSharedCold, kThreads>;
     const V Jy{kSharedCold ? (s_cold + threadIdx.x) : r_cold};
@@ -197,7 +234,7 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     bool current_jac = true;         // radau.py:460 (quirk 7)
     bool lu_valid = false, step_begin = true, retry = false;
     int32_t nfev = 0, njev = 0, nlu = 0, nsolve = 0, nacc = 0, nrej = 0, nfail = 0, niter = 0;
-    int32_t status = B200DAE_ST_RUNNING;
+    int32_t status = valid ? B200DAE_ST_RUNNING : B200DAE_ST_FINISHED;   // threads past the end (staged I/O only) skip the loop
     int64_t ie = 0;                  // next t_eval index
     int32_t nst = 0;                 // rows written to the step trace
     const int newton_max_iter = L.newton_max_iter;
@@ -751,6 +788,34 @@ radau_kernel(const __grid_constant__ RadauLaunch L) {
     }
 
     // ---- results ----------------------------------------------------------------------------
+    if (staged) {
+        __syncwarp();                                      // every lane of the warp is done with its cold state
+        constexpr int oY = 0, oYp = 32 * N, oC = 64 * N;   // counters: 8 ints = 4 doubles per lane
+        if (L.out.bad_input != nullptr && status == B200DAE_ST_NONFINITE && nacc == 0) *L.out.bad_input = 1;
+#pragma unroll U
+        for (int j = 0; j < N; ++j) { stage(oY + wl * N + j) = y[j]; stage(oYp + wl * N + j) = yp[j]; }
+        stage(oC + wl * 4 + 0) = __hiloint2double(njev, nfev);
+        stage(oC + wl * 4 + 1) = __hiloint2double(nsolve, nlu);
+        stage(oC + wl * 4 + 2) = __hiloint2double(nrej, nacc);
+        stage(oC + wl * 4 + 3) = __hiloint2double(niter, nfail);
+        __syncwarp();
+        for (int e = wl; e < wn * N; e += 32) {
+            L.out.y_final[winst0 * N + e] = stage(oY + e);
+            if (L.out.yp_final) L.out.yp_final[winst0 * N + e] = stage(oYp + e);
+        }
+        if (L.out.counters) {
+            double* c2 = reinterpret_cast<double*>(L.out.counters + winst0 * 8);      // [instance][8] ints, 32-byte rows
+            for (int e = wl; e < wn * 4; e += 32) c2[e] = stage(oC + e);
+        }
+        if (valid) {
+            L.out.t_final[inst] = t;
+            L.out.status[inst] = status;
+            if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
+            if (L.out.n_steps) L.out.n_steps[inst] = nst;
+        }
+        return;
+    }
+    if (L.out.bad_input != nullptr && status == B200DAE_ST_NONFINITE && nacc == 0) *L.out.bad_input = 1;
 #pragma unroll U
     for (int j = 0; j < N; ++j) {
         L.out.y_final[io_index(L.io_aos, ld, N, j, inst)] = y[j];

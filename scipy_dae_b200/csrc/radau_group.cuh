@@ -707,6 +707,7 @@ radau_group_kernel(const __grid_constant__ RadauLaunch L) {
     if (lane == 0) {
         L.out.t_final[inst] = t;
         L.out.status[inst] = status;
+        if (L.out.bad_input != nullptr && status == B200DAE_ST_NONFINITE && nacc == 0) *L.out.bad_input = 1;
         if (L.out.n_eval_valid) L.out.n_eval_valid[inst] = (int32_t)ie;
         if (L.out.n_steps) L.out.n_steps[inst] = nst;
         if (!kLean) for (int k = 0; k < L.ev.spec.n_events; ++k) L.ev.n_found[(int64_t)k * ld + inst] = evs.found[k];

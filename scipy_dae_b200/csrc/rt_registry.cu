@@ -445,14 +445,14 @@ int rt_launch_radau(int idx, const RadauLaunch& L, cudaStream_t st, bool do_laun
         const bool lean_opts = L.newton_iter_embedded == 1 && L.cew == 0.0 && L.out.t_steps == nullptr &&
                                L.ev.spec.n_events == 0;
         const bool lean = lean_opts && L.out.t_eval == nullptr;
-        bool kl = lean, kj = false, ke = false;
+        bool kl = lean, kj = false, ke = false, kio = false;
         int bits = 5;
         if (L.analytic_jac) kj = true;
         else if (S == 3 && lean_opts && !lean) { kl = true; ke = true; }
-        else if (S == 3 && lean && L.newton_max_iter <= 8) bits = 3;
-        snprintf(key, sizeof(key), "radau s%d l%d j%d e%d b%d", S, kl, kj, ke, bits);
+        else if (S == 3 && lean && L.newton_max_iter <= 8) { bits = 3; kio = L.io_aos != 0; }
+        snprintf(key, sizeof(key), "radau s%d l%d j%d e%d b%d io%d", S, kl, kj, ke, bits, kio);
         snprintf(kern, sizeof(kern), "b200dae::radau_kernel<P, %d, RadauTune<P, %d>::kThreads, RadauTune<P, %d>::kMinBlocks, "
-                 "RadauTune<P, %d>::kSharedCold, %s, %s, %s, %d>", S, S, S, S, tf(kl), tf(kj), tf(ke), bits);
+                 "RadauTune<P, %d>::kSharedCold, %s, %s, %s, %d, %s>", S, S, S, S, tf(kl), tf(kj), tf(ke), bits, tf(kio));
         snprintf(shape, sizeof(shape), "1, RadauTune<P, %d>::kThreads, RadauTune<P, %d>::kMinBlocks, (long long)RadauTune<P, %d>::kDynSmem", S, S, S);
     }
     RtKernel* k = nullptr;

@@ -74,6 +74,43 @@ def main():
         st = b["st"] if where == "host" else b["st"].cpu()
         res[where] = dict(ms_min=min(ts), ms_med=float(np.median(ts)), wall_ms_min=min(wall), finished=int((st == 0).sum()),
                           y_checksum=float((b["y"] if where == "host" else b["y"].cpu()).double().sum()))
+    # instance-major pinned host arrays (the shapes of the reference's API) through io_layout = 1
+    hp, hy, hyp = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (params, y0, yp0))
+    from scipy_dae_b200 import alloc_host_result, solve_dae_batched_host
+    ob = alloc_host_result(N, n)
+    out = _lib.Outputs()
+    out.y_final, out.yp_final, out.t_final = ob.y_final.data_ptr(), ob.yp_final.data_ptr(), ob.t_final.data_ptr()
+    out.status, out.counters = ob.status.data_ptr(), ob.counters.data_ptr()
+    ro.io_layout = 1
+
+    def launch_aos():
+        _lib.check(L.b200dae_solve_radau(pid, N, N, hy.data_ptr(), hyp.data_ptr(), hp.data_ptr(), 0.0, 1e7, atol,
+                                         ctypes.byref(ro), ctypes.byref(tb), ctypes.byref(out), ctypes.c_void_p(stream.cuda_stream)))
+    for _ in range(2):
+        launch_aos()
+    torch.cuda.synchronize()
+    ts, wall = [], []
+    for _ in range(5):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(); launch_aos(); e1.record()
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e3)
+        ts.append(e0.elapsed_time(e1))
+    res["host_aos_cabi"] = dict(ms_min=min(ts), wall_ms_min=min(wall), finished=int((ob.status == 0).sum()),
+                                y_checksum=float(ob.y_final.double().sum()))
+    for cf in (True, False):
+        wall = []
+        for _ in range(6):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            solve_dae_batched_host("robertson", (0.0, 1e7), hy, hyp, hp, rtol=1e-6, atol=1e-6, out=ob, zero_copy=True,
+                                   check_finite=cf)
+            wall.append((time.perf_counter() - t0) * 1e3)
+        res["host_aos_api_check_finite_%s" % cf] = dict(wall_ms_min=min(wall[1:]), wall_ms_med=float(np.median(wall[1:])))
     print(json.dumps(res))
 
 
