@@ -129,7 +129,9 @@ __device__ __noinline__ void change_D(double* __restrict__ D, int order, double 
         for (int c = 0; c < N; ++c) acc[c] = 0.0;
 #pragma unroll
         for (int l = 0; l < kBdfQ; ++l) {
-            if (l < q) {
+            // U = compute_R(order, 1) is upper triangular (its entry (l, i) carries the factor l - 1 - i + ... = 0
+            // for l > i, exactly), so rows l > i add exact zeros in the reference's product: skipped
+            if (l <= i) {
                 const double u = Umat[l * kBdfQ + i];
 #pragma unroll
                 for (int c = 0; c < N; ++c) acc[c] = fma(u, E[l * N + c], acc[c]);

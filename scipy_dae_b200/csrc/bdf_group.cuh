@@ -61,7 +61,7 @@ static __device__ __noinline__ void change_D_lane(double* __restrict__ D, int or
         double acc = 0.0;
 #pragma unroll
         for (int l = 0; l < kBdfQ; ++l)
-            if (l < q) acc = fma(Umat[l * kBdfQ + i], El[l], acc);
+            if (l <= i && l < q) acc = fma(Umat[l * kBdfQ + i], El[l], acc);   // U is upper triangular: rows l > i add exact zeros
         if (i < q) D[i] = acc;
     }
 }
