@@ -16,6 +16,9 @@
 #ifndef B200DAE_REG_THREADS
 #define B200DAE_REG_THREADS 64
 #endif
+#ifndef B200DAE_BIG_THREADS
+#define B200DAE_BIG_THREADS 64
+#endif
 #ifndef B200DAE_GROUP_MINBLOCKS
 #define B200DAE_GROUP_MINBLOCKS(G) ((G) == 32 ? 1 : 6)
 #endif
@@ -25,7 +28,10 @@ namespace b200dae {
 // threads per block: register-regime kernels keep ~255 registers per thread live, so 128
 // threads x 2 blocks fill an SM's register file; the local-memory regime prefers fewer
 // threads per SM so that its per-thread arrays stay L1-resident.
-template <class P> struct BlockSize { static constexpr int value = Regime<P::N>::kReg ? 128 : 64; };
+#ifndef B200DAE_BDF_BIG_THREADS
+#define B200DAE_BDF_BIG_THREADS 128
+#endif
+template <class P> struct BlockSize { static constexpr int value = Regime<P::N>::kReg ? (P::N > 4 ? B200DAE_BDF_BIG_THREADS : 128) : 64; };
 
 // Launch shape of the Radau kernel per (problem size, stages).
 //   register regime (n <= 4): 64-thread blocks, the cold per-instance state in shared memory
@@ -38,7 +44,7 @@ struct RadauTune {
     static constexpr int N = P::N, NCS = S / 2;
     static constexpr bool kReg = Regime<N>::kReg;
     static constexpr bool kBig = kReg && N > 4;         // unrolled thread regime beyond n = 4 (B200DAE_REG_MAXN)
-    static constexpr int kThreads = kReg ? (kBig ? 32 : B200DAE_REG_THREADS) : 64;
+    static constexpr int kThreads = kReg ? (kBig ? B200DAE_BIG_THREADS : B200DAE_REG_THREADS) : 64;
     static constexpr int kCold = 2 * N * N + 2 * N + N * S + 2 * NCS * N * N;
     static constexpr bool kSharedCold = kReg && (kBig || kCold * kThreads * 8 <= 48 * 1024);
     static constexpr size_t kDynSmem = (kSharedCold && (size_t)kCold * kThreads * 8 > 48 * 1024) ? (size_t)kCold * kThreads * 8 : 0;

@@ -11,6 +11,10 @@
 #include "../../include/b200dae.h"
 #include "launch_shapes.cuh"
 
+#ifndef B200DAE_BIG_CARVEOUT_DEFAULT
+#define B200DAE_BIG_CARVEOUT_DEFAULT 40     // percent of the SM's 228 KB; 0: leave the carve-out to the driver
+#endif
+
 namespace b200dae {
 
 extern std::atomic<int64_t> g_launches;
@@ -157,6 +161,20 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
             done = true;
         }
     }
+    if constexpr (Regime<P::N>::kReg && S == 3 && Tn::kBig) {
+        // unrolled thread regime beyond n = 4: the kernel lives on its spills (1.5 KB per thread), which hit L1
+        // only if the shared-memory carve-out leaves room for them; fewer resident blocks with a larger L1 win
+        // (B200DAE_BIG_CARVEOUT = percent of the 228 KB given to shared memory; measured default below)
+        static bool carve_set = false;
+        if (!carve_set) {
+            const char* env = getenv("B200DAE_BIG_CARVEOUT");
+            const int pct = env ? atoi(env) : B200DAE_BIG_CARVEOUT_DEFAULT;
+            if (pct > 0)
+                cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, false, 3>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            carve_set = true;
+        }
+    }
     if constexpr (Regime<P::N>::kReg && S == 3) {
         // the headline kernel with a 3-bit exponent in the Newton rate test (newton_max_iter <= 8: the default 7)
         if (!done && lean && L.newton_max_iter <= 8) {
@@ -227,7 +245,24 @@ static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
         if (L.analytic_jac) { bdf_kernel<P, T, true, false, SC><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L); done = true; }
     }
     if constexpr (Regime<P::N>::kReg) {
-        if (!done && lean) { bdf_kernel<P, T, false, true, SC><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L); done = true; }
+        if (!done && lean) {
+            // B200DAE_BDF_PAD_SMEM (experiments): unused dynamic shared memory per block, which caps the resident
+            // blocks per SM so that the spilled difference arrays of the unrolled n > 4 kernel fit L1
+            static const size_t pad = getenv("B200DAE_BDF_PAD_SMEM") ? (size_t)atol(getenv("B200DAE_BDF_PAD_SMEM")) : 0;
+            size_t dyn = Tn::kDynSmem;
+            if (pad > dyn && P::N > 4) {
+                static bool pad_set = false;
+                if (!pad_set) {
+                    cudaFuncSetAttribute(bdf_kernel<P, T, false, true, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+                    if (getenv("B200DAE_BDF_CARVEOUT"))
+                        cudaFuncSetAttribute(bdf_kernel<P, T, false, true, SC>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("B200DAE_BDF_CARVEOUT")));
+                    pad_set = true;
+                }
+                dyn = pad;
+            }
+            bdf_kernel<P, T, false, true, SC><<<(unsigned)blocks, T, dyn, st>>>(L);
+            done = true;
+        }
     }
     if (!done) bdf_kernel<P, T, false, false, SC><<<(unsigned)blocks, T, Tn::kDynSmem, st>>>(L);
     g_launches.fetch_add(1);
