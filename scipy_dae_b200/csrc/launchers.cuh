@@ -128,6 +128,10 @@ static int launch_radau(const RadauLaunch& L, cudaStream_t st) {
         if (!attr_set) {
             cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
             cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+            if constexpr (kJacOk && Regime<P::N>::kReg) {
+                cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+                cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
+            }
             if constexpr (Regime<P::N>::kReg && S == 3) {
                 cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
                 cudaFuncSetAttribute(radau_kernel<P, S, T, Tn::kMinBlocks, Tn::kSharedCold, true, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tn::kDynSmem);
