@@ -254,6 +254,13 @@ static int launch_bdf(const BdfLaunch& L, cudaStream_t st) {
             // blocks per SM so that the spilled difference arrays of the unrolled n > 4 kernel fit L1
             static const size_t pad = getenv("B200DAE_BDF_PAD_SMEM") ? (size_t)atol(getenv("B200DAE_BDF_PAD_SMEM")) : 0;
             size_t dyn = Tn::kDynSmem;
+            if (P::N > 4 && getenv("B200DAE_BDF_CARVEOUT")) {
+                static bool carve_set = false;
+                if (!carve_set) {
+                    cudaFuncSetAttribute(bdf_kernel<P, T, false, true, SC>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("B200DAE_BDF_CARVEOUT")));
+                    carve_set = true;
+                }
+            }
             if (pad > dyn && P::N > 4) {
                 static bool pad_set = false;
                 if (!pad_set) {
