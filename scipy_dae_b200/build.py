@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for _, log in results:
             if log:
                 print(log)
-    subprocess.run([nvcc, "-shared", "-o", LIB_PATH, *[o for o, _ in results]], check=True)
+    subprocess.run([nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB_PATH, *[o for o, _ in results]], check=True)
     return LIB_PATH
 
 
