@@ -215,6 +215,7 @@ struct RtKernel {
     std::vector<char> cubin;
     int G = 1, T = 0, MB = 0;
     long long smem = 0;
+    int carveout = 0;                                     // preferred shared-memory carve-out in percent (0: driver's choice)
     CUfunction fn = nullptr;                              // null until loaded on a device
 };
 
@@ -354,6 +355,7 @@ int load_kernel(RtKernel& k, std::string& err) {
         rc = d.set_attr(k.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)k.smem);
         if (rc != CUDA_SUCCESS) { k.fn = nullptr; return msg(rc, "cuFuncSetAttribute(max dynamic shared memory)"); }
     }
+    if (k.carveout > 0) (void)d.set_attr(k.fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, k.carveout);   // a hint
     return 0;
 }
 
@@ -458,6 +460,8 @@ int rt_launch_radau(int idx, const RadauLaunch& L, cudaStream_t st, bool do_laun
     RtKernel* k = nullptr;
     int rc = get_kernel(p, key, kern, shape, &k, err);
     if (rc) return rc;
+    // the unrolled thread regime beyond n = 4 wants ONE resident block per SM (launchers.cuh: B200DAE_BIG_CARVEOUT_DEFAULT)
+    if (p.n > 4 && p.n <= B200DAE_REG_MAXN && strstr(key, "b3") != nullptr && k->fn == nullptr) k->carveout = 40;
     if (!do_launch) return 0;
     RadauLaunch Lc = L;
     return launch(*k, L.N, &Lc, st, err);
