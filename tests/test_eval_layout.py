@@ -58,3 +58,24 @@ def test_negative_strides_are_rejected():
     rc = L.b200dae_solve_radau(pid, 1, 1, 8, 8, 8, 0.0, 1.0, atol, ctypes.byref(ro), ctypes.byref(tb),
                                ctypes.byref(out), None)
     assert rc == -1 and b"strides" in L.b200dae_last_error()
+
+
+def test_unknown_io_layout_is_rejected():
+    """b200dae_radau_opts.io_layout / b200dae_bdf_opts.io_layout: 0 ([n][ld]) or 1 (instance-major)."""
+    from scipy_dae_b200 import _lib
+    from scipy_dae_b200.constants import radau_tables_c
+    L = _lib.load()
+    pid, n, npar = _lib.problem_lookup("robertson")
+    out = _lib.Outputs()
+    out.y_final = out.t_final = out.status = 8          # never dereferenced: the call fails on validation
+    atol = (ctypes.c_double * n)(*([1e-6] * n))
+    ro = _lib.RadauOpts(rtol=1e-6, max_step=float("inf"), first_step=0.0, continuous_error_weight=0.0,
+                        jac_recompute_rate=1e-3, deadband_lo=1.0, deadband_hi=1.2, newton_max_iter=0,
+                        newton_iter_embedded=1, max_steps=0, analytic_jac=0, io_layout=2)
+    tb = radau_tables_c(3)
+    rc = L.b200dae_solve_radau(pid, 1, 1, 8, 8, 8, 0.0, 1.0, atol, ctypes.byref(ro), ctypes.byref(tb), ctypes.byref(out), None)
+    assert rc == -1 and b"io_layout" in L.b200dae_last_error()
+    bo = _lib.BdfOpts(rtol=1e-6, max_step=float("inf"), first_step=0.0, max_order=5, ndf_strategy=0, max_steps=0,
+                      analytic_jac=0, io_layout=7)
+    rc = L.b200dae_solve_bdf(pid, 1, 1, 8, 8, 8, 0.0, 1.0, atol, ctypes.byref(bo), ctypes.byref(out), None)
+    assert rc == -1 and b"io_layout" in L.b200dae_last_error()
