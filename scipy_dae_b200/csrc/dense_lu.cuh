@@ -30,6 +30,10 @@ struct Vec {
     __device__ __forceinline__ Vec operator+(int off) const { return Vec{p + (SH ? off * STRIDE : off)}; }
 };
 
+// 1 (default): LINPACK-style partial interchanges in the register regime, see lu_factor
+#ifndef B200DAE_LINPACK_SWAPS
+#define B200DAE_LINPACK_SWAPS 1
+#endif
 #ifndef B200DAE_REG_MAXN
 #define B200DAE_REG_MAXN 6
 #endif
@@ -63,11 +67,17 @@ __device__ __forceinline__ void lu_factor(double* __restrict__ a, int* __restric
         if (kFirstDone && k == 0) {
             // nothing to move
         } else if (REG) {
+            // register regime: an interchange is a select per entry, so only the part of the rows that is
+            // still to be eliminated moves (columns >= k, LINPACK's dgefa layout: the multipliers of the
+            // earlier columns stay where they were computed and lu_solve interleaves the interchanges of
+            // the right-hand side with the column sweeps, dgesl).  Same multipliers applied to the same
+            // values in the same order as with LAPACK's full-row interchanges: bit-identical solutions,
+            // 22 % fewer selects per factorisation at n = 6.
 #pragma unroll U
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = (p == i);
 #pragma unroll U
-                for (int j = 0; j < N; ++j) {
+                for (int j = B200DAE_LINPACK_SWAPS ? k : 0; j < N; ++j) {
                     const double x = a[k * N + j], z = a[i * N + j];
                     a[k * N + j] = sw ? z : x;
                     a[i * N + j] = sw ? x : z;
@@ -101,6 +111,21 @@ __device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const in
     if constexpr (REG) {
         // (`#pragma unroll` without a count: with the count form ptxas once kept the inner loop of the
         // complex twin rolled, which put its right-hand side into local memory)
+#if B200DAE_LINPACK_SWAPS
+#pragma unroll
+        for (int k = 0; k < N; ++k) {                  // dgesl: interchange k, then the column sweep of step k
+            const int p = piv[k];
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const bool sw = (p == i);
+                const double x = b[k], z = b[i];
+                b[k] = sw ? z : x;
+                b[i] = sw ? x : z;
+            }
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) b[i] = fma(-lu[i * N + k], b[k], b[i]);
+        }
+#else
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             const int p = piv[k];
@@ -119,6 +144,7 @@ __device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const in
             for (int j = 0; j < i; ++j) acc = fma(-lu[i * N + j], b[j], acc);
             b[i] = acc;
         }
+#endif
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
             double acc = b[i];
@@ -201,7 +227,7 @@ __device__ __forceinline__ void zlu_factor(MR ar, MI ai, int* __restrict__ piv) 
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = (p == i);
 #pragma unroll U
-                for (int j = 0; j < N; ++j) {
+                for (int j = B200DAE_LINPACK_SWAPS ? k : 0; j < N; ++j) {      // see lu_factor
                     double x = ar[k * N + j], z = ar[i * N + j];
                     ar[k * N + j] = sw ? z : x;
                     ar[i * N + j] = sw ? x : z;
@@ -244,6 +270,27 @@ __device__ __forceinline__ void zlu_solve(MR ar, MI ai, const int* __restrict__ 
                                           double* __restrict__ br, double* __restrict__ bi) {
     constexpr bool REG = Regime<N>::kReg;
     if constexpr (REG) {
+#if B200DAE_LINPACK_SWAPS
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int p = piv[k];
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const bool sw = (p == i);
+                double x = br[k], z = br[i];
+                br[k] = sw ? z : x; br[i] = sw ? x : z;
+                x = bi[k]; z = bi[i];
+                bi[k] = sw ? z : x; bi[i] = sw ? x : z;
+            }
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const double lr = ar[i * N + k], li = ai[i * N + k];
+                const double sr = br[i], si = bi[i];
+                br[i] = fma(li, bi[k], fma(-lr, br[k], sr));
+                bi[i] = fma(-li, br[k], fma(-lr, bi[k], si));
+            }
+        }
+#else
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             const int p = piv[k];
@@ -267,6 +314,7 @@ __device__ __forceinline__ void zlu_solve(MR ar, MI ai, const int* __restrict__ 
             }
             br[i] = sr; bi[i] = si;
         }
+#endif
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
             double sr = br[i], si = bi[i];
