@@ -30,10 +30,14 @@ struct Vec {
     __device__ __forceinline__ Vec operator+(int off) const { return Vec{p + (SH ? off * STRIDE : off)}; }
 };
 
-// 1 (default): LINPACK-style partial interchanges in the register regime, see lu_factor
+// 1 (default): LINPACK-style partial interchanges in the unrolled regime beyond n = 4, see lu_factor.  Measured
+// on B200: Akzo Nobel (n = 6) BDF 6.12 -> 6.35 M, Radau 8.62 -> 9.13 M solves/s; for n = 3 the interleaved
+// interchange / sweep chain of the solve lengthens the critical path of the headline kernel (10.70 -> 11.82 ms),
+// so n <= 4 keeps LAPACK's full-row interchanges.
 #ifndef B200DAE_LINPACK_SWAPS
 #define B200DAE_LINPACK_SWAPS 1
 #endif
+template <int N> struct LinpackSwaps { static constexpr bool value = (B200DAE_LINPACK_SWAPS != 0) && N > 4; };
 #ifndef B200DAE_REG_MAXN
 #define B200DAE_REG_MAXN 6
 #endif
@@ -77,7 +81,7 @@ __device__ __forceinline__ void lu_factor(double* __restrict__ a, int* __restric
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = (p == i);
 #pragma unroll U
-                for (int j = B200DAE_LINPACK_SWAPS ? k : 0; j < N; ++j) {
+                for (int j = LinpackSwaps<N>::value ? k : 0; j < N; ++j) {
                     const double x = a[k * N + j], z = a[i * N + j];
                     a[k * N + j] = sw ? z : x;
                     a[i * N + j] = sw ? x : z;
@@ -111,7 +115,7 @@ __device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const in
     if constexpr (REG) {
         // (`#pragma unroll` without a count: with the count form ptxas once kept the inner loop of the
         // complex twin rolled, which put its right-hand side into local memory)
-#if B200DAE_LINPACK_SWAPS
+        if constexpr (LinpackSwaps<N>::value) {
 #pragma unroll
         for (int k = 0; k < N; ++k) {                  // dgesl: interchange k, then the column sweep of step k
             const int p = piv[k];
@@ -125,7 +129,7 @@ __device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const in
 #pragma unroll
             for (int i = k + 1; i < N; ++i) b[i] = fma(-lu[i * N + k], b[k], b[i]);
         }
-#else
+        } else {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             const int p = piv[k];
@@ -144,7 +148,7 @@ __device__ __forceinline__ void lu_solve(const double* __restrict__ lu, const in
             for (int j = 0; j < i; ++j) acc = fma(-lu[i * N + j], b[j], acc);
             b[i] = acc;
         }
-#endif
+        }
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
             double acc = b[i];
@@ -227,7 +231,7 @@ __device__ __forceinline__ void zlu_factor(MR ar, MI ai, int* __restrict__ piv) 
             for (int i = k + 1; i < N; ++i) {
                 const bool sw = (p == i);
 #pragma unroll U
-                for (int j = B200DAE_LINPACK_SWAPS ? k : 0; j < N; ++j) {      // see lu_factor
+                for (int j = LinpackSwaps<N>::value ? k : 0; j < N; ++j) {      // see lu_factor
                     double x = ar[k * N + j], z = ar[i * N + j];
                     ar[k * N + j] = sw ? z : x;
                     ar[i * N + j] = sw ? x : z;
@@ -270,7 +274,7 @@ __device__ __forceinline__ void zlu_solve(MR ar, MI ai, const int* __restrict__ 
                                           double* __restrict__ br, double* __restrict__ bi) {
     constexpr bool REG = Regime<N>::kReg;
     if constexpr (REG) {
-#if B200DAE_LINPACK_SWAPS
+        if constexpr (LinpackSwaps<N>::value) {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             const int p = piv[k];
@@ -290,7 +294,7 @@ __device__ __forceinline__ void zlu_solve(MR ar, MI ai, const int* __restrict__ 
                 bi[i] = fma(-li, br[k], fma(-lr, bi[k], si));
             }
         }
-#else
+        } else {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             const int p = piv[k];
@@ -314,7 +318,7 @@ __device__ __forceinline__ void zlu_solve(MR ar, MI ai, const int* __restrict__ 
             }
             br[i] = sr; bi[i] = si;
         }
-#endif
+        }
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
             double sr = br[i], si = bi[i];
