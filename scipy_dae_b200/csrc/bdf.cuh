@@ -15,6 +15,11 @@
 #include "fd_jacobian.cuh"
 #include "radau.cuh"   // finite_d, powi
 
+// 1 (default): rolled FD-Jacobian column loop in the thread BDF kernel beyond n = 4 (fd_jacobian.cuh)
+#ifndef B200DAE_BDF_FD_ROLL
+#define B200DAE_BDF_FD_ROLL 1
+#endif
+
 namespace b200dae {
 
 constexpr int kBdfNewtonMaxIter = 4;     // bdf.py:9
@@ -225,7 +230,7 @@ bdf_kernel(const __grid_constant__ BdfLaunch L) {
         // ---- phase J: FD Jacobian at the committed (t, y, yp) (base.py:297, bdf.py:330) ------
         if (need_jac) {
             if constexpr (kJac) analytic_jacobian<P, N>(t, y, yp, p, Jy, Jyp);
-            else fd_jacobian<P, V>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
+            else fd_jacobian<P, V, V, (B200DAE_BDF_FD_ROLL != 0)>(t, y, yp, p, L.thr, factor_y, factor_yp, Jy, Jyp);
             ++njev;
             need_jac = false;
         }

@@ -220,7 +220,7 @@ __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y,
 // Jacobian the same launch takes 10.9 ms); the second attempt is not rare either: a column of
 // Jyp that belongs to an algebraic variable has diff = 0 and always takes it (16.4 % of the
 // Robertson columns, counted with the CPU oracle).
-template <class P, class V, class VJ = V>
+template <class P, class V, class VJ = V, bool kRollColumns = false>
 __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, double* __restrict__ yp,
                                             const double* __restrict__ p, const double* __restrict__ thr,
                                             V factor_y, V factor_yp, VJ Jy, VJ Jyp) {
@@ -228,6 +228,17 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
     constexpr int U = Regime<N>::kUnroll;
     double f[N];
     P::eval(t, y, yp, p, f);
+    // kRollColumns (the thread BDF kernel, n > 4): the columns run through ONE rolled loop body instead of 2n
+    // inlined residual evaluations.  The unrolled n = 6 BDF kernel is 104 KB of code with 8 resident warps in
+    // different phases and stalls on instruction fetch (ncu: stall_no_inst 34 %); rolled it is 67 KB and Akzo
+    // Nobel BDF goes from 6.2 M to 7.3 M solves/s with identical work counters.  The Radau kernel of the same
+    // regime runs 2 warps per SM and is latency-bound instead: rolled it LOSES 19 % (9.1 -> 7.4 M), so it
+    // keeps the batched form.
+    constexpr bool kRollBig = kRollColumns && N > 4;
+    constexpr int UF = kRollBig ? 1 : U;
+    if constexpr (kRollBig) {
+        // falls through to the column loop below
+    } else
     if constexpr (Regime<N>::kReg && B200DAE_FD_BATCH == 2) {
         fd_batch<P, V, VJ, 0, 2 * N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
         return;
@@ -236,13 +247,13 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
         fd_batch<P, V, VJ, N, 2 * N>(t, y, yp, p, thr, f, factor_y, factor_yp, Jy, Jyp);
         return;
     }
-#pragma unroll U
+#pragma unroll UF
     for (int which = 0; which < 2; ++which) {
         const bool wrt_yp = (which == 1);
         const double* x = wrt_yp ? yp : y;
         V factor = wrt_yp ? factor_yp : factor_y;
         VJ J = wrt_yp ? Jyp : Jy;
-#pragma unroll U
+#pragma unroll UF
         for (int i = 0; i < N; ++i) {
             const double xi = x[i];
             const double f_sign = (f[i] >= 0.0) ? 1.0 : -1.0;
