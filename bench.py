@@ -68,8 +68,10 @@ def parse_args():
                     help="host-facing call reported as e2e: the chunked H2D / kernel / D2H pipeline (default) or ONE "
                          "launch working on the pinned host arrays in place over PCIe; both are timed every run "
                          "(e2e_pipeline, e2e_zero_copy)")
-    ap.add_argument("--strong-pipeline", action="store_true",
-                    help="strong scaling through the chunked host pipeline instead of the zero-copy launch")
+    ap.add_argument("--strong-mode", default="auto", choices=["auto", "zero_copy", "pipeline"],
+                    help="host path of the strong-scaling job: zero-copy launches, the chunked pipeline, or auto = "
+                         "zero-copy up to 4 GPUs (measured 5.93 vs 6.15 ms at 2 GPUs) and the pipeline at 8, where "
+                         "eight GPUs reading and writing host memory in small transactions contend (2.57 vs 2.22 ms)")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="pipeline chunks of the host-facing call")
     ap.add_argument("--e2e-no-taper", action="store_true", help="equal chunk sizes in the host pipeline")
     ap.add_argument("--e2e-streams", type=int, default=3, help="compute streams of the host pipeline")
@@ -661,7 +663,7 @@ def main():
         shared = SharedHostResult(f"b200dae_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}", Nt, n)
         chunks = max(2, args.e2e_chunks // max(1, min(world, 4)))
 
-        strong_zc = not args.strong_pipeline
+        strong_zc = args.strong_mode == "zero_copy" or (args.strong_mode == "auto" and world <= 4)
 
         def strong_step():
             if strong_zc:       # every rank's launch writes its shard straight into the shared pinned arrays
