@@ -204,6 +204,10 @@ __device__ __forceinline__ void fd_batch(double t, const double* __restrict__ y,
     }
 }
 
+#ifndef B200DAE_FD_ROLL_MINN
+#define B200DAE_FD_ROLL_MINN 4      // rolled FD columns (thread BDF kernel) only beyond this system size
+                                     // (measured with 0: Robertson BDF 16.13 -> 16.44 M solves/s, +2 %; left at 4)
+#endif
 #ifndef B200DAE_FD_BATCH
 #define B200DAE_FD_BATCH 1
 #endif
@@ -234,7 +238,7 @@ __device__ __forceinline__ void fd_jacobian(double t, double* __restrict__ y, do
     // Nobel BDF goes from 6.2 M to 7.3 M solves/s with identical work counters.  The Radau kernel of the same
     // regime runs 2 warps per SM and is latency-bound instead: rolled it LOSES 19 % (9.1 -> 7.4 M), so it
     // keeps the batched form.
-    constexpr bool kRollBig = kRollColumns && N > 4;
+    constexpr bool kRollBig = kRollColumns && N > B200DAE_FD_ROLL_MINN;
     constexpr int UF = kRollBig ? 1 : U;
     if constexpr (kRollBig) {
         // falls through to the column loop below
