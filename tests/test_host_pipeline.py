@@ -81,3 +81,29 @@ def test_zero_copy_reports_non_finite_initial_values_like_the_reference():
     with pytest.raises(ValueError, match="must be finite"):          # base.py:33-37
         solve_dae_batched_host("robertson", (0.0, 1e3), hy, hyp, hp, rtol=1e-6, atol=1e-6,
                                out=alloc_host_result(64, 3), zero_copy=True)
+
+
+@pytest.mark.gpu
+def test_sharded_zero_copy_gather_matches_the_plain_solve():
+    """distributed.solve_dae_sharded(gather="host", zero_copy=True) at world size 1: the launch writes the
+    shard straight into the shared, page-locked result arrays (cudaHostRegister'ed /dev/shm mapping)."""
+    import os
+    import torch
+    from scipy_dae_b200 import solve_dae_batched, perturbed_params, initial_conditions
+    from scipy_dae_b200.distributed import SharedHostResult, solve_dae_sharded
+    N = 3000
+    params = perturbed_params("robertson", N, 0.1, seed=4)
+    y0, yp0 = initial_conditions("robertson", params)
+    hp, hy, hyp = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (params, y0, yp0))
+    shared = SharedHostResult(f"b200dae_test_{os.getpid()}", N, 3)
+    try:
+        res = solve_dae_sharded("robertson", (0.0, 1e7), hy, hyp, hp, method="Radau", rtol=1e-6, atol=1e-6,
+                                gather="host", host_result=shared, zero_copy=True)
+        ref = solve_dae_batched("robertson", (0.0, 1e7), y0, yp0, params, method="Radau", rtol=1e-6, atol=1e-6)
+        torch.cuda.synchronize()
+        ref = ref.numpy()
+        assert np.array_equal(res["status"].numpy(), ref.status)
+        assert np.array_equal(res["y_final"].numpy(), ref.y_final)
+        assert np.array_equal(res["n_accepted"].numpy(), ref.n_accepted)
+    finally:
+        shared.close()
